@@ -1,0 +1,206 @@
+/*
+ * piet_metal_b200.h -- C ABI of the B200-native drop-in for piet-metal's compute render path.
+ *
+ * Plain C types only (pointers, sizes, fixed-width integers) so that the reference's Rust host can
+ * bind it with an `extern "C"` block and its Objective-C host can include it directly; see
+ * INTEGRATION.md for the binding a maintainer would add.  Every function returns 0 (PM_OK) or a
+ * negative pm_status and never throws or aborts across the boundary.
+ *
+ * What each group replaces in the reference (paths relative to linebender/piet-metal):
+ *
+ *   feed      init_test_scene                 include/piet_metal.h:3, src/lib.rs:387-393
+ *             pm_encoder_*                    `Encoder` src/lib.rs:79-254
+ *             pm_scene_build                  make_tiger / make_cardioid / make_path_test
+ *                                             src/lib.rs:257-328 (+ the synthetic stress scenes)
+ *   renderer  pm_renderer_create/destroy      -[PietRenderer initWithMetalKitView:]
+ *                                             TestApp/PietRenderer.m:23-57
+ *             pm_renderer_resize              -[PietRenderer mtkView:drawableSizeWillChange:]
+ *                                             TestApp/PietRenderer.m:105-146
+ *             pm_renderer_set_scene           -[PietRenderer initScene] TestApp/PietRenderer.m:203-205
+ *                                             (the 16 MiB shared MTLBuffer, :52-53, is gone: the
+ *                                             renderer owns device memory sized to the scene)
+ *             pm_renderer_render              -[PietRenderer drawInMTKView:] compute passes,
+ *                                             TestApp/PietRenderer.m:59-88, i.e. tileKernel +
+ *                                             renderKernel of TestApp/PietRender.metal:160-566
+ *                                             and the solid-tile composite (:16-44)
+ *
+ * Threading: one renderer is driven by one host thread at a time (like an MTKView delegate).
+ * Ownership: the renderer owns all device memory; the caller owns every host buffer it passes in.
+ */
+#ifndef PIET_METAL_B200_H
+#define PIET_METAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include <sys/types.h> /* ssize_t, as in the reference header */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pm_status {
+    PM_OK = 0,
+    PM_ERR_INVALID_ARG = -1,
+    PM_ERR_NO_DEVICE = -2,      /* no CUDA device / driver: there is no CPU fallback */
+    PM_ERR_CUDA = -3,           /* a CUDA call failed; pm_last_error() has the text */
+    PM_ERR_SCENE_MALFORMED = -4,/* a ref or count in the scene points outside the buffer */
+    PM_ERR_BUFFER_TOO_SMALL = -5,
+    PM_ERR_STATE = -6,          /* render before set_scene/resize, encoder misuse, ... */
+    PM_ERR_PARSE = -7,          /* SVG path data / path list could not be parsed */
+    PM_ERR_NOMEM = -8
+} pm_status;
+
+const char *pm_strerror(int status);
+/* Text of the last failing CUDA call on this thread ("" if none). */
+const char *pm_last_error(void);
+/* Library version, "major.minor.patch". */
+const char *pm_version(void);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Feed: scene encoding (host only, no GPU needed)                                              */
+/* ------------------------------------------------------------------------------------------- */
+
+/* Same symbol, signature and behaviour as the reference (include/piet_metal.h:3): writes the
+ * default test scene (the tiger at scale 8, src/lib.rs:286-328,369-373) from offset 0 of `buf`.
+ * The reference panics on overflow; this one writes nothing past buf_size and leaves n_items = 0. */
+void init_test_scene(uint8_t *buf, ssize_t buf_size);
+
+/* Bump-allocating scene writer, mirroring `Encoder` (src/lib.rs:79-254).  Colours are
+ * 0xRRGGBBAA as in the reference API and are stored byte-swapped (rgba.to_be(), lib.rs:181). */
+typedef struct pm_encoder pm_encoder;
+int pm_encoder_new(pm_encoder **out, uint8_t *buf, size_t cap);          /* Encoder::new   :104 */
+int pm_encoder_begin_group(pm_encoder *e, uint32_t n_items);             /* begin_group    :132 */
+int pm_encoder_end_group(pm_encoder *e);                                 /* end_group      :146 */
+int pm_encoder_circle(pm_encoder *e, double cx, double cy, double r);    /* circle         :167 */
+int pm_encoder_stroke_line(pm_encoder *e, double x0, double y0, double x1, double y1,
+                           float width, uint32_t rgba);                  /* stroke_line    :177 */
+int pm_encoder_fill(pm_encoder *e, const double *xy, uint32_t n_points, uint32_t rgba);   /* :195 */
+int pm_encoder_polyline(pm_encoder *e, const double *xy, uint32_t n_points, uint32_t rgba,
+                        float width);                                    /* polyline       :209 */
+/* Bytes used so far (free_space, lib.rs:112-116). */
+size_t pm_encoder_bytes(const pm_encoder *e);
+void pm_encoder_free(pm_encoder *e);
+
+/* Path-level helpers: parse SVG path data (kurbo BezPath::from_svg as used at lib.rs:296,312),
+ * scale it, flatten it with flatten_path's rule (src/flatten.rs:10-47) and report the subpaths.
+ * out_xy receives x,y pairs of all subpaths back to back; out_counts the points per subpath.
+ * Returns the number of subpaths, or a negative pm_status (PM_ERR_BUFFER_TOO_SMALL if either
+ * capacity is exceeded; *need_points is then the total required). */
+int64_t pm_flatten_svg_path(const char *d, double scale, double tolerance, double *out_xy,
+                            size_t cap_points, uint32_t *out_counts, size_t cap_subpaths,
+                            size_t *need_points);
+/* parse_color (src/lib.rs:375-385): "#RGB" / "#RRGGBB" -> 0xRRGGBBff, anything else 0xff00ff80. */
+uint32_t pm_parse_color(const char *s);
+
+typedef enum pm_scene_kind {
+    PM_SCENE_RECT1 = 0,      /* BASELINE config 1: one solid-fill rectangle (x0,y0,x1,y1 in rect[]) */
+    PM_SCENE_PATH_TEST = 1,  /* make_path_test, src/lib.rs:273-284 */
+    PM_SCENE_CARDIOID = 2,   /* make_cardioid,  src/lib.rs:257-270 */
+    PM_SCENE_TIGER = 3,      /* make_tiger,     src/lib.rs:286-328 with scale = width / 200 */
+    PM_SCENE_RAND_BEZIER = 4,/* BASELINE config 4: `count` random filled Bezier paths */
+    PM_SCENE_GLYPHS = 5      /* BASELINE config 5: `count` small glyph-like outlines */
+} pm_scene_kind;
+
+typedef struct pm_scene_desc {
+    uint32_t kind;     /* pm_scene_kind */
+    uint32_t width;    /* target surface in pixels (scenes are encoded in pixel coordinates) */
+    uint32_t height;
+    uint32_t count;    /* RAND_BEZIER / GLYPHS: number of paths (0 = the config's default) */
+    uint64_t seed;     /* SplitMix64 seed (0 = the config's default) */
+    double scale;      /* TIGER: 0 = width/200; CARDIOID: 0 = 1 (coordinates as in the reference) */
+    double rect[4];    /* RECT1 */
+    uint32_t rgba;     /* RECT1 colour, 0xRRGGBBAA (0 = 0x3366ccff) */
+    uint32_t reserved;
+} pm_scene_desc;
+
+/* Writes the scene into buf; returns bytes written, or a negative pm_status.  With buf == NULL it
+ * returns the size needed. */
+int64_t pm_scene_build(const pm_scene_desc *desc, uint8_t *buf, size_t cap);
+/* Same as make_tiger but for an arbitrary "path list" text (see tools/make_tiger_fixture.py). */
+int64_t pm_scene_from_pathlist(const char *text, size_t len, double scale, uint8_t *buf, size_t cap);
+/* Bounds-checks every ref/count of an encoded scene (the reference never does). */
+int pm_scene_validate(const uint8_t *scene, size_t len);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Renderer (CUDA, sm_100a)                                                                     */
+/* ------------------------------------------------------------------------------------------- */
+
+typedef struct pm_renderer pm_renderer;
+
+enum {
+    PM_FLAG_FIX_POLY_PRECULL = 1u << 0, /* use the per-row polyline pre-cull instead of the
+                                           reference's lane-row one */
+    PM_FLAG_EXACT_SRGB = 1u << 1        /* powf() for the linear->sRGB encode instead of ex2/lg2 */
+};
+
+typedef struct pm_config {
+    int32_t device;          /* CUDA device ordinal */
+    uint32_t flags;
+    uint64_t scratch_bytes;  /* per-frame record pool; 0 = sized automatically, grows on demand */
+} pm_config;
+
+typedef struct pm_frame_stats {
+    float ms_total;          /* device time of the last render (CUDA events on the render stream) */
+    float ms_bin;            /* binning / coarse kernels */
+    float ms_fine;           /* fill/blend kernel */
+    uint32_t n_tiles;        /* tiles in the strip */
+    uint32_t n_records;      /* per-tile records produced by binning */
+    uint32_t n_launches;     /* kernels launched for the frame */
+    uint32_t retries;        /* re-renders after growing the record pool */
+} pm_frame_stats;
+
+int pm_renderer_create(pm_renderer **out, const pm_config *cfg);
+void pm_renderer_destroy(pm_renderer *r);
+
+/* Surface size in pixels.  The framebuffer is RGBA8 (bytes R,G,B,A), row-major, top-left origin.
+ * By default the renderer owns the whole frame; pm_renderer_set_strip restricts it to the
+ * contiguous tile rows [tile_y0, tile_y1) for the multi-GPU row-strip shard. */
+int pm_renderer_resize(pm_renderer *r, uint32_t width, uint32_t height);
+int pm_renderer_set_strip(pm_renderer *r, uint32_t tile_y0, uint32_t tile_y1);
+
+/* Upload (and validate) an encoded scene from host memory. */
+int pm_renderer_set_scene(pm_renderer *r, const uint8_t *scene, size_t len);
+/* Adopt a scene that already is in this device's memory (e.g. the output of an NCCL broadcast);
+ * it is copied device-to-device on the render stream and validated on the device. */
+int pm_renderer_set_scene_device(pm_renderer *r, const void *scene_dev, size_t len);
+
+/* Enqueue one frame on the renderer's stream (asynchronous, like drawInMTKView's commit). */
+int pm_renderer_render(pm_renderer *r);
+/* Wait for the stream; report the last frame's statistics (stats may be NULL). */
+int pm_renderer_sync(pm_renderer *r, pm_frame_stats *stats);
+/* Copy the strip's pixels to host memory: rows [16*tile_y0, min(16*tile_y1, height)),
+ * `stride` bytes between rows (>= 4*width). */
+int pm_renderer_read_rgba8(pm_renderer *r, uint8_t *dst, size_t stride);
+/* One call from host scene bytes to host pixels: upload, render, read back, synchronise. */
+int pm_renderer_render_host(pm_renderer *r, const uint8_t *scene, size_t len, uint8_t *dst,
+                            size_t stride, pm_frame_stats *stats);
+
+/* Device pointer / pitch of the strip's framebuffer and the stream the frame is enqueued on
+ * (cudaStream_t), for zero-copy consumers such as a torch tensor view. */
+int pm_renderer_framebuffer(pm_renderer *r, void **dev_ptr, size_t *pitch_bytes, uint32_t *rows);
+int pm_renderer_stream(pm_renderer *r, void **cuda_stream);
+
+/* Debug / parity read-backs (never on the timed path). */
+/* Re-render the strip with fp32 RGBA output (4 floats per pixel, alpha = 1) and copy it out. */
+int pm_renderer_read_rgba32f(pm_renderer *r, float *dst, size_t stride_bytes);
+
+typedef struct pm_tile_item {
+    uint32_t item;      /* item index */
+    int32_t backdrop;   /* Fill items: integer backdrop handed to DrawFill; 0 otherwise */
+    uint32_t effect;    /* 0 = draw, 1 = solid */
+} pm_tile_item;
+/* Per-tile item lists of the last frame, in the definition of SURVEY.md 8(a): for tile t (row-major
+ * within the strip) items[offsets[t] .. offsets[t+1]) ascending, truncated at the last opaque solid
+ * cover, plus the tile's final solid colour (0 if the tile is not solid).  offsets has n_tiles+1
+ * entries.  Returns PM_ERR_BUFFER_TOO_SMALL (with *n_items_out set) if cap_items is too small. */
+int pm_renderer_read_tile_items(pm_renderer *r, uint32_t *offsets, pm_tile_item *items,
+                                size_t cap_items, size_t *n_items_out, uint32_t *solid_colors);
+
+/* Pinned host memory for fast host<->device copies of scenes and frames. */
+int pm_host_alloc(void **out, size_t bytes);
+void pm_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIET_METAL_B200_H */
