@@ -136,16 +136,22 @@ enum {
 typedef struct pm_config {
     int32_t device;          /* CUDA device ordinal */
     uint32_t flags;
-    uint64_t scratch_bytes;  /* per-frame record pool; 0 = sized automatically, grows on demand */
+    uint64_t scratch_bytes;  /* overflow part of the record pool (beyond the 8 inline slots per
+                                tile); 0 = sized automatically; it grows on demand either way */
 } pm_config;
 
 typedef struct pm_frame_stats {
-    float ms_total;          /* device time of the last render (CUDA events on the render stream) */
-    float ms_bin;            /* binning / coarse kernels */
-    float ms_fine;           /* fill/blend kernel */
+    float ms_total;          /* device time of the last frame (CUDA events on the render stream) */
+    float ms_bin;            /*   its binning kernel */
+    float ms_fine;           /*   its fill/blend kernel */
+    uint32_t frames;         /* frames enqueued since the previous sync that the sums below cover */
+    float ms_total_sum;      /* the same three times summed over those frames */
+    float ms_bin_sum;
+    float ms_fine_sum;
     uint32_t n_tiles;        /* tiles in the strip */
-    uint32_t n_records;      /* per-tile records produced by binning */
-    uint32_t n_launches;     /* kernels launched for the frame */
+    uint32_t n_overflow_records; /* records that did not fit their tile's 8 inline slots (last frame) */
+    uint32_t n_complex_tiles;/* tiles that own at least one record (last frame) */
+    uint32_t n_launches;     /* kernels launched per frame */
     uint32_t retries;        /* re-renders after growing the record pool */
 } pm_frame_stats;
 

@@ -1,0 +1,357 @@
+"""piet_metal_b200 -- Python host-side mirror of the reference's operator interface.
+
+The product is the C-ABI shared library ``libpiet_metal_b200.so`` (``include/piet_metal_b200.h``);
+this module is the thin ctypes binding the tests and ``bench.py`` drive it through.  Names follow the
+reference: ``Encoder`` mirrors the Rust ``Encoder`` (src/lib.rs:79-254) and ``PietRenderer`` mirrors
+the Objective-C ``PietRenderer`` (TestApp/PietRenderer.m: ``initWithMetalKitView:`` :23,
+``mtkView:drawableSizeWillChange:`` :105, ``initScene`` :203, ``drawInMTKView:`` :59).
+
+There is no CPU rendering path: if the library is missing, or there is no sm_100 GPU, the renderer
+raises instead of falling back.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpiet_metal_b200.so")
+
+PM_OK = 0
+PM_ERR_NO_DEVICE = -2
+PM_ERR_SCENE_MALFORMED = -4
+PM_ERR_BUFFER_TOO_SMALL = -5
+PM_ERR_STATE = -6
+
+SCENE_RECT1, SCENE_PATH_TEST, SCENE_CARDIOID, SCENE_TIGER, SCENE_RAND_BEZIER, SCENE_GLYPHS = range(6)
+FLAG_FIX_POLY_PRECULL = 1
+FLAG_EXACT_SRGB = 2
+
+
+class PietMetalError(RuntimeError):
+    def __init__(self, status, where):
+        self.status = status
+        lib = _lib()
+        msg = lib.pm_strerror(status).decode()
+        last = lib.pm_last_error().decode()
+        super().__init__("%s: %s (%d)%s" % (where, msg, status, (" -- " + last) if last else ""))
+
+
+class SceneDesc(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_uint32), ("width", ctypes.c_uint32), ("height", ctypes.c_uint32),
+                ("count", ctypes.c_uint32), ("seed", ctypes.c_uint64), ("scale", ctypes.c_double),
+                ("rect", ctypes.c_double * 4), ("rgba", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
+class Config(ctypes.Structure):
+    _fields_ = [("device", ctypes.c_int32), ("flags", ctypes.c_uint32), ("scratch_bytes", ctypes.c_uint64)]
+
+
+class FrameStats(ctypes.Structure):
+    _fields_ = [("ms_total", ctypes.c_float), ("ms_bin", ctypes.c_float), ("ms_fine", ctypes.c_float),
+                ("frames", ctypes.c_uint32), ("ms_total_sum", ctypes.c_float), ("ms_bin_sum", ctypes.c_float),
+                ("ms_fine_sum", ctypes.c_float), ("n_tiles", ctypes.c_uint32), ("n_overflow_records", ctypes.c_uint32),
+                ("n_complex_tiles", ctypes.c_uint32), ("n_launches", ctypes.c_uint32), ("retries", ctypes.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+TILE_ITEM_DTYPE = np.dtype([("item", np.uint32), ("backdrop", np.int32), ("effect", np.uint32)])
+
+# every entry point declared in include/piet_metal_b200.h
+EXPORTS = [
+    "pm_strerror", "pm_last_error", "pm_version", "init_test_scene",
+    "pm_encoder_new", "pm_encoder_begin_group", "pm_encoder_end_group", "pm_encoder_circle",
+    "pm_encoder_stroke_line", "pm_encoder_fill", "pm_encoder_polyline", "pm_encoder_bytes", "pm_encoder_free",
+    "pm_flatten_svg_path", "pm_parse_color", "pm_scene_build", "pm_scene_from_pathlist", "pm_scene_validate",
+    "pm_renderer_create", "pm_renderer_destroy", "pm_renderer_resize", "pm_renderer_set_strip",
+    "pm_renderer_set_scene", "pm_renderer_set_scene_device", "pm_renderer_render", "pm_renderer_sync",
+    "pm_renderer_read_rgba8", "pm_renderer_render_host", "pm_renderer_framebuffer", "pm_renderer_stream",
+    "pm_renderer_read_rgba32f", "pm_renderer_read_tile_items", "pm_host_alloc", "pm_host_free",
+]
+
+_LIB = None
+
+
+def _lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: build it with `make -C %s` (or __graft_entry__.build()); "
+                          "there is no fallback implementation" % (LIB_PATH, _HERE))
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, sz, u32, u64, i64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int64
+    dbl, flt, cint = ctypes.c_double, ctypes.c_float, ctypes.c_int
+    sig = {
+        "pm_strerror": (ctypes.c_char_p, [cint]),
+        "pm_last_error": (ctypes.c_char_p, []),
+        "pm_version": (ctypes.c_char_p, []),
+        "init_test_scene": (None, [vp, ctypes.c_ssize_t]),
+        "pm_encoder_new": (cint, [ctypes.POINTER(vp), vp, sz]),
+        "pm_encoder_begin_group": (cint, [vp, u32]),
+        "pm_encoder_end_group": (cint, [vp]),
+        "pm_encoder_circle": (cint, [vp, dbl, dbl, dbl]),
+        "pm_encoder_stroke_line": (cint, [vp, dbl, dbl, dbl, dbl, flt, u32]),
+        "pm_encoder_fill": (cint, [vp, vp, u32, u32]),
+        "pm_encoder_polyline": (cint, [vp, vp, u32, u32, flt]),
+        "pm_encoder_bytes": (sz, [vp]),
+        "pm_encoder_free": (None, [vp]),
+        "pm_flatten_svg_path": (i64, [ctypes.c_char_p, dbl, dbl, vp, sz, vp, sz, ctypes.POINTER(sz)]),
+        "pm_parse_color": (u32, [ctypes.c_char_p]),
+        "pm_scene_build": (i64, [ctypes.POINTER(SceneDesc), vp, sz]),
+        "pm_scene_from_pathlist": (i64, [ctypes.c_char_p, sz, dbl, vp, sz]),
+        "pm_scene_validate": (cint, [vp, sz]),
+        "pm_renderer_create": (cint, [ctypes.POINTER(vp), ctypes.POINTER(Config)]),
+        "pm_renderer_destroy": (None, [vp]),
+        "pm_renderer_resize": (cint, [vp, u32, u32]),
+        "pm_renderer_set_strip": (cint, [vp, u32, u32]),
+        "pm_renderer_set_scene": (cint, [vp, vp, sz]),
+        "pm_renderer_set_scene_device": (cint, [vp, vp, sz]),
+        "pm_renderer_render": (cint, [vp]),
+        "pm_renderer_sync": (cint, [vp, ctypes.POINTER(FrameStats)]),
+        "pm_renderer_read_rgba8": (cint, [vp, vp, sz]),
+        "pm_renderer_render_host": (cint, [vp, vp, sz, vp, sz, ctypes.POINTER(FrameStats)]),
+        "pm_renderer_framebuffer": (cint, [vp, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(u32)]),
+        "pm_renderer_stream": (cint, [vp, ctypes.POINTER(vp)]),
+        "pm_renderer_read_rgba32f": (cint, [vp, vp, sz]),
+        "pm_renderer_read_tile_items": (cint, [vp, vp, vp, sz, ctypes.POINTER(sz), vp]),
+        "pm_host_alloc": (cint, [ctypes.POINTER(vp), sz]),
+        "pm_host_free": (None, [vp]),
+    }
+    for name in EXPORTS:
+        fn = getattr(lib, name)  # AttributeError if the library does not export what the header declares
+        fn.restype, fn.argtypes = sig[name]
+    _LIB = lib
+    return lib
+
+
+def _check(status, where):
+    if status != PM_OK:
+        raise PietMetalError(status, where)
+
+
+def _ptr(arr):
+    return arr.ctypes.data_as(ctypes.c_void_p)
+
+
+def version():
+    return _lib().pm_version().decode()
+
+
+# ------------------------------------------------------------------------------------------------
+# feed
+# ------------------------------------------------------------------------------------------------
+def build_scene(kind, width, height, count=0, seed=0, scale=0.0, rect=(0.0, 0.0, 0.0, 0.0), rgba=0):
+    """pm_scene_build: returns the encoded scene as a uint8 numpy array."""
+    lib = _lib()
+    d = SceneDesc(kind=kind, width=width, height=height, count=count, seed=seed, scale=scale, rgba=rgba)
+    for i in range(4):
+        d.rect[i] = float(rect[i])
+    need = lib.pm_scene_build(ctypes.byref(d), None, 0)
+    if need < 0:
+        raise PietMetalError(int(need), "pm_scene_build")
+    buf = np.zeros(int(need), np.uint8)
+    got = lib.pm_scene_build(ctypes.byref(d), _ptr(buf), buf.size)
+    if got != need:
+        raise PietMetalError(int(got) if got < 0 else PM_ERR_BUFFER_TOO_SMALL, "pm_scene_build")
+    return buf
+
+
+def init_test_scene(buf_size=16 * 1024 * 1024):
+    """The reference's C entry point (include/piet_metal.h:3) into a caller-owned buffer."""
+    buf = np.zeros(buf_size, np.uint8)
+    _lib().init_test_scene(_ptr(buf), buf_size)
+    return buf
+
+
+def scene_len(buf):
+    """Bytes actually used by an encoded scene (highest ref in it)."""
+    n = int(buf[:4].view(np.uint32)[0])
+    items_ix = int(buf[4:8].view(np.uint32)[0])
+    end = items_ix + 32 * n
+    items = buf[items_ix:items_ix + 32 * n].view(np.uint32).reshape(n, 8)
+    for tag, npts, pix in ((3, 3, 4), (4, 3, 4)):
+        sel = items[:, 0] == tag
+        if sel.any():
+            end = max(end, int((items[sel, pix].astype(np.int64) + 8 * items[sel, npts].astype(np.int64)).max()))
+    return end
+
+
+def validate_scene(buf):
+    return _lib().pm_scene_validate(_ptr(buf), buf.size)
+
+
+def parse_color(s):
+    return _lib().pm_parse_color(s.encode())
+
+
+def flatten_svg_path(d, scale=1.0, tolerance=0.1):
+    """flatten_path(BezPath::from_svg(d) scaled): list of (n_i, 2) float64 arrays, one per subpath."""
+    lib = _lib()
+    need = ctypes.c_size_t(0)
+    cap_pts, cap_sub = 1 << 16, 1 << 12
+    while True:
+        xy = np.zeros((cap_pts, 2), np.float64)
+        counts = np.zeros(cap_sub, np.uint32)
+        n = lib.pm_flatten_svg_path(d.encode(), scale, tolerance, _ptr(xy), cap_pts, _ptr(counts), cap_sub, ctypes.byref(need))
+        if n == PM_ERR_BUFFER_TOO_SMALL:
+            cap_pts, cap_sub = max(cap_pts * 2, need.value), cap_sub * 2
+            continue
+        if n < 0:
+            raise PietMetalError(int(n), "pm_flatten_svg_path")
+        out, k = [], 0
+        for i in range(int(n)):
+            out.append(xy[k:k + counts[i]].copy())
+            k += int(counts[i])
+        return out
+
+
+class Encoder:
+    """Mirror of the reference's `Encoder` (src/lib.rs:79-254) over a caller-sized buffer."""
+
+    def __init__(self, capacity):
+        self.buf = np.zeros(capacity, np.uint8)
+        self._h = ctypes.c_void_p()
+        _check(_lib().pm_encoder_new(ctypes.byref(self._h), _ptr(self.buf), capacity), "pm_encoder_new")
+
+    def begin_group(self, n_items):
+        _check(_lib().pm_encoder_begin_group(self._h, n_items), "begin_group")
+
+    def end_group(self):
+        _check(_lib().pm_encoder_end_group(self._h), "end_group")
+
+    def circle(self, cx, cy, r):
+        _check(_lib().pm_encoder_circle(self._h, cx, cy, r), "circle")
+
+    def stroke_line(self, p0, p1, width, rgba):
+        _check(_lib().pm_encoder_stroke_line(self._h, p0[0], p0[1], p1[0], p1[1], width, rgba), "stroke_line")
+
+    def fill(self, points, rgba):
+        pts = np.ascontiguousarray(points, np.float64)
+        _check(_lib().pm_encoder_fill(self._h, _ptr(pts), pts.shape[0], rgba), "fill")
+
+    def polyline(self, points, rgba, width):
+        pts = np.ascontiguousarray(points, np.float64)
+        _check(_lib().pm_encoder_polyline(self._h, _ptr(pts), pts.shape[0], rgba, width), "polyline")
+
+    def bytes(self):
+        """The encoded scene (a copy of the used prefix of the buffer)."""
+        return self.buf[:_lib().pm_encoder_bytes(self._h)].copy()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _lib().pm_encoder_free(self._h)
+            self._h = None
+
+
+# ------------------------------------------------------------------------------------------------
+# renderer
+# ------------------------------------------------------------------------------------------------
+class PietRenderer:
+    """Mirror of the reference's PietRenderer (TestApp/PietRenderer.m) on one B200."""
+
+    def __init__(self, device=0, flags=0, scratch_bytes=0):
+        self._h = ctypes.c_void_p()
+        cfg = Config(device=device, flags=flags, scratch_bytes=scratch_bytes)
+        _check(_lib().pm_renderer_create(ctypes.byref(self._h), ctypes.byref(cfg)), "pm_renderer_create")
+        self.width = self.height = 0
+        self.tile_y0 = self.tile_y1 = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib().pm_renderer_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # mtkView:drawableSizeWillChange: (PietRenderer.m:105)
+    def drawable_size_will_change(self, width, height):
+        _check(_lib().pm_renderer_resize(self._h, width, height), "pm_renderer_resize")
+        self.width, self.height = width, height
+        self.tile_y0, self.tile_y1 = 0, (height + 15) // 16
+
+    resize = drawable_size_will_change
+
+    def set_strip(self, tile_y0, tile_y1):
+        _check(_lib().pm_renderer_set_strip(self._h, tile_y0, tile_y1), "pm_renderer_set_strip")
+        self.tile_y0, self.tile_y1 = tile_y0, tile_y1
+
+    # initScene (PietRenderer.m:203): hand the encoded scene to the renderer
+    def init_scene(self, scene):
+        scene = np.ascontiguousarray(scene, np.uint8)
+        _check(_lib().pm_renderer_set_scene(self._h, _ptr(scene), scene.size), "pm_renderer_set_scene")
+
+    set_scene = init_scene
+
+    def set_scene_device(self, dev_ptr, nbytes):
+        _check(_lib().pm_renderer_set_scene_device(self._h, ctypes.c_void_p(dev_ptr), nbytes), "pm_renderer_set_scene_device")
+
+    # drawInMTKView: (PietRenderer.m:59): enqueue one frame
+    def draw(self):
+        _check(_lib().pm_renderer_render(self._h), "pm_renderer_render")
+
+    render = draw
+
+    def sync(self):
+        st = FrameStats()
+        _check(_lib().pm_renderer_sync(self._h, ctypes.byref(st)), "pm_renderer_sync")
+        return st
+
+    @property
+    def strip_rows(self):
+        return min(self.tile_y1 * 16, self.height) - self.tile_y0 * 16
+
+    def read_rgba8(self, out=None):
+        if out is None:
+            out = np.empty((self.strip_rows, self.width, 4), np.uint8)
+        _check(_lib().pm_renderer_read_rgba8(self._h, _ptr(out), out.strides[0]), "pm_renderer_read_rgba8")
+        return out
+
+    def read_rgba32f(self):
+        out = np.empty((self.strip_rows, self.width, 4), np.float32)
+        _check(_lib().pm_renderer_read_rgba32f(self._h, _ptr(out), out.strides[0]), "pm_renderer_read_rgba32f")
+        return out
+
+    def read_tile_items(self):
+        """(offsets[n_tiles+1], items[structured], solid_colors[n_tiles]) of the strip, row-major."""
+        n_tiles = (self.tile_y1 - self.tile_y0) * ((self.width + 15) // 16)
+        offsets = np.zeros(n_tiles + 1, np.uint32)
+        solid = np.zeros(n_tiles, np.uint32)
+        cap = max(1024, 4 * n_tiles)
+        while True:
+            items = np.zeros(cap, TILE_ITEM_DTYPE)
+            n = ctypes.c_size_t(0)
+            st = _lib().pm_renderer_read_tile_items(self._h, _ptr(offsets), _ptr(items), cap, ctypes.byref(n), _ptr(solid))
+            if st == PM_ERR_BUFFER_TOO_SMALL:
+                cap = n.value
+                continue
+            _check(st, "pm_renderer_read_tile_items")
+            return offsets, items[:n.value], solid
+
+    def render_host(self, scene, out=None):
+        """Host bytes in, host pixels out: upload + one frame + read-back (the e2e call)."""
+        scene = np.ascontiguousarray(scene, np.uint8)
+        if out is None:
+            out = np.empty((self.strip_rows, self.width, 4), np.uint8)
+        st = FrameStats()
+        _check(_lib().pm_renderer_render_host(self._h, _ptr(scene), scene.size, _ptr(out), out.strides[0], ctypes.byref(st)),
+               "pm_renderer_render_host")
+        return out, st
+
+    def framebuffer(self):
+        """(device pointer, pitch in bytes, rows) of the strip's RGBA8 framebuffer."""
+        p, pitch, rows = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_uint32()
+        _check(_lib().pm_renderer_framebuffer(self._h, ctypes.byref(p), ctypes.byref(pitch), ctypes.byref(rows)), "pm_renderer_framebuffer")
+        return p.value, pitch.value, rows.value
+
+    def stream(self):
+        s = ctypes.c_void_p()
+        _check(_lib().pm_renderer_stream(self._h, ctypes.byref(s)), "pm_renderer_stream")
+        return s.value or 0
+
+
+def strip_bounds(n_tile_rows, world_size):
+    """Contiguous row-strip shard of the frame's tile rows: rank g renders [b[g], b[g+1])."""
+    return [(n_tile_rows * g) // world_size for g in range(world_size + 1)]

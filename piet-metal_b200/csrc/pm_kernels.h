@@ -1,0 +1,67 @@
+// Host-visible interface of the CUDA kernels (pm_kernels.cu) used by the renderer (pm_renderer.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pm_pixel_logic.h"
+
+// Per-frame counters.  Two sets alternate by frame parity so that the fill kernel of frame f can
+// clear the set frame f+1 will use (no memset node in the frame).
+struct PmBinCounters {
+    uint32_t n_complex;   // tiles that own at least one record
+    uint32_t n_overflow;  // records that did not fit the inline slots of their tile
+    uint32_t pad[2];
+};
+// Work queues of the fill kernel; cleared by the binning kernel of the same frame.
+struct PmFineQueue {
+    uint32_t complex_next;
+    uint32_t batch_next;
+    uint32_t pad[2];
+};
+// Written by the device into mapped host memory at the end of every frame.
+struct PmFrameReport {
+    uint32_t n_complex;
+    uint32_t n_overflow;
+    uint32_t frame;
+    uint32_t pad;
+};
+
+struct PmFrameArgs {
+    const uint8_t *scene;       // encoded scene in device memory
+    uint32_t scene_len;
+    uint32_t n_items;
+    uint32_t items_ix;
+    const uint32_t *unit_base;  // exclusive prefix of per-item tile-row counts, n_items + 1 entries
+    uint32_t n_units;
+    uint32_t tile_y0;           // first tile row of the strip
+    uint32_t n_rows;            // tile rows in the strip
+    uint32_t n_tx;              // tiles per row
+    unsigned long long *occ;    // n_rows * n_tx stamped words (see pm_pixel_logic.h)
+    unsigned long long *cnt;
+    unsigned long long *ovf;
+    PmRecord *pool;             // [n_tiles * PM_TILE_SLOTS inline slots][overflow_cap records]
+    uint32_t overflow_cap;
+    uint32_t *complex_list;     // n_rows * n_tx
+    PmBinCounters *counters;    // this frame's set
+    PmBinCounters *counters_next;
+    PmFineQueue *queue;
+    PmFrameReport *report;      // mapped host memory
+    uint32_t stamp;             // frame number + 1, never 0
+    uint32_t flags;             // PM_FLAG_*
+    uint8_t *fb;                // RGBA8 strip, n_rows*16 rows, pitch bytes apart
+    size_t pitch;
+    float *fb32;                // optional fp32 RGBA strip (debug renders)
+    size_t pitch32;
+    const float *srgb_lut;      // 256 floats: sRGB byte -> linear
+};
+
+struct PmPlanResult { uint32_t n_units; uint32_t error; };
+
+// Validates an encoded scene on the device.  *err (device) becomes non-zero if a ref or count is
+// out of bounds or a coordinate is not finite.
+void pm_launch_validate(const uint8_t *scene, uint32_t scene_len, uint32_t *err, cudaStream_t s);
+// Fills unit_base[0..n_items] and result (device) for the given strip.
+void pm_launch_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1,
+                    uint32_t n_tx, uint32_t *unit_base, PmPlanResult *result, cudaStream_t s);
+// One frame: binning then fill/blend.  `mid` (optional) is recorded between the two kernels.
+void pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, cudaStream_t s);

@@ -1,0 +1,204 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the oracle on the same encoded scene.
+
+Bar (BASELINE.json north_star): per-tile item lists and solid colours bit-exact; fp32 RGBA within
+1e-5 absolute; RGBA8 within 1 LSB."""
+import numpy as np
+import pytest
+
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def renderer(pm):
+    r = pm.PietRenderer(device=0)
+    yield r
+    r.close()
+
+
+def gpu_render(r, scene, w, h, strip=None):
+    r.drawable_size_will_change(w, h)
+    if strip:
+        r.set_strip(*strip)
+    r.init_scene(scene)
+    r.draw()
+    stats = r.sync()
+    out = {"rgba8": r.read_rgba8(), "rgba32f": r.read_rgba32f(), "stats": stats}
+    out["offsets"], out["items"], out["solid"] = r.read_tile_items()
+    # the debug renders must not disturb the product framebuffer
+    assert np.array_equal(out["rgba8"], r.read_rgba8())
+    return out
+
+
+def check(gpu, ref, what):
+    assert scenes.items_equal(gpu, ref), "%s: per-tile item lists differ" % what
+    d8 = np.abs(gpu["rgba8"].astype(np.int16) - ref["rgba8"].astype(np.int16)).max()
+    assert d8 <= 1, "%s: RGBA8 differs by %d LSB" % (what, d8)
+    a, b = gpu["rgba32f"], ref["rgba32f"]
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "%s: NaN pattern differs" % what
+    df = np.nanmax(np.abs(a - b)) if a.size else 0.0
+    assert df <= F32_TOL, "%s: fp32 RGBA differs by %g" % (what, df)
+
+
+CASES = [
+    ("rect1_int", lambda pm: (pm.build_scene(pm.SCENE_RECT1, 16, 16, rect=(3, 2, 13, 14)), 16, 16)),
+    ("rect1_frac", lambda pm: (pm.build_scene(pm.SCENE_RECT1, 16, 16, rect=(3.25, 2.5, 12.75, 13.5)), 16, 16)),
+    ("path_test", lambda pm: (pm.build_scene(pm.SCENE_PATH_TEST, 320, 816), 320, 816)),
+    ("cardioid", lambda pm: (pm.build_scene(pm.SCENE_CARDIOID, 2048, 1536), 2048, 1536)),
+    ("tiger_1024", lambda pm: (pm.build_scene(pm.SCENE_TIGER, 1024, 1024), 1024, 1024)),
+    ("tiger_1000x700", lambda pm: (pm.build_scene(pm.SCENE_TIGER, 1000, 1000), 1000, 700)),
+    ("rand_bezier_1024", lambda pm: (pm.build_scene(pm.SCENE_RAND_BEZIER, 1024, 1024, count=400), 1024, 1024)),
+    ("glyphs_512", lambda pm: (pm.build_scene(pm.SCENE_GLYPHS, 512, 512, count=2000), 512, 512)),
+]
+
+
+@pytest.mark.parametrize("name,make", CASES, ids=[c[0] for c in CASES])
+def test_scene_matches_oracle(pm, oracle, renderer, name, make):
+    scene, w, h = make(pm)
+    gpu = gpu_render(renderer, scene, w, h)
+    ref = oracle.render(scene, w, h, f32=True, items=True)
+    check(gpu, ref, name)
+
+
+def test_fuzz_knife_edges(pm, oracle):
+    for seed in range(120):
+        scene, w, h, flags = scenes.fuzz_case(pm, seed)
+        r = pm.PietRenderer(device=0, flags=flags)
+        try:
+            gpu = gpu_render(r, scene, w, h)
+        finally:
+            r.close()
+        ref = oracle.render(scene, w, h, flags=flags, f32=True, items=True)
+        check(gpu, ref, "fuzz seed %d" % seed)
+
+
+def test_exact_srgb_flag_is_tighter(pm, oracle):
+    scene, w, h = pm.build_scene(pm.SCENE_TIGER, 512, 512), 512, 512
+    r = pm.PietRenderer(device=0, flags=pm.FLAG_EXACT_SRGB)
+    try:
+        gpu = gpu_render(r, scene, w, h)
+    finally:
+        r.close()
+    ref = oracle.render(scene, w, h, f32=True, items=True)
+    check(gpu, ref, "tiger_512 exact sRGB")
+    assert np.abs(gpu["rgba32f"] - ref["rgba32f"]).max() <= 2e-6  # fixed-point coverage + powf ULPs
+
+
+def test_row_strips_equal_full_frame(pm, renderer):
+    """Multi-GPU shard property: N contiguous row-strips reproduce the 1-GPU frame byte for byte."""
+    w = h = 1536
+    scene = pm.build_scene(pm.SCENE_TIGER, w, h)
+    full = gpu_render(renderer, scene, w, h)["rgba8"]
+    for n in (2, 3, 8):
+        b = pm.strip_bounds((h + 15) // 16, n)
+        parts = []
+        for g in range(n):
+            renderer.drawable_size_will_change(w, h)
+            renderer.set_strip(b[g], b[g + 1])
+            renderer.init_scene(scene)
+            renderer.draw()
+            parts.append(renderer.read_rgba8())
+        assert np.array_equal(np.concatenate(parts, axis=0), full), "%d strips differ from the full frame" % n
+
+
+def test_render_host_roundtrip(pm, renderer):
+    w = h = 640
+    scene = pm.build_scene(pm.SCENE_TIGER, w, h)
+    renderer.drawable_size_will_change(w, h)
+    img, stats = renderer.render_host(scene)
+    renderer.init_scene(scene)
+    renderer.draw()
+    assert np.array_equal(img, renderer.read_rgba8())
+    assert stats.n_launches == 2 and stats.n_complex_tiles > 0
+
+
+def test_scene_device_pointer_path(pm, renderer):
+    """set_scene_device: the entry point a rank uses after the NCCL broadcast of the scene."""
+    import torch
+    w = h = 512
+    scene = pm.build_scene(pm.SCENE_TIGER, w, h)
+    renderer.drawable_size_will_change(w, h)
+    renderer.init_scene(scene)
+    renderer.draw()
+    want = renderer.read_rgba8()
+    t = torch.from_numpy(scene).cuda()
+    torch.cuda.synchronize()
+    renderer.set_scene_device(t.data_ptr(), t.numel())
+    renderer.draw()
+    assert np.array_equal(renderer.read_rgba8(), want)
+
+
+def test_malformed_scene_is_rejected(pm, renderer):
+    scene = pm.build_scene(pm.SCENE_PATH_TEST, 320, 816).copy()
+    scene[8 + 8 + 16:8 + 8 + 20].view(np.uint32)[0] = 1 << 30  # points_ix far outside the buffer
+    renderer.drawable_size_will_change(64, 64)
+    with pytest.raises(pm.PietMetalError) as e:
+        renderer.init_scene(scene)
+    assert e.value.status == pm.PM_ERR_SCENE_MALFORMED
+
+
+def test_deep_stacks_overflow_chain(pm, oracle, renderer):
+    """Hundreds of records per tile: inline slots + overflow chain + records beyond the fill
+    kernel's shared-memory index."""
+    for layers in (40, 420):
+        scene, w, h = scenes.stacked_scene(pm, layers), 96, 64
+        gpu = gpu_render(renderer, scene, w, h)
+        ref = oracle.render(scene, w, h, f32=True, items=True)
+        check(gpu, ref, "stack of %d" % layers)
+
+
+def test_record_pool_grows_on_demand(pm, oracle):
+    scene, w, h = scenes.stacked_scene(pm, 200), 96, 64
+    r = pm.PietRenderer(device=0, scratch_bytes=64 * 32)  # room for 64 overflow records: far too few
+    try:
+        r.drawable_size_will_change(w, h)
+        r.init_scene(scene)
+        r.draw()
+        stats = r.sync()
+        assert stats.retries >= 1 and stats.n_overflow_records > 64
+        img = r.read_rgba8()
+    finally:
+        r.close()
+    ref = oracle.render(scene, w, h)["rgba8"]
+    assert np.abs(img.astype(np.int16) - ref.astype(np.int16)).max() <= 1
+
+
+def test_full_size_properties_8192(pm, renderer):
+    """BASELINE full size (tiger at 8192^2), checked through size-independent properties: the frame
+    equals the concatenation of its row strips, an untouched corner is background white, and a band
+    of it matches the oracle rendered for that band only."""
+    w = h = 8192
+    scene = pm.build_scene(pm.SCENE_TIGER, w, h)
+    renderer.drawable_size_will_change(w, h)
+    renderer.init_scene(scene)
+    renderer.draw()
+    stats = renderer.sync()
+    full = renderer.read_rgba8()
+    assert stats.n_tiles == 512 * 512
+    assert (full[:64, :64] == 255).all()
+    import zlib
+    crc_full = zlib.crc32(full.tobytes())
+    b = pm.strip_bounds(512, 4)
+    crc = 0
+    for g in range(4):
+        renderer.drawable_size_will_change(w, h)
+        renderer.set_strip(b[g], b[g + 1])
+        renderer.init_scene(scene)
+        renderer.draw()
+        part = renderer.read_rgba8()
+        assert np.array_equal(part, full[b[g] * 16:b[g + 1] * 16])
+        crc = zlib.crc32(part.tobytes(), crc)
+    assert crc == crc_full
+
+
+def test_full_size_band_matches_oracle_8192(pm, oracle, renderer):
+    """Two tile rows through the middle of the 8192^2 tiger, GPU strip vs oracle strip."""
+    w = h = 8192
+    scene = pm.build_scene(pm.SCENE_TIGER, w, h)
+    y0, y1 = 255, 257
+    gpu = gpu_render(renderer, scene, w, h, strip=(y0, y1))
+    ref = oracle.render(scene, w, h, tile_y0=y0, tile_y1=y1, f32=True, items=True)
+    check(gpu, ref, "tiger 8192 rows %d..%d" % (y0, y1))
