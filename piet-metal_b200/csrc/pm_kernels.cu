@@ -200,6 +200,47 @@ struct BinSink {
     }
 };
 
+#define PM_BIN_UNROLL 4   // point loads in flight per lane while scanning an item's segments
+#define PM_BIN_PEND (32 * (PM_BIN_UNROLL + 1))   // pending (row-overlapping) segment indices per warp
+
+// Scans the n_seg segments of an item for the ones whose y range reaches this unit's tile row
+// (`overlap(sy, ey)`), compacts their indices and hands them to `process(k)` 32 at a time, so that
+// the expensive exact tests run with all lanes busy.  Order does not matter: every effect of a
+// segment is an atomic add / or / append.
+template <class Overlap, class Process>
+__device__ __forceinline__ void scan_segments(const uint8_t *pts, uint32_t n_seg, uint32_t n_points, uint32_t *pend, uint32_t lane,
+                                              Overlap overlap, Process process) {
+    uint32_t n_pend = 0;
+    for (uint32_t k0 = 0; k0 < n_seg; k0 += 32 * PM_BIN_UNROLL) {
+        float sy[PM_BIN_UNROLL], ey[PM_BIN_UNROLL];
+        #pragma unroll
+        for (int u = 0; u < PM_BIN_UNROLL; u++) {
+            const uint32_t k = k0 + 32u * u + lane;
+            sy[u] = ey[u] = 0.0f;
+            if (k < n_seg) {
+                sy[u] = ld_f32(pts + 8 * (size_t)k + 4);
+                ey[u] = ld_f32(pts + 8 * (size_t)(k + 1 == n_points ? 0 : k + 1) + 4);
+            }
+        }
+        #pragma unroll
+        for (int u = 0; u < PM_BIN_UNROLL; u++) {
+            const uint32_t k = k0 + 32u * u + lane;
+            const bool ov = k < n_seg && overlap(sy[u], ey[u]);
+            const uint32_t mask = __ballot_sync(PM_FULL_MASK, ov);
+            if (ov) pend[n_pend + __popc(mask & ((1u << lane) - 1u))] = k;
+            n_pend += __popc(mask);
+        }
+        __syncwarp();
+        const bool last = k0 + 32 * PM_BIN_UNROLL >= n_seg;
+        while (n_pend >= 32 || (last && n_pend > 0)) {  // the one call site of process()
+            const uint32_t take = n_pend < 32 ? n_pend : 32;
+            if (lane < take) process(pend[n_pend - 1 - lane]);
+            n_pend -= take;
+        }
+        __syncwarp();
+    }
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_bin(const PmFrameArgs A) {
     extern __shared__ uint32_t smem_u32[];
@@ -230,7 +271,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_bin(const PmFrameArgs A) {
     const uint32_t span = t_hi - t_lo + 1;
     const float y0 = (float)(row * PM_TILE_H);
 
-    uint32_t *sm = smem_u32 + (size_t)warp * (A.n_tx + 1);
+    uint32_t *sm = smem_u32 + (size_t)warp * (A.n_tx + 1 + PM_BIN_PEND);
+    uint32_t *pend = sm + A.n_tx + 1;
     for (uint32_t j = lane; j <= span; j += 32) sm[j] = 0;
     __syncwarp();
 
@@ -240,16 +282,15 @@ __global__ void __launch_bounds__(WARPS * 32) k_bin(const PmFrameArgs A) {
         const uint32_t rgba = ld_u32(it + PM_FILL_RGBA);
         const uint32_t n_points = ld_u32(it + PM_FILL_NPOINTS);
         const uint8_t *pts = A.scene + ld_u32(it + PM_FILL_POINTS_IX);
-        for (uint32_t k0 = 0; k0 < n_points; k0 += 32) {
-            uint32_t k = k0 + lane;
-            if (k < n_points) {
+        const uint32_t n_tx = A.n_tx;
+        scan_segments(pts, n_points, n_points, pend, lane,
+            [=](float sy, float ey) { return fmaxf(sy, ey) >= y0 && fminf(sy, ey) < y0 + 16.0f; },  // pm_fill_row_overlap
+            [&](uint32_t k) {
                 float2 s = ld_f2(pts + 8 * (size_t)k);
                 float2 e = ld_f2(pts + 8 * (size_t)(k + 1 == n_points ? 0 : k + 1));  // closing segment, metal:262
                 PmSeg g = pm_seg(s.x, s.y, e.x, e.y);
-                pm_fill_segment_row(sink, g, y0, t_lo, t_hi, A.n_tx, k);
-            }
-        }
-        __syncwarp();
+                pm_fill_segment_row(sink, g, y0, t_lo, t_hi, n_tx, k);
+            });
         // per-tile epilogue (metal:359-363): DrawFill / Solid / nothing
         int carry = 0;
         for (uint32_t base = 0; base < span; base += 32) {
@@ -279,20 +320,19 @@ __global__ void __launch_bounds__(WARPS * 32) k_bin(const PmFrameArgs A) {
     } else if (tag == PM_ITEM_POLY) {
         const uint32_t rgba = ld_u32(it + PM_POLY_RGBA);
         const float width = ld_f32(it + PM_POLY_WIDTH);
-        const uint32_t n_seg = ld_u32(it + PM_POLY_NPOINTS) - 1;  // open polyline, metal:369
+        const uint32_t n_points = ld_u32(it + PM_POLY_NPOINTS);
+        const uint32_t n_seg = n_points - 1;  // open polyline, metal:369
         const uint8_t *pts = A.scene + ld_u32(it + PM_POLY_POINTS_IX);
         const float hw = 0.5f * width + 0.5f;
         const bool fix = (A.flags & PM_FLAG_FIX_POLY_PRECULL) != 0;
-        for (uint32_t k0 = 0; k0 < n_seg; k0 += 32) {
-            uint32_t k = k0 + lane;
-            if (k < n_seg) {
+        scan_segments(pts, n_seg, n_points + 1, pend, lane,
+            [=](float sy, float ey) { return fmaxf(sy, ey) > y0 - hw && fminf(sy, ey) < y0 + 16.0f + hw; },
+            [&](uint32_t k) {
                 float2 s = ld_f2(pts + 8 * (size_t)k);
                 float2 e = ld_f2(pts + 8 * (size_t)(k + 1));
                 PmSeg g = pm_seg(s.x, s.y, e.x, e.y);
                 pm_poly_segment_row(sink, g, y0, hw, t_lo, t_hi, k, fix);
-            }
-        }
-        __syncwarp();
+            });
         for (uint32_t j = lane; j < span; j += 32)
             if (sm[j] & 1u) sink.trailer(t_lo + j, PM_REC_STROKE, PM_REC_SEG_MAX, pm_f2u(0.5f * width), rgba);  // metal:441-443
     } else if (tag == PM_ITEM_LINE) {  // metal:223-247
@@ -329,7 +369,6 @@ struct FineWarpSmem {
     int cov[16 * PM_ACC_STRIDE];     // per-row cover deltas (pixel x and everything right of it)
     float dmin[16 * PM_ACC_STRIDE];  // stroke distance field
     uint32_t idx[PM_FINE_LIST_CAP];  // pool indices of the tile's records
-    uint32_t item[PM_FINE_LIST_CAP]; // their item ids (0xffffffff: below the opaque cover, ignored)
 };
 
 struct FineAcc {
@@ -341,26 +380,27 @@ struct FineAcc {
     }
 };
 
-__device__ __noinline__ float srgb_pow_exact(float v) { return powf(v, 1.0f / 2.4f); }
-
-__device__ __forceinline__ float linear_to_srgb(float v, bool exact) {  // metal:563
+template <bool EXACT>
+__device__ __forceinline__ float linear_to_srgb(float v) {  // metal:563
     if (v < 0.0031308f) return 12.92f * v;
     // default: ex2(lg2(v) / 2.4) on the SFU, a few 1e-7 from powf; PM_FLAG_EXACT_SRGB asks for powf
-    float p = exact ? srgb_pow_exact(v) : exp2f(__log2f(v) * (1.0f / 2.4f));
+    float p = EXACT ? powf(v, 1.0f / 2.4f) : exp2f(__log2f(v) * (1.0f / 2.4f));
     return 1.055f * p - 0.055f;
 }
 
 // Linear -> sRGB for one pixel, packed RGBA8 (alpha 255).  Out of line: 8 call sites per tile.
-__device__ __noinline__ uint32_t encode_pixel(float r, float g, float b, bool exact) {
-    return pm_unorm8(linear_to_srgb(r, exact)) | (pm_unorm8(linear_to_srgb(g, exact)) << 8) |
-           (pm_unorm8(linear_to_srgb(b, exact)) << 16) | 0xff000000u;
+template <bool EXACT>
+__device__ __noinline__ uint32_t encode_pixel(float r, float g, float b) {
+    return pm_unorm8(linear_to_srgb<EXACT>(r)) | (pm_unorm8(linear_to_srgb<EXACT>(g)) << 8) |
+           (pm_unorm8(linear_to_srgb<EXACT>(b)) << 16) | 0xff000000u;
 }
 
-__device__ __forceinline__ void unpack_fg(const float *lut, uint32_t rgba, float fg[4]) {  // unpack_unorm4x8_srgb_to_half
+// lut[0..255]: sRGB byte -> linear; lut[256..511]: alpha byte / 255 (unpack_unorm4x8_srgb_to_half)
+__device__ __forceinline__ void unpack_fg(const float *lut, uint32_t rgba, float fg[4]) {
     fg[0] = lut[rgba & 0xffu];
     fg[1] = lut[(rgba >> 8) & 0xffu];
     fg[2] = lut[(rgba >> 16) & 0xffu];
-    fg[3] = (float)(rgba >> 24) / 255.0f;
+    fg[3] = lut[256u + (rgba >> 24)];
 }
 
 __device__ __forceinline__ PmRecord load_record(const PmRecord *pool, uint32_t idx) {
@@ -376,7 +416,7 @@ __device__ __forceinline__ PmRecord load_record(const PmRecord *pool, uint32_t i
 // the current item): the (record, pixel row) pairs are enumerated across the lanes and each lane
 // adds its pair's coverage / distance into shared memory.
 __device__ __noinline__ void fine_pairs(FineAcc &acc, bool mine, const PmRecord &r, bool stroke, float reach,
-                                           float tile_x0, float tile_y0, uint32_t lane) {
+                                        float tile_x0, float tile_y0, uint32_t lane) {
     const uint32_t kind = r.key & 15u;
     int ra = 1, rb = 0;
     if (mine) {
@@ -418,21 +458,23 @@ __device__ __noinline__ void fine_pairs(FineAcc &acc, bool mine, const PmRecord 
     }
 }
 
-// One tile that owns records.  All 32 lanes execute this together.  Blend/store layout: lane l owns
-// pixel row (l >> 1), pixels 8*(l & 1) .. +7.
-template <bool F32>
+// One tile that owns records.  All 32 lanes execute this together.  Records are handled in chunks
+// of 32, one per lane; the first chunk (all of them, for nearly every tile) stays in registers.
+// Blend/store layout: lane l owns pixel row (l >> 1), pixels 8*(l & 1) .. +7.
+template <bool F32, bool EXACT>
 __device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t tile, FineWarpSmem *w, const float *lut, uint32_t lane) {
     const u64 cw = A.cnt[tile], ow = A.occ[tile];
     const uint32_t n = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
     const uint32_t occ_item1 = (uint32_t)(ow >> 32) == A.stamp ? (uint32_t)ow : 0u;
+
     // index the records: inline slots first, then the overflow chain.  n_cached counts what was
     // actually found (a frame whose overflow pool ran out has fewer links than cnt says; the host
     // re-renders such a frame, it only must not fault).
     const uint32_t n_inline = n < PM_TILE_SLOTS ? n : PM_TILE_SLOTS;
-    if (lane < n_inline) w->idx[lane] = tile * PM_TILE_SLOTS + lane;
     uint32_t n_cached = n_inline;
     uint32_t tail = 0;  // 1 + pool index of the first record that did not fit the shared-memory index
     if (n > PM_TILE_SLOTS) {
+        if (lane < PM_TILE_SLOTS) w->idx[lane] = tile * PM_TILE_SLOTS + lane;
         const u64 vw = A.ovf[tile];
         uint32_t cur = (uint32_t)(vw >> 32) == A.stamp ? (uint32_t)vw : 0u;
         while (cur != 0 && n_cached < PM_FINE_LIST_CAP) {
@@ -441,21 +483,28 @@ __device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t tile, FineWarpS
             n_cached++;
         }
         tail = cur;
+        __syncwarp();
     }
-    __syncwarp();
-    bool has_draw = false;
-    for (uint32_t i = lane; i < n_cached; i += 32) {
-        const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[w->idx[i]]);
-        const bool live = ik.x >= occ_item1;  // below the topmost opaque cover: rewound away (metal:132-135)
-        w->item[i] = live ? ik.x : 0xffffffffu;
-        if (live && (ik.y & 15u) != PM_REC_SOLID) has_draw = true;
+    const uint32_t n_chunks = (n_cached + 31u) >> 5;
+    // chunk 0 lives in registers for the whole tile
+    PmRecord r0;
+    r0.item = 0xffffffffu; r0.key = 0; r0.p[0] = r0.p[1] = r0.p[2] = r0.p[3] = 0.0f; r0.edge_y = 0.0f; r0.next = 0;
+    if (lane < n_cached) r0 = load_record(A.pool, n > PM_TILE_SLOTS ? w->idx[lane] : tile * PM_TILE_SLOTS + lane);
+    if (r0.item < occ_item1) r0.item = 0xffffffffu;  // below the topmost opaque cover: rewound away (metal:132-135)
+
+    bool has_draw = r0.item != 0xffffffffu && (r0.key & 15u) != PM_REC_SOLID;
+    for (uint32_t c = 1; c < n_chunks; c++) {
+        const uint32_t i = c * 32u + lane;
+        if (i < n_cached) {
+            const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[w->idx[i]]);
+            if (ik.x >= occ_item1 && (ik.y & 15u) != PM_REC_SOLID) has_draw = true;
+        }
     }
     for (uint32_t cur = tail; cur != 0; cur = A.pool[cur - 1u].next) {
         const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[cur - 1u]);
         if (ik.x >= occ_item1 && (ik.y & 15u) != PM_REC_SOLID) has_draw = true;
     }
     has_draw = __any_sync(PM_FULL_MASK, has_draw);
-    __syncwarp();
 
     const uint32_t trow = tile / A.n_tx, tx = tile - trow * A.n_tx;
     const uint32_t prow = lane >> 1, half = lane & 1u;
@@ -503,28 +552,32 @@ __device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t tile, FineWarpS
     uint32_t last_item = 0;
     bool first = true;
     for (;;) {
-        uint32_t cur_item = 0xffffffffu;
-        for (uint32_t i = lane; i < n_cached; i += 32) {
-            uint32_t it = w->item[i];
-            if ((first || it > last_item) && it < cur_item) cur_item = it;
+        uint32_t cur_item = (first || r0.item > last_item) ? r0.item : 0xffffffffu;
+        for (uint32_t c = 1; c < n_chunks; c++) {
+            const uint32_t i = c * 32u + lane;
+            if (i < n_cached) {
+                const uint32_t it = A.pool[w->idx[i]].item;
+                if (it >= occ_item1 && (first || it > last_item) && it < cur_item) cur_item = it;
+            }
         }
         for (uint32_t cur = tail; cur != 0; cur = A.pool[cur - 1u].next) {
-            uint32_t it = A.pool[cur - 1u].item;
+            const uint32_t it = A.pool[cur - 1u].item;
             if (it >= occ_item1 && (first || it > last_item) && it < cur_item) cur_item = it;
         }
-        #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cur_item = min(cur_item, __shfl_xor_sync(PM_FULL_MASK, cur_item, o));
+        cur_item = __reduce_min_sync(PM_FULL_MASK, cur_item);
         if (cur_item == 0xffffffffu) break;
         first = false;
         last_item = cur_item;
 
         // the item's closing record says what it is (DrawFill / Stroke / Circle / Solid)
         uint32_t t_kind = 0, t_w0 = 0, t_w1 = 0;
-        for (uint32_t i = lane; i < n_cached; i += 32) {
-            if (w->item[i] != cur_item) continue;
-            const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[w->idx[i]]);
-            const uint32_t k = a.y & 15u;
-            if (k >= PM_REC_CIRCLE) { t_kind = k; t_w0 = a.z; t_w1 = a.w; }
+        if (r0.item == cur_item && (r0.key & 15u) >= PM_REC_CIRCLE) { t_kind = r0.key & 15u; t_w0 = pm_f2u(r0.p[0]); t_w1 = pm_f2u(r0.p[1]); }
+        for (uint32_t c = 1; c < n_chunks; c++) {
+            const uint32_t i = c * 32u + lane;
+            if (i < n_cached) {
+                const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[w->idx[i]]);
+                if (a.x == cur_item && (a.y & 15u) >= PM_REC_CIRCLE) { t_kind = a.y & 15u; t_w0 = a.z; t_w1 = a.w; }
+            }
         }
         for (uint32_t cur = tail; cur != 0; cur = A.pool[cur - 1u].next) {
             const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[cur - 1u]);
@@ -546,21 +599,20 @@ __device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t tile, FineWarpS
             const float half_width = pm_u2f(t_w0);
             const float reach = half_width + 0.5f;
             // phase A: coverage of the item's segments, 32 records at a time
-            for (uint32_t base = 0; base < n_cached; base += 32) {
-                const uint32_t i = base + lane;
-                bool mine = i < n_cached && w->item[i] == cur_item;
-                PmRecord r;
-                r.key = 0; r.p[0] = r.p[1] = r.p[2] = r.p[3] = 0.0f; r.edge_y = 0.0f;
-                if (mine) {
-                    r = load_record(A.pool, w->idx[i]);
-                    mine = (r.key & 15u) <= PM_REC_LINE;
+            for (uint32_t c = 0; c < n_chunks; c++) {
+                PmRecord rc = r0;
+                if (c > 0) {
+                    const uint32_t i = c * 32u + lane;
+                    rc.item = 0xffffffffu;
+                    if (i < n_cached) rc = load_record(A.pool, w->idx[i]);
                 }
-                if (__any_sync(PM_FULL_MASK, mine)) fine_pairs(acc, mine, r, stroke, reach, tile_x0, tile_y0, lane);
+                const bool mine = rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE;
+                if (__any_sync(PM_FULL_MASK, mine)) fine_pairs(acc, mine, rc, stroke, reach, tile_x0, tile_y0, lane);
             }
             for (uint32_t cur = tail; cur != 0;) {  // records beyond the shared-memory index, one at a time
-                PmRecord r = load_record(A.pool, cur - 1u);
-                cur = r.next;
-                if (r.item == cur_item && (r.key & 15u) <= PM_REC_LINE) fine_pairs(acc, lane == 0, r, stroke, reach, tile_x0, tile_y0, lane);
+                PmRecord rc = load_record(A.pool, cur - 1u);
+                cur = rc.next;
+                if (rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE) fine_pairs(acc, lane == 0, rc, stroke, reach, tile_x0, tile_y0, lane);
             }
             __syncwarp();
             // phase B: resolve this lane's 8 pixels
@@ -604,13 +656,12 @@ __device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t tile, FineWarpS
             for (int k = 0; k < 3; k++) rgb[j][k] = pm_mix(rgb[j][k], fg[k], alpha[j]);
     }
 
-    const bool exact = (A.flags & PM_FLAG_EXACT_SRGB) != 0;
     uint32_t packed[8];
     #pragma unroll
     for (int j = 0; j < 8; j++) {
-        packed[j] = encode_pixel(rgb[j][0], rgb[j][1], rgb[j][2], exact);
+        packed[j] = encode_pixel<EXACT>(rgb[j][0], rgb[j][1], rgb[j][2]);
         if (F32)  // debug render: the un-quantised values
-            dst32[j] = make_float4(linear_to_srgb(rgb[j][0], exact), linear_to_srgb(rgb[j][1], exact), linear_to_srgb(rgb[j][2], exact), 1.0f);
+            dst32[j] = make_float4(linear_to_srgb<EXACT>(rgb[j][0]), linear_to_srgb<EXACT>(rgb[j][1]), linear_to_srgb<EXACT>(rgb[j][2]), 1.0f);
     }
     reinterpret_cast<uint4 *>(dst)[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     reinterpret_cast<uint4 *>(dst)[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
@@ -657,12 +708,12 @@ __device__ void fine_solid_batch(const PmFrameArgs &A, uint32_t batch, uint32_t 
     }
 }
 
-template <bool F32>
-__global__ void __launch_bounds__(PM_FINE_WARPS * 32) k_fine(const PmFrameArgs A) {
-    __shared__ float s_lut[256];
+template <bool F32, bool EXACT>
+__global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArgs A) {
+    __shared__ float s_lut[512];
     __shared__ FineWarpSmem s_warp[PM_FINE_WARPS];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = A.srgb_lut[i];
+    for (uint32_t i = threadIdx.x; i < 512; i += blockDim.x) s_lut[i] = A.srgb_lut[i];
     FineWarpSmem *w = &s_warp[warp];
     for (uint32_t i = lane; i < 16 * PM_ACC_STRIDE; i += 32) { w->acc[i] = 0; w->cov[i] = 0; w->dmin[i] = 1e9f; }
     const uint32_t n_complex = A.counters->n_complex;
@@ -685,7 +736,7 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32) k_fine(const PmFrameArgs A
         q = __shfl_sync(PM_FULL_MASK, q, 0);
         if (take_complex) {
             if (q >= n_complex) { complex_left = false; continue; }
-            fine_complex_tile<F32>(A, A.complex_list[q], w, s_lut, lane);
+            fine_complex_tile<F32, EXACT>(A, A.complex_list[q], w, s_lut, lane);
         } else {
             if (q >= n_batches) { batches_left = false; continue; }
             fine_solid_batch<F32>(A, q, batches_per_row, lane);
@@ -708,7 +759,7 @@ void pm_launch_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, u
 }
 
 static size_t bin_smem_bytes(uint32_t n_tx, int *warps_per_cta) {
-    size_t per_warp = (size_t)(n_tx + 1) * sizeof(uint32_t);
+    size_t per_warp = (size_t)(n_tx + 1 + PM_BIN_PEND) * sizeof(uint32_t);
     int warps = 8;
     while (warps > 1 && per_warp * warps > 160 * 1024) warps >>= 1;
     *warps_per_cta = warps;
@@ -739,6 +790,12 @@ void pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, cudaSt
     if (mid) cudaEventRecord(mid, s);
     // persistent fill kernel: enough CTAs to fill every SM, work pulled from two queues
     int grid = sm_count * 4;
-    if (a.fb32) k_fine<true><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
-    else        k_fine<false><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
+    const bool exact = (a.flags & PM_FLAG_EXACT_SRGB) != 0;
+    if (a.fb32) {  // debug render with the fp32 parity buffer
+        if (exact) k_fine<true, true><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
+        else       k_fine<true, false><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
+    } else {
+        if (exact) k_fine<false, true><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
+        else       k_fine<false, false><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
+    }
 }

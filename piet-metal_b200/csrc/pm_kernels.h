@@ -52,7 +52,7 @@ struct PmFrameArgs {
     size_t pitch;
     float *fb32;                // optional fp32 RGBA strip (debug renders)
     size_t pitch32;
-    const float *srgb_lut;      // 256 floats: sRGB byte -> linear
+    const float *srgb_lut;      // 512 floats: [0,256) sRGB byte -> linear, [256,512) alpha byte / 255
 };
 
 struct PmPlanResult { uint32_t n_units; uint32_t error; };

@@ -291,14 +291,14 @@ int pm_renderer_create(pm_renderer **out, const pm_config *cfg) {
     PM_TRY(cudaMalloc(&r->queue, sizeof(PmFineQueue)));
     PM_TRY(cudaMalloc(&r->dev_err, sizeof(uint32_t)));
     PM_TRY(cudaMalloc(&r->dev_plan, sizeof(PmPlanResult)));
-    PM_TRY(cudaMalloc(&r->lut, 256 * sizeof(float)));
+    PM_TRY(cudaMalloc(&r->lut, 512 * sizeof(float)));
     PM_TRY(cudaHostAlloc(&r->report, sizeof(PmFrameReport), cudaHostAllocMapped));
     memset(r->report, 0, sizeof(PmFrameReport));
     PM_TRY(cudaHostGetDevicePointer(&r->report_dev, r->report, 0));
     PM_TRY(cudaMemsetAsync(r->counters, 0, 2 * sizeof(PmBinCounters), r->stream));
     PM_TRY(cudaMemsetAsync(r->queue, 0, sizeof(PmFineQueue), r->stream));
-    float lut[256];
-    for (int i = 0; i < 256; i++) lut[i] = pm_srgb_byte_to_linear((uint32_t)i);
+    float lut[512];  // [0,256): sRGB byte -> linear; [256,512): alpha byte / 255
+    for (int i = 0; i < 256; i++) { lut[i] = pm_srgb_byte_to_linear((uint32_t)i); lut[256 + i] = (float)i / 255.0f; }
     PM_TRY(cudaMemcpyAsync(r->lut, lut, sizeof lut, cudaMemcpyHostToDevice, r->stream));
     PM_TRY(cudaStreamSynchronize(r->stream));
 #undef PM_TRY
