@@ -309,7 +309,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": fb_bytes,
                     "steps": args.e2e_steps, "call": "pm_renderer_render_host (pinned host buffers)"},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": 3 * args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_fine (fill/blend)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": fine_ms,

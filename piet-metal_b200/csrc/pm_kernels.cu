@@ -67,92 +67,200 @@ __global__ void k_validate(const uint8_t *scene, uint32_t len, uint32_t *err) {
     }
 }
 
+typedef unsigned long long u64;
+
 // ---------------------------------------------------------------------------------------------
-// k_plan: one work unit per (item, tile row of its bbox inside the strip)
+// k_plan: per-item prefixes for the two binning kernels (once per scene / size / strip)
+//   plan_a[i]  low 32 bits: segments of items < i (k_seg: one thread per segment)
+//              high 32 bits: (tile row, 32-tile chunk) pairs of items < i (k_row: one warp each)
+//   plan_b[i]  words of the backdrop scratch before item i: rows * (tile span + 1) per item
+// Items that do not touch the strip count nothing.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t item_row_count(const uint8_t *scene, uint32_t items_ix, uint32_t i, uint32_t tile_y0,
-                                                   uint32_t tile_y1, uint32_t n_tx) {
+struct ItemSpan { uint32_t tag, r_lo, rows, t_lo, t_hi, n_points; };
+
+__device__ __forceinline__ ItemSpan item_span(const uint8_t *scene, uint32_t items_ix, uint32_t i, uint32_t tile_y0,
+                                              uint32_t tile_y1, uint32_t n_tx) {
+    ItemSpan sp;
     const pm_bbox bb = *reinterpret_cast<const pm_bbox *>(scene + PM_GROUP_HEADER_SIZE + (size_t)i * PM_BBOX_SIZE);
-    uint32_t tag = ld_u32(scene + items_ix + (size_t)i * PM_ITEM_SIZE);
-    if (tag < PM_ITEM_CIRCLE || tag > PM_ITEM_POLY) return 0;
+    const uint8_t *it = scene + items_ix + (size_t)i * PM_ITEM_SIZE;
+    sp.tag = ld_u32(it);
+    sp.rows = 0;
+    sp.n_points = (sp.tag == PM_ITEM_FILL || sp.tag == PM_ITEM_POLY) ? ld_u32(it + PM_FILL_NPOINTS) : 1u;
     // `hit` (metal:214): bbox.z >= x0 && bbox.x < x0 + 16 && bbox.w >= y0 && bbox.y < y0 + 16
     // <=> tile column in [bbox.x >> 4, bbox.z >> 4] and tile row in [bbox.y >> 4, bbox.w >> 4]
-    uint32_t t_lo = bb.x0 >> 4, t_hi = bb.x1 >> 4;
-    if (t_lo >= n_tx || t_hi < t_lo) return 0;
+    sp.t_lo = bb.x0 >> 4;
+    sp.t_hi = bb.x1 >> 4;
     uint32_t r_lo = bb.y0 >> 4, r_hi = bb.y1 >> 4;
     if (r_lo < tile_y0) r_lo = tile_y0;
     if (r_hi >= tile_y1) r_hi = tile_y1 - 1;  // tile_y1 > tile_y0 >= 0
-    if (r_hi < r_lo) return 0;
-    return r_hi - r_lo + 1;
+    sp.r_lo = r_lo;
+    if (sp.tag < PM_ITEM_CIRCLE || sp.tag > PM_ITEM_POLY) return sp;
+    if (sp.t_lo >= n_tx || sp.t_hi < sp.t_lo || r_hi < r_lo) return sp;
+    if (sp.t_hi > n_tx - 1) sp.t_hi = n_tx - 1;
+    sp.rows = r_hi - r_lo + 1;
+    return sp;
+}
+
+// block-wide inclusive scan of one u64 per thread (1024 threads); returns the exclusive value and the block total
+__device__ __forceinline__ u64 block_scan_excl(u64 v, u64 *warp_excl, u64 *block_total) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        u64 t = __shfl_up_sync(PM_FULL_MASK, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) warp_excl[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        u64 ws = warp_excl[lane], wi = ws;
+        for (int o = 1; o < 32; o <<= 1) {
+            u64 t = __shfl_up_sync(PM_FULL_MASK, wi, o);
+            if (lane >= (uint32_t)o) wi += t;
+        }
+        warp_excl[lane] = wi - ws;
+        if (lane == 31) *block_total = wi;
+    }
+    __syncthreads();
+    u64 r = warp_excl[warp] + incl - v;
+    __syncthreads();
+    return r;
 }
 
 __global__ void __launch_bounds__(1024) k_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0,
-                                               uint32_t tile_y1, uint32_t n_tx, uint32_t *unit_base, PmPlanResult *result) {
-    __shared__ uint32_t warp_excl[32];
-    __shared__ uint32_t block_total;
-    __shared__ uint32_t carry_s;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry_s = 0;
+                                               uint32_t tile_y1, uint32_t n_tx, u64 *plan_a, u64 *plan_b, PmPlanResult *result) {
+    __shared__ u64 warp_excl[32];
+    __shared__ u64 total_a, total_b, carry_a, carry_b;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) { carry_a = 0; carry_b = 0; }
     __syncthreads();
     for (uint32_t base = 0; base < n_items; base += blockDim.x) {
-        uint32_t i = base + tid;
-        uint32_t cnt = i < n_items ? item_row_count(scene, items_ix, i, tile_y0, tile_y1, n_tx) : 0;
-        uint32_t incl = cnt;
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t v = __shfl_up_sync(PM_FULL_MASK, incl, o);
-            if (lane >= (uint32_t)o) incl += v;
-        }
-        if (lane == 31) warp_excl[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t ws = warp_excl[lane];
-            uint32_t wi = ws;
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t v = __shfl_up_sync(PM_FULL_MASK, wi, o);
-                if (lane >= (uint32_t)o) wi += v;
+        const uint32_t i = base + tid;
+        u64 ca = 0, cb = 0;
+        if (i < n_items) {
+            const ItemSpan sp = item_span(scene, items_ix, i, tile_y0, tile_y1, n_tx);
+            if (sp.rows) {
+                const uint32_t n_seg = sp.tag == PM_ITEM_FILL ? sp.n_points : (sp.tag == PM_ITEM_POLY ? sp.n_points - 1u : 0u);
+                ca = ((u64)(sp.rows * ((sp.t_hi - sp.t_lo + 32u) / 32u)) << 32) | n_seg;  // rows x 32-tile chunks
+                if (sp.tag == PM_ITEM_FILL || sp.tag == PM_ITEM_POLY) cb = (u64)sp.rows * (sp.t_hi - sp.t_lo + 2u);
             }
-            warp_excl[lane] = wi - ws;
-            if (lane == 31) block_total = wi;
         }
+        const u64 ea = carry_a + block_scan_excl(ca, warp_excl, &total_a);
+        const u64 eb = carry_b + block_scan_excl(cb, warp_excl, &total_b);
+        if (i < n_items) { plan_a[i] = ea; plan_b[i] = eb; }
+        // a carry out of the low half (or 2^31 in either half) would corrupt the packed prefixes
+        if (((ea + ca) & 0x8000000080000000ull) != 0) result->error = 1;
         __syncthreads();
-        uint32_t excl = carry_s + warp_excl[warp] + incl - cnt;
-        if (i < n_items) unit_base[i] = excl;
-        if (excl + cnt < excl) result->error = 1;  // more than 2^32 work units
-        __syncthreads();
-        if (tid == 0) carry_s += block_total;
+        if (tid == 0) { carry_a += total_a; carry_b += total_b; }
         __syncthreads();
     }
     if (tid == 0) {
-        unit_base[n_items] = carry_s;
-        result->n_units = carry_s;
+        plan_a[n_items] = carry_a;
+        plan_b[n_items] = carry_b;
+        result->n_segments = (uint32_t)carry_a;
+        result->n_rows = (uint32_t)(carry_a >> 32);
+        result->bd_words = carry_b;
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// k_bin
-// ---------------------------------------------------------------------------------------------
-typedef unsigned long long u64;
+// One segment of a Fill / Poly item and the tile rows of the strip it can reach.  For a Fill the
+// range is exact (rows with mxy >= y0 && mny < y0 + 16: division by 16 and floor are exact); for a
+// Poly it is conservative and pm_poly_segment_row applies the exact y test.
+struct SegCtx { ItemSpan sp; PmSeg sg; float hw; int ra, rb; };
 
-// Claims the next record slot of a tile for this frame: returns its position (0 for the first).
-// cnt word = stamp << 32 | count; a word with another stamp is a leftover of an earlier frame.
-__device__ __forceinline__ uint32_t tile_claim_slot(u64 *word, uint32_t stamp) {
-    u64 old = atomicAdd(word, 1ull);
-    if ((uint32_t)(old >> 32) == stamp) return (uint32_t)old;
-    u64 v = old + 1ull;  // we bumped a stale word: race to (re)initialise it
-    for (;;) {
-        if ((uint32_t)(v >> 32) == stamp) {  // somebody else initialised it (our bump went with the stale word)
-            old = atomicAdd(word, 1ull);
-            return (uint32_t)old;
+__device__ __forceinline__ SegCtx load_segment(const uint8_t *scene, uint32_t items_ix, uint32_t item, uint32_t k, uint32_t tile_y0,
+                                               uint32_t tile_y1, uint32_t n_tx) {
+    SegCtx c;
+    c.sp = item_span(scene, items_ix, item, tile_y0, tile_y1, n_tx);
+    const uint8_t *it = scene + items_ix + (size_t)item * PM_ITEM_SIZE;
+    const uint8_t *pts = scene + ld_u32(it + PM_FILL_POINTS_IX);  // same offset in both variants
+    const float2 s = ld_f2(pts + 8 * (size_t)k);
+    c.hw = 0.0f;
+    if (c.sp.tag == PM_ITEM_FILL) {
+        const float2 e = ld_f2(pts + 8 * (size_t)(k + 1 == c.sp.n_points ? 0 : k + 1));  // closing segment, metal:262
+        c.sg = pm_seg(s.x, s.y, e.x, e.y);
+        c.ra = pm_floor_i(c.sg.mny * (1.0f / 16.0f));
+        c.rb = pm_floor_i(c.sg.mxy * (1.0f / 16.0f));
+    } else {
+        const float2 e = ld_f2(pts + 8 * (size_t)(k + 1));
+        c.sg = pm_seg(s.x, s.y, e.x, e.y);
+        c.hw = 0.5f * ld_f32(it + PM_POLY_WIDTH) + 0.5f;
+        c.ra = pm_floor_i((c.sg.mny - c.hw) * (1.0f / 16.0f)) - 1;
+        c.rb = pm_floor_i((c.sg.mxy + c.hw) * (1.0f / 16.0f)) + 1;
+    }
+    const int r_first = (int)c.sp.r_lo, r_last = (int)(c.sp.r_lo + c.sp.rows) - 1;
+    if (c.ra < r_first) c.ra = r_first;
+    if (c.rb > r_last) c.rb = r_last;
+    return c;
+}
+
+__device__ __forceinline__ uint32_t item_of_segment(const u64 *plan_a, uint32_t n_items, uint32_t g) {
+    uint32_t lo = 0, hi = n_items;
+    while (hi - lo > 1) {  // largest i with segment prefix <= g
+        uint32_t mid = (lo + hi) >> 1;
+        if ((uint32_t)plan_a[mid] <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// pair_prefix[g] = number of (segment, tile row) pairs of the segments before g: k_seg runs one
+// thread per pair, so that a long segment crossing hundreds of rows is spread over as many threads.
+__global__ void __launch_bounds__(1024) k_plan_pairs(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0,
+                                                     uint32_t tile_y1, uint32_t n_tx, const u64 *plan_a, uint32_t n_segments,
+                                                     uint32_t *pair_prefix, uint32_t *seg_item, uint2 *pair_info, uint32_t pair_cap,
+                                                     PmPlanResult *result) {
+    __shared__ u64 warp_excl[32];
+    __shared__ u64 total, carry;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_segments; base += blockDim.x) {
+        const uint32_t g = base + tid;
+        u64 cnt = 0;
+        int ra = 0;
+        if (g < n_segments) {
+            const uint32_t item = item_of_segment(plan_a, n_items, g);
+            const SegCtx c = load_segment(scene, items_ix, item, g - (uint32_t)plan_a[item], tile_y0, tile_y1, n_tx);
+            if (c.rb >= c.ra) cnt = (u64)(c.rb - c.ra + 1);
+            ra = c.ra;
+            seg_item[g] = item;
         }
-        u64 prev = atomicCAS(word, v, ((u64)stamp << 32) | 1ull);
-        if (prev == v) return 0;
-        v = prev;
+        const u64 e = carry + block_scan_excl(cnt, warp_excl, &total);
+        if (g < n_segments) {
+            pair_prefix[g] = (uint32_t)e;
+            // second pass (pair_info given): the (segment, row) of every pair, so that k_seg needs no search
+            if (pair_info)
+                for (u64 j = 0; j < cnt && e + j < pair_cap; j++) pair_info[e + j] = make_uint2(g, (uint32_t)(ra + (int)j));
+        }
+        if (e + cnt >= 0x80000000ull) result->error = 1;
+        __syncthreads();
+        if (tid == 0) carry += total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        pair_prefix[n_segments] = (uint32_t)carry;
+        result->n_pairs = (uint32_t)carry;
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_seg + k_row: binning
+// ---------------------------------------------------------------------------------------------
+// Claims the next record slot of a tile for this frame: returns its position (0 for the first).
+// cnt word = stamp << 32 | count.  The atomic max lifts a leftover of an earlier frame (smaller
+// stamp) to (stamp, 0) and leaves a current word alone; the add that follows from the same thread
+// to the same address is ordered after it, so it always sees this frame's stamp.  No CAS loop:
+// a tile that many segments hit at once would make one quadratic in the number of contenders.
+__device__ __forceinline__ uint32_t tile_claim_slot(u64 *word, uint32_t stamp) {
+    atomicMax(word, (u64)stamp << 32);
+    return (uint32_t)atomicAdd(word, 1ull);
+}
+
+// Where the exact tile tests of one (item, tile row) send their results.  bd is the row's slice of
+// the backdrop scratch: word j <-> tile t_lo + j; bit 0 = "the item has a command in this tile",
+// bits 1.. = 2 * (backdrop delta at this tile, difference-encoded along the row).
 struct BinSink {
     const PmFrameArgs &A;
-    uint32_t *sm;        // per-warp: word j <-> tile t_lo + j; bit 0 = "has a command", bits 1.. = 2 * backdrop delta
+    uint32_t *bd;
     uint32_t t_lo;
     uint32_t row_tile0;  // index of the row's first tile
     uint32_t item;
@@ -165,7 +273,11 @@ struct BinSink {
         if (pos < PM_TILE_SLOTS) {
             idx = tile * PM_TILE_SLOTS + pos;
         } else {
-            uint32_t o = atomicAdd(&A.counters->n_overflow, 1u);
+            // one counter serves every overflow record of the frame: aggregate the lanes that are here together
+            cg::coalesced_group og = cg::coalesced_threads();
+            uint32_t o = 0;
+            if (og.thread_rank() == 0) o = atomicAdd(&A.counters->n_overflow, og.size());
+            o = og.shfl(o, 0) + og.thread_rank();
             if (o >= A.overflow_cap) return;  // the host sees n_overflow > overflow_cap, grows the pool and re-renders
             idx = A.n_rows * A.n_tx * PM_TILE_SLOTS + o;
             u64 prev = atomicExch(&A.ovf[tile], ((u64)A.stamp << 32) | (u64)(idx + 1u));
@@ -180,178 +292,166 @@ struct BinSink {
             uint32_t base = 0;
             if (g.thread_rank() == 0) base = atomicAdd(&A.counters->n_complex, g.size());
             base = g.shfl(base, 0);
-            A.complex_list[base + g.thread_rank()] = tile;
+            A.complex_list[base + g.thread_rank()] = ((tile - t) / A.n_tx << 16) | t;  // (strip-local tile row, tile column)
         }
     }
     __device__ __forceinline__ void fill(uint32_t t, uint32_t seg, const PmFillEmit &e, const PmSeg &g) {
         append(t, pm_rec_fill(item, seg, t, e, g));
-        atomicOr(&sm[t - t_lo], 1u);
+        atomicOr(&bd[t - t_lo], 1u);
     }
     __device__ __forceinline__ void backdrop(uint32_t ta, uint32_t tb, int delta) {
-        atomicAdd(&sm[ta - t_lo], (uint32_t)(2 * delta));
-        atomicAdd(&sm[tb + 1 - t_lo], (uint32_t)(-2 * delta));
+        atomicAdd(&bd[ta - t_lo], (uint32_t)(2 * delta));
+        atomicAdd(&bd[tb + 1 - t_lo], (uint32_t)(-2 * delta));
     }
     __device__ __forceinline__ void line(uint32_t t, uint32_t seg, const PmSeg &g) {
         append(t, pm_rec_line(item, seg, g));
-        atomicOr(&sm[t - t_lo], 1u);
+        atomicOr(&bd[t - t_lo], 1u);
     }
     __device__ __forceinline__ void trailer(uint32_t t, uint32_t kind, uint32_t seg, uint32_t w0, uint32_t w1) {
         append(t, pm_rec_words(item, kind, seg, w0, w1));
     }
 };
 
-#define PM_BIN_UNROLL 4   // point loads in flight per lane while scanning an item's segments
-#define PM_BIN_PEND (32 * (PM_BIN_UNROLL + 1))   // pending (row-overlapping) segment indices per warp
-
-// Scans the n_seg segments of an item for the ones whose y range reaches this unit's tile row
-// (`overlap(sy, ey)`), compacts their indices and hands them to `process(k)` 32 at a time, so that
-// the expensive exact tests run with all lanes busy.  Order does not matter: every effect of a
-// segment is an atomic add / or / append.
-template <class Overlap, class Process>
-__device__ __forceinline__ void scan_segments(const uint8_t *pts, uint32_t n_seg, uint32_t n_points, uint32_t *pend, uint32_t lane,
-                                              Overlap overlap, Process process) {
-    uint32_t n_pend = 0;
-    for (uint32_t k0 = 0; k0 < n_seg; k0 += 32 * PM_BIN_UNROLL) {
-        float sy[PM_BIN_UNROLL], ey[PM_BIN_UNROLL];
-        #pragma unroll
-        for (int u = 0; u < PM_BIN_UNROLL; u++) {
-            const uint32_t k = k0 + 32u * u + lane;
-            sy[u] = ey[u] = 0.0f;
-            if (k < n_seg) {
-                sy[u] = ld_f32(pts + 8 * (size_t)k + 4);
-                ey[u] = ld_f32(pts + 8 * (size_t)(k + 1 == n_points ? 0 : k + 1) + 4);
-            }
-        }
-        #pragma unroll
-        for (int u = 0; u < PM_BIN_UNROLL; u++) {
-            const uint32_t k = k0 + 32u * u + lane;
-            const bool ov = k < n_seg && overlap(sy[u], ey[u]);
-            const uint32_t mask = __ballot_sync(PM_FULL_MASK, ov);
-            if (ov) pend[n_pend + __popc(mask & ((1u << lane) - 1u))] = k;
-            n_pend += __popc(mask);
-        }
-        __syncwarp();
-        const bool last = k0 + 32 * PM_BIN_UNROLL >= n_seg;
-        while (n_pend >= 32 || (last && n_pend > 0)) {  // the one call site of process()
-            const uint32_t take = n_pend < 32 ? n_pend : 32;
-            if (lane < take) process(pend[n_pend - 1 - lane]);
-            n_pend -= take;
-        }
-        __syncwarp();
-    }
-}
-
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_bin(const PmFrameArgs A) {
-    extern __shared__ uint32_t smem_u32[];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// One thread per (segment, tile row) pair of the Fill / Poly items: the exact tile tests of
+// TestApp/PietRender.metal:248-445 for that segment in that row.  A pair whose segment can reach
+// more than 32 tiles of the row (a long, flat segment) hands its candidate tiles to the whole warp.
+__global__ void __launch_bounds__(256) k_seg(const PmFrameArgs A) {
+    // PM_DEBUG_SEG=1: per-CTA [start, end] in globaltimer ns, two words per CTA
+    struct Timer {
+        const PmFrameArgs &A;
+        __device__ static unsigned long long now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+        __device__ Timer(const PmFrameArgs &a) : A(a) { if (A.debug) atomicMin(&A.debug[2 * blockIdx.x], now()); }
+        __device__ ~Timer() { if (A.debug) atomicMax(&A.debug[2 * blockIdx.x + 1], now()); }
+    } timer(A);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         A.queue->complex_next = 0;
         A.queue->batch_next = 0;
     }
-    const uint32_t unit = blockIdx.x * WARPS + warp;
-    if (unit >= A.n_units) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < A.n_pairs;
+    const bool fixp = (A.flags & PM_FLAG_FIX_POLY_PRECULL) != 0;
+    SegCtx c;
+    c.sp.tag = 0; c.sp.t_lo = c.sp.t_hi = c.sp.r_lo = 0; c.hw = 0.0f;
+    c.sg = pm_seg(0.0f, 0.0f, 0.0f, 0.0f);
+    uint32_t item = 0, k = 0, row = 0, ta = 1, tb = 0;
+    uint32_t *bd = A.bd;
+    if (valid) {
+        const uint2 pi = A.pair_info[p];  // (segment, tile row), tabulated by k_plan_pairs
+        const uint32_t g = pi.x;
+        item = A.seg_item[g];
+        k = g - (uint32_t)A.plan_a[item];
+        c = load_segment(A.scene, A.items_ix, item, k, A.tile_y0, A.tile_y0 + A.n_rows, A.n_tx);
+        row = pi.y;
+        bd = A.bd + A.plan_b[item] + (size_t)(row - c.sp.r_lo) * (c.sp.t_hi - c.sp.t_lo + 2u);
+    }
+    const float y0 = (float)(row * PM_TILE_H);
+    const bool is_fill = c.sp.tag == PM_ITEM_FILL;
+    BinSink sink{A, bd, c.sp.t_lo, (row - A.tile_y0) * A.n_tx, item};
+    bool has_span = false;
+    if (valid) {
+        has_span = is_fill ? pm_fill_candidate_span(c.sg, y0, c.sp.t_lo, c.sp.t_hi, &ta, &tb)
+                           : pm_poly_candidate_span(c.sg, y0, c.hw, c.sp.t_lo, c.sp.t_hi, &ta, &tb);
+        if (is_fill) pm_fill_backdrop_row(sink, c.sg, y0, c.sp.t_lo, c.sp.t_hi, A.n_tx);
+    }
+    const bool wide = has_span && tb - ta >= 32u;
+    if (has_span && !wide) {
+        for (uint32_t t = ta; t <= tb; t++) {
+            if (is_fill) pm_fill_candidate_tile(sink, c.sg, y0, t, k);
+            else pm_poly_candidate_tile(sink, c.sg, y0, c.hw, t, k, fixp);
+        }
+    }
+    // wide spans: one at a time, 32 candidate tiles per step across the warp
+    for (uint32_t wide_mask = __ballot_sync(PM_FULL_MASK, wide); wide_mask != 0; wide_mask &= wide_mask - 1) {
+        const int src = __ffs(wide_mask) - 1;
+        const unsigned long long bd_bits = __shfl_sync(PM_FULL_MASK, (unsigned long long)(uintptr_t)bd, src);
+        BinSink ws{A, reinterpret_cast<uint32_t *>((uintptr_t)bd_bits), __shfl_sync(PM_FULL_MASK, c.sp.t_lo, src),
+                   __shfl_sync(PM_FULL_MASK, sink.row_tile0, src), __shfl_sync(PM_FULL_MASK, item, src)};
+        const PmSeg wg = pm_seg(__shfl_sync(PM_FULL_MASK, c.sg.sx, src), __shfl_sync(PM_FULL_MASK, c.sg.sy, src),
+                                __shfl_sync(PM_FULL_MASK, c.sg.ex, src), __shfl_sync(PM_FULL_MASK, c.sg.ey, src));
+        const float wy0 = __shfl_sync(PM_FULL_MASK, y0, src), whw = __shfl_sync(PM_FULL_MASK, c.hw, src);
+        const uint32_t wk = __shfl_sync(PM_FULL_MASK, k, src);
+        const uint32_t wta = __shfl_sync(PM_FULL_MASK, ta, src), wtb = __shfl_sync(PM_FULL_MASK, tb, src);
+        const bool wfill = __shfl_sync(PM_FULL_MASK, (int)is_fill, src) != 0;
+        for (uint32_t t = wta + lane; t <= wtb; t += 32) {
+            if (wfill) pm_fill_candidate_tile(ws, wg, wy0, t, wk);
+            else pm_poly_candidate_tile(ws, wg, wy0, whw, t, wk, fixp);
+        }
+    }
+}
 
-    // item = largest i with unit_base[i] <= unit
+// One warp per (item, tile row, chunk of 32 tiles): closes what k_seg accumulated -- DrawFill /
+// Solid / opaque cover per tile of a Fill item (metal:359-363), Stroke per tile of a Poly item
+// (metal:441-443).  Line and Circle items have no segments and are binned here directly
+// (metal:218-247).  The scratch is cleared by a memset at the start of the next frame.
+#define PM_ROW_WARPS 8
+__global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t unit = blockIdx.x * PM_ROW_WARPS + warp;
+    if (unit >= A.n_row_units) return;
     uint32_t lo = 0, hi = A.n_items;
-    while (hi - lo > 1) {
+    while (hi - lo > 1) {  // item = largest i with row-chunk prefix <= unit
         uint32_t mid = (lo + hi) >> 1;
-        if (A.unit_base[mid] <= unit) lo = mid; else hi = mid;
+        if ((uint32_t)(A.plan_a[mid] >> 32) <= unit) lo = mid; else hi = mid;
     }
     const uint32_t item = lo;
+    const ItemSpan sp = item_span(A.scene, A.items_ix, item, A.tile_y0, A.tile_y0 + A.n_rows, A.n_tx);
     const uint8_t *it = A.scene + A.items_ix + (size_t)item * PM_ITEM_SIZE;
-    const pm_bbox bb = *reinterpret_cast<const pm_bbox *>(A.scene + PM_GROUP_HEADER_SIZE + (size_t)item * PM_BBOX_SIZE);
-    const uint32_t tag = ld_u32(it);
-    uint32_t r_lo = bb.y0 >> 4;
-    if (r_lo < A.tile_y0) r_lo = A.tile_y0;
-    const uint32_t row = r_lo + (unit - A.unit_base[item]);
-    const uint32_t t_lo = bb.x0 >> 4;
-    uint32_t t_hi = bb.x1 >> 4;
-    if (t_hi > A.n_tx - 1) t_hi = A.n_tx - 1;
-    const uint32_t span = t_hi - t_lo + 1;
+    const uint32_t span = sp.t_hi - sp.t_lo + 1, chunks = (span + 31u) / 32u;
+    const uint32_t local = unit - (uint32_t)(A.plan_a[item] >> 32);
+    const uint32_t row = sp.r_lo + local / chunks, j0 = (local % chunks) * 32u;
+    const uint32_t t_lo = sp.t_lo;
     const float y0 = (float)(row * PM_TILE_H);
+    const uint32_t *bd = A.bd + A.plan_b[item] + (size_t)(row - sp.r_lo) * (span + 1);
+    BinSink sink{A, nullptr, t_lo, (row - A.tile_y0) * A.n_tx, item};
+    const uint32_t j = j0 + lane;
 
-    uint32_t *sm = smem_u32 + (size_t)warp * (A.n_tx + 1 + PM_BIN_PEND);
-    uint32_t *pend = sm + A.n_tx + 1;
-    for (uint32_t j = lane; j <= span; j += 32) sm[j] = 0;
-    __syncwarp();
-
-    BinSink sink{A, sm, t_lo, (row - A.tile_y0) * A.n_tx, item};
-
-    if (tag == PM_ITEM_FILL) {
+    if (sp.tag == PM_ITEM_FILL) {
         const uint32_t rgba = ld_u32(it + PM_FILL_RGBA);
-        const uint32_t n_points = ld_u32(it + PM_FILL_NPOINTS);
-        const uint8_t *pts = A.scene + ld_u32(it + PM_FILL_POINTS_IX);
-        const uint32_t n_tx = A.n_tx;
-        scan_segments(pts, n_points, n_points, pend, lane,
-            [=](float sy, float ey) { return fmaxf(sy, ey) >= y0 && fminf(sy, ey) < y0 + 16.0f; },  // pm_fill_row_overlap
-            [&](uint32_t k) {
-                float2 s = ld_f2(pts + 8 * (size_t)k);
-                float2 e = ld_f2(pts + 8 * (size_t)(k + 1 == n_points ? 0 : k + 1));  // closing segment, metal:262
-                PmSeg g = pm_seg(s.x, s.y, e.x, e.y);
-                pm_fill_segment_row(sink, g, y0, t_lo, t_hi, n_tx, k);
-            });
-        // per-tile epilogue (metal:359-363): DrawFill / Solid / nothing
+        // backdrop entering this chunk: sum of the deltas of the tiles before it
         int carry = 0;
-        for (uint32_t base = 0; base < span; base += 32) {
-            uint32_t j = base + lane;
-            uint32_t v = j < span ? sm[j] : 0u;
-            int d = (int)v >> 1;
-            int incl = d;
-            for (int o = 1; o < 32; o <<= 1) {
-                int u = __shfl_up_sync(PM_FULL_MASK, incl, o);
-                if (lane >= (uint32_t)o) incl += u;
-            }
-            int backdrop = carry + incl;
-            carry = __shfl_sync(PM_FULL_MASK, backdrop, 31);
-            if (j < span) {
-                uint32_t t = t_lo + j;
-                if (v & 1u) {
-                    sink.trailer(t, PM_REC_DRAWFILL, PM_REC_SEG_MAX, (uint32_t)backdrop, rgba);
-                } else if (backdrop != 0) {
-                    if ((rgba & 0xff000000u) == 0xff000000u) {  // opaque full cover: rewinds the tile (metal:132-135)
-                        atomicMax(&A.occ[sink.row_tile0 + t], ((u64)A.stamp << 32) | (u64)(item + 1u));
-                    } else {
-                        sink.trailer(t, PM_REC_SOLID, 0, 0, rgba);
-                    }
+        for (uint32_t q = lane; q < j0; q += 32) carry += (int)bd[q] >> 1;
+        carry = __reduce_add_sync(PM_FULL_MASK, carry);
+        const uint32_t v = j < span ? bd[j] : 0u;
+        int incl = (int)v >> 1;
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(PM_FULL_MASK, incl, o);
+            if (lane >= (uint32_t)o) incl += u;
+        }
+        const int backdrop = carry + incl;
+        if (j < span) {
+            const uint32_t t = t_lo + j;
+            if (v & 1u) {
+                sink.trailer(t, PM_REC_DRAWFILL, PM_REC_SEG_MAX, (uint32_t)backdrop, rgba);
+            } else if (backdrop != 0) {
+                if ((rgba & 0xff000000u) == 0xff000000u) {  // opaque full cover: rewinds the tile (metal:132-135)
+                    atomicMax(&A.occ[sink.row_tile0 + t], ((u64)A.stamp << 32) | (u64)(item + 1u));
+                } else {
+                    sink.trailer(t, PM_REC_SOLID, 0, 0, rgba);
                 }
             }
         }
-    } else if (tag == PM_ITEM_POLY) {
-        const uint32_t rgba = ld_u32(it + PM_POLY_RGBA);
-        const float width = ld_f32(it + PM_POLY_WIDTH);
-        const uint32_t n_points = ld_u32(it + PM_POLY_NPOINTS);
-        const uint32_t n_seg = n_points - 1;  // open polyline, metal:369
-        const uint8_t *pts = A.scene + ld_u32(it + PM_POLY_POINTS_IX);
-        const float hw = 0.5f * width + 0.5f;
-        const bool fix = (A.flags & PM_FLAG_FIX_POLY_PRECULL) != 0;
-        scan_segments(pts, n_seg, n_points + 1, pend, lane,
-            [=](float sy, float ey) { return fmaxf(sy, ey) > y0 - hw && fminf(sy, ey) < y0 + 16.0f + hw; },
-            [&](uint32_t k) {
-                float2 s = ld_f2(pts + 8 * (size_t)k);
-                float2 e = ld_f2(pts + 8 * (size_t)(k + 1));
-                PmSeg g = pm_seg(s.x, s.y, e.x, e.y);
-                pm_poly_segment_row(sink, g, y0, hw, t_lo, t_hi, k, fix);
-            });
-        for (uint32_t j = lane; j < span; j += 32)
-            if (sm[j] & 1u) sink.trailer(t_lo + j, PM_REC_STROKE, PM_REC_SEG_MAX, pm_f2u(0.5f * width), rgba);  // metal:441-443
-    } else if (tag == PM_ITEM_LINE) {  // metal:223-247
+    } else if (sp.tag == PM_ITEM_POLY) {
+        if (j < span && (bd[j] & 1u))
+            sink.trailer(t_lo + j, PM_REC_STROKE, PM_REC_SEG_MAX, pm_f2u(0.5f * ld_f32(it + PM_POLY_WIDTH)), ld_u32(it + PM_POLY_RGBA));
+    } else if (sp.tag == PM_ITEM_LINE) {  // metal:223-247
         const uint32_t rgba = ld_u32(it + PM_LINE_RGBA);
         const float width = ld_f32(it + PM_LINE_WIDTH);
         const float2 s = ld_f2(it + PM_LINE_START), e = ld_f2(it + PM_LINE_END);
         const PmSeg g = pm_seg(s.x, s.y, e.x, e.y);
         const float hw = 0.5f * width + 0.5f;
-        for (uint32_t j = lane; j < span; j += 32) {
-            uint32_t t = t_lo + j;
-            float x0 = (float)(t * PM_TILE_W);
+        if (j < span) {
+            const uint32_t t = t_lo + j;
+            const float x0 = (float)(t * PM_TILE_W);
             if (pm_stroke_cross(g, x0, x0 + 16.0f, y0, y0 + 16.0f, hw)) {
-                sink.line(t, 0, g);
+                sink.append(t, pm_rec_line(item, 0, g));
                 sink.trailer(t, PM_REC_STROKE, PM_REC_SEG_MAX, pm_f2u(0.5f * width), rgba);
             }
         }
-    } else if (tag == PM_ITEM_CIRCLE) {  // metal:218-222
-        uint32_t b_lo = (uint32_t)bb.x0 | ((uint32_t)bb.y0 << 16), b_hi = (uint32_t)bb.x1 | ((uint32_t)bb.y1 << 16);
-        for (uint32_t j = lane; j < span; j += 32) sink.trailer(t_lo + j, PM_REC_CIRCLE, 0, b_lo, b_hi);
+    } else if (sp.tag == PM_ITEM_CIRCLE) {  // metal:218-222
+        const pm_bbox bb = *reinterpret_cast<const pm_bbox *>(A.scene + PM_GROUP_HEADER_SIZE + (size_t)item * PM_BBOX_SIZE);
+        const uint32_t b_lo = (uint32_t)bb.x0 | ((uint32_t)bb.y0 << 16), b_hi = (uint32_t)bb.x1 | ((uint32_t)bb.y1 << 16);
+        if (j < span) sink.trailer(t_lo + j, PM_REC_CIRCLE, 0, b_lo, b_hi);
     }
 }
 
@@ -384,7 +484,15 @@ template <bool EXACT>
 __device__ __forceinline__ float linear_to_srgb(float v) {  // metal:563
     if (v < 0.0031308f) return 12.92f * v;
     // default: ex2(lg2(v) / 2.4) on the SFU, a few 1e-7 from powf; PM_FLAG_EXACT_SRGB asks for powf
-    float p = EXACT ? powf(v, 1.0f / 2.4f) : exp2f(__log2f(v) * (1.0f / 2.4f));
+    float p;
+    if (EXACT) {
+        p = powf(v, 1.0f / 2.4f);
+    } else {  // v in [0.003, ~1]: no denormals, no special cases
+        float l;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(v));
+        l *= 1.0f / 2.4f;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(l));
+    }
     return 1.055f * p - 0.055f;
 }
 
@@ -462,7 +570,9 @@ __device__ __noinline__ void fine_pairs(FineAcc &acc, bool mine, const PmRecord 
 // of 32, one per lane; the first chunk (all of them, for nearly every tile) stays in registers.
 // Blend/store layout: lane l owns pixel row (l >> 1), pixels 8*(l & 1) .. +7.
 template <bool F32, bool EXACT>
-__device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t tile, FineWarpSmem *w, const float *lut, uint32_t lane) {
+__device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t packed_tile, FineWarpSmem *w, const float *lut, uint32_t lane) {
+    const uint32_t trow = packed_tile >> 16, tx = packed_tile & 0xffffu;
+    const uint32_t tile = trow * A.n_tx + tx;
     const u64 cw = A.cnt[tile], ow = A.occ[tile];
     const uint32_t n = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
     const uint32_t occ_item1 = (uint32_t)(ow >> 32) == A.stamp ? (uint32_t)ow : 0u;
@@ -506,7 +616,6 @@ __device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t tile, FineWarpS
     }
     has_draw = __any_sync(PM_FULL_MASK, has_draw);
 
-    const uint32_t trow = tile / A.n_tx, tx = tile - trow * A.n_tx;
     const uint32_t prow = lane >> 1, half = lane & 1u;
     uint8_t *dst = A.fb + (size_t)(trow * PM_TILE_H + prow) * A.pitch + (size_t)(tx * PM_TILE_W + half * 8u) * 4u;
     float4 *dst32 = nullptr;
@@ -520,8 +629,8 @@ __device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t tile, FineWarpS
         // Only Solid commands after the last rewind: the tile Bails and shows solidColor (metal:145-147, :34-44)
         const uint32_t c = occ_rgba;
         const uint4 v = make_uint4(c, c, c, c);
-        reinterpret_cast<uint4 *>(dst)[0] = v;
-        reinterpret_cast<uint4 *>(dst)[1] = v;
+        __stcs(reinterpret_cast<uint4 *>(dst), v);
+        __stcs(reinterpret_cast<uint4 *>(dst) + 1, v);
         if (F32) {
             const float4 f = make_float4((float)(c & 0xff) / 255.0f, (float)((c >> 8) & 0xff) / 255.0f,
                                          (float)((c >> 16) & 0xff) / 255.0f, (float)(c >> 24) / 255.0f);
@@ -663,8 +772,8 @@ __device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t tile, FineWarpS
         if (F32)  // debug render: the un-quantised values
             dst32[j] = make_float4(linear_to_srgb<EXACT>(rgb[j][0]), linear_to_srgb<EXACT>(rgb[j][1]), linear_to_srgb<EXACT>(rgb[j][2]), 1.0f);
     }
-    reinterpret_cast<uint4 *>(dst)[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    reinterpret_cast<uint4 *>(dst)[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+    __stcs(reinterpret_cast<uint4 *>(dst), make_uint4(packed[0], packed[1], packed[2], packed[3]));
+    __stcs(reinterpret_cast<uint4 *>(dst) + 1, make_uint4(packed[4], packed[5], packed[6], packed[7]));
 }
 
 // 32 consecutive tiles of one tile row; the solid ones are written row-wise: each store
@@ -694,7 +803,7 @@ __device__ void fine_solid_batch(const PmFrameArgs &A, uint32_t batch, uint32_t 
         const uint4 v = make_uint4(c, c, c, c);
         uint8_t *dst = A.fb + (size_t)(row * PM_TILE_H) * A.pitch + ((size_t)t0 * PM_TILE_W + (size_t)q * 128u + lane * 4u) * 4u;
         #pragma unroll
-        for (int y = 0; y < PM_TILE_H; y++) *reinterpret_cast<uint4 *>(dst + (size_t)y * A.pitch) = v;
+        for (int y = 0; y < PM_TILE_H; y++) __stcs(reinterpret_cast<uint4 *>(dst + (size_t)y * A.pitch), v);  // streaming: keep L2 for the records
         if (F32) {
             float4 f = make_float4((float)(c & 0xff) / 255.0f, (float)((c >> 8) & 0xff) / 255.0f,
                                    (float)((c >> 16) & 0xff) / 255.0f, (float)(c >> 24) / 255.0f);
@@ -754,39 +863,21 @@ void pm_launch_validate(const uint8_t *scene, uint32_t scene_len, uint32_t *err,
 }
 
 void pm_launch_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1,
-                    uint32_t n_tx, uint32_t *unit_base, PmPlanResult *result, cudaStream_t s) {
-    k_plan<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, unit_base, result);
+                    uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, PmPlanResult *result, cudaStream_t s) {
+    k_plan<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, plan_b, result);
 }
 
-static size_t bin_smem_bytes(uint32_t n_tx, int *warps_per_cta) {
-    size_t per_warp = (size_t)(n_tx + 1 + PM_BIN_PEND) * sizeof(uint32_t);
-    int warps = 8;
-    while (warps > 1 && per_warp * warps > 160 * 1024) warps >>= 1;
-    *warps_per_cta = warps;
-    return per_warp * warps;
-}
-
-template <int WARPS>
-static void launch_bin(const PmFrameArgs &a, size_t smem, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_bin<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        configured = true;
-    }
-    uint32_t grid = (a.n_units + WARPS - 1) / WARPS;
-    if (grid == 0) grid = 1;  // still clears the fill kernel's queues
-    k_bin<WARPS><<<grid, WARPS * 32, smem, s>>>(a);
+void pm_launch_plan_pairs(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
+                          const unsigned long long *plan_a, uint32_t n_segments, uint32_t *pair_prefix, uint32_t *seg_item,
+                          uint2 *pair_info, uint32_t pair_cap, PmPlanResult *result, cudaStream_t s) {
+    k_plan_pairs<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, n_segments, pair_prefix, seg_item, pair_info, pair_cap, result);
 }
 
 void pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, cudaStream_t s) {
-    int warps = 8;
-    size_t smem = bin_smem_bytes(a.n_tx, &warps);
-    switch (warps) {
-        case 8: launch_bin<8>(a, smem, s); break;
-        case 4: launch_bin<4>(a, smem, s); break;
-        case 2: launch_bin<2>(a, smem, s); break;
-        default: launch_bin<1>(a, smem, s); break;
-    }
+    uint32_t grid_seg = (a.n_pairs + 255u) / 256u;
+    if (grid_seg == 0) grid_seg = 1;  // still clears the fill kernel's queues
+    k_seg<<<grid_seg, 256, 0, s>>>(a);
+    if (a.n_row_units) k_row<<<(a.n_row_units + PM_ROW_WARPS - 1) / PM_ROW_WARPS, PM_ROW_WARPS * 32, 0, s>>>(a);
     if (mid) cudaEventRecord(mid, s);
     // persistent fill kernel: enough CTAs to fill every SM, work pulled from two queues
     int grid = sm_count * 4;

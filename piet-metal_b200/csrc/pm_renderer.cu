@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -51,9 +52,16 @@ struct pm_renderer {
     uint8_t *scene = nullptr;
     size_t scene_cap = 0;
     uint32_t scene_len = 0, n_items = 0, items_ix = 0;
-    uint32_t *unit_base = nullptr;
-    size_t unit_base_cap = 0;
-    uint32_t n_units = 0;
+    unsigned long long *plan_a = nullptr, *plan_b = nullptr;  // per-item prefixes (pm_kernels.cu, k_plan)
+    size_t plan_cap = 0;
+    uint32_t n_segments = 0, n_row_units = 0, n_pairs = 0;
+    uint32_t *pair_prefix = nullptr, *seg_item = nullptr;
+    size_t pair_cap = 0;
+    uint2 *pair_info = nullptr;
+    size_t pair_info_cap = 0;
+    uint32_t *bd = nullptr;  // backdrop scratch, zero between frames
+    unsigned long long *debug = nullptr;
+    size_t bd_cap = 0, bd_words = 0;
     bool have_scene = false, plan_dirty = true;
     uint32_t *dev_err = nullptr;
     PmPlanResult *dev_plan = nullptr;
@@ -149,13 +157,56 @@ int alloc_surface(pm_renderer *r) {
 
 int run_plan(pm_renderer *r) {
     PM_CUDA(cudaMemsetAsync(r->dev_plan, 0, sizeof(PmPlanResult), r->stream));
-    pm_launch_plan(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->unit_base, r->dev_plan, r->stream);
+    pm_launch_plan(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, r->plan_b, r->dev_plan, r->stream);
     PM_CUDA(cudaGetLastError());
     PmPlanResult res;
     PM_CUDA(cudaMemcpyAsync(&res, r->dev_plan, sizeof res, cudaMemcpyDeviceToHost, r->stream));
     PM_CUDA(cudaStreamSynchronize(r->stream));
-    if (res.error) { g_last_error = "scene needs more than 2^32 (item, tile row) work units"; return PM_ERR_INVALID_ARG; }
-    r->n_units = res.n_units;
+    if (res.error) { g_last_error = "scene has more than 2^31 segments or (item, tile row) pairs"; return PM_ERR_INVALID_ARG; }
+    if (res.bd_words > (1ull << 31)) { g_last_error = "item bounding boxes cover more than 2^31 tiles in total"; return PM_ERR_NOMEM; }
+    r->n_segments = res.n_segments;
+    if ((size_t)res.n_segments + 1 > r->pair_cap) {
+        if (r->pair_prefix) PM_CUDA(cudaFree(r->pair_prefix));
+        if (r->seg_item) PM_CUDA(cudaFree(r->seg_item));
+        r->pair_prefix = r->seg_item = nullptr;
+        PM_CUDA(cudaMalloc(&r->pair_prefix, ((size_t)res.n_segments + 1) * sizeof(uint32_t)));
+        PM_CUDA(cudaMalloc(&r->seg_item, ((size_t)res.n_segments + 1) * sizeof(uint32_t)));
+        r->pair_cap = (size_t)res.n_segments + 1;
+    }
+    // pass 1 counts the (segment, tile row) pairs; pass 2 tabulates them
+    for (int pass = 0; pass < 2; pass++) {
+        pm_launch_plan_pairs(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, res.n_segments, r->pair_prefix,
+                             r->seg_item, pass ? r->pair_info : nullptr, (uint32_t)r->pair_info_cap, r->dev_plan, r->stream);
+        PM_CUDA(cudaGetLastError());
+        PM_CUDA(cudaMemcpyAsync(&res, r->dev_plan, sizeof res, cudaMemcpyDeviceToHost, r->stream));
+        PM_CUDA(cudaStreamSynchronize(r->stream));
+        if (res.error) { g_last_error = "scene has more than 2^31 (segment, tile row) pairs"; return PM_ERR_INVALID_ARG; }
+        if (pass == 0 && (size_t)res.n_pairs + 1 > r->pair_info_cap) {
+            if (r->pair_info) PM_CUDA(cudaFree(r->pair_info));
+            r->pair_info = nullptr;
+            PM_CUDA(cudaMalloc(&r->pair_info, ((size_t)res.n_pairs + 1) * sizeof(uint2)));
+            r->pair_info_cap = (size_t)res.n_pairs + 1;
+        }
+    }
+    r->n_pairs = res.n_pairs;
+    if (getenv("PM_DEBUG_SEG")) {
+        if (r->debug) cudaFree(r->debug);
+        PM_CUDA(cudaMalloc(&r->debug, (size_t)(1u << 20) * 8));
+        {
+            std::vector<unsigned long long> init(1u << 20);
+            for (size_t i = 0; i < init.size(); i += 2) { init[i] = ~0ull; init[i + 1] = 0; }
+            PM_CUDA(cudaMemcpy(r->debug, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+        }
+    }
+    r->n_row_units = res.n_rows;
+    const size_t want = (size_t)res.bd_words + 1;
+    if (want > r->bd_cap) {
+        if (r->bd) PM_CUDA(cudaFree(r->bd));
+        r->bd = nullptr;
+        PM_CUDA(cudaMalloc(&r->bd, want * sizeof(uint32_t)));
+        r->bd_cap = want;
+    }
+    r->bd_words = want;
     r->plan_dirty = false;
     return PM_OK;
 }
@@ -175,7 +226,8 @@ int enqueue_frame(pm_renderer *r, bool debug_f32) {
     PmFrameArgs a;
     memset(&a, 0, sizeof a);
     a.scene = r->scene; a.scene_len = r->scene_len; a.n_items = r->n_items; a.items_ix = r->items_ix;
-    a.unit_base = r->unit_base; a.n_units = r->n_units;
+    a.plan_a = r->plan_a; a.plan_b = r->plan_b; a.n_segments = r->n_segments; a.n_row_units = r->n_row_units; a.bd = r->bd;
+    a.pair_info = r->pair_info; a.seg_item = r->seg_item; a.n_pairs = r->n_pairs;
     a.tile_y0 = r->tile_y0; a.n_rows = r->tile_y1 - r->tile_y0; a.n_tx = r->n_tx;
     a.occ = r->occ; a.cnt = r->cnt; a.ovf = r->ovf;
     a.pool = r->pool; a.overflow_cap = r->overflow_cap; a.complex_list = r->complex_list;
@@ -184,8 +236,10 @@ int enqueue_frame(pm_renderer *r, bool debug_f32) {
     a.fb = r->fb; a.pitch = r->pitch;
     a.fb32 = debug_f32 ? r->fb32 : nullptr; a.pitch32 = r->pitch32;
     a.srgb_lut = r->lut;
+    a.debug = r->debug;
     const uint32_t slot = r->frame % EVENT_RING;
     PM_CUDA(cudaEventRecord(r->ev_start[slot], r->stream));
+    PM_CUDA(cudaMemsetAsync(r->bd, 0, r->bd_words * sizeof(uint32_t), r->stream));  // backdrop scratch of this frame
     pm_launch_frame(a, r->sm_count, r->ev_mid[slot], r->stream);
     PM_CUDA(cudaEventRecord(r->ev_end[slot], r->stream));
     PM_CUDA(cudaGetLastError());
@@ -236,11 +290,13 @@ int install_scene(pm_renderer *r, const void *src, size_t len, cudaMemcpyKind ki
     r->scene_len = (uint32_t)len;
     r->n_items = hdr.n_items;
     r->items_ix = hdr.items_ix;
-    if ((size_t)r->n_items + 1 > r->unit_base_cap) {
-        if (r->unit_base) PM_CUDA(cudaFree(r->unit_base));
-        r->unit_base = nullptr;
-        PM_CUDA(cudaMalloc(&r->unit_base, ((size_t)r->n_items + 1) * sizeof(uint32_t)));
-        r->unit_base_cap = (size_t)r->n_items + 1;
+    if ((size_t)r->n_items + 1 > r->plan_cap) {
+        if (r->plan_a) PM_CUDA(cudaFree(r->plan_a));
+        if (r->plan_b) PM_CUDA(cudaFree(r->plan_b));
+        r->plan_a = r->plan_b = nullptr;
+        PM_CUDA(cudaMalloc(&r->plan_a, ((size_t)r->n_items + 1) * sizeof(unsigned long long)));
+        PM_CUDA(cudaMalloc(&r->plan_b, ((size_t)r->n_items + 1) * sizeof(unsigned long long)));
+        r->plan_cap = (size_t)r->n_items + 1;
     }
     r->have_scene = true;
     r->plan_dirty = true;
@@ -310,7 +366,7 @@ void pm_renderer_destroy(pm_renderer *r) {
     if (!r) return;
     cudaSetDevice(r->device);
     if (r->stream) cudaStreamSynchronize(r->stream);
-    cudaFree(r->scene); cudaFree(r->unit_base); cudaFree(r->dev_err); cudaFree(r->dev_plan);
+    cudaFree(r->scene); cudaFree(r->plan_a); cudaFree(r->plan_b); cudaFree(r->bd); cudaFree(r->pair_prefix); cudaFree(r->seg_item); cudaFree(r->pair_info); cudaFree(r->debug); cudaFree(r->dev_err); cudaFree(r->dev_plan);
     cudaFree(r->fb); cudaFree(r->fb32); cudaFree(r->occ); cudaFree(r->cnt); cudaFree(r->ovf); cudaFree(r->complex_list);
     cudaFree(r->pool); cudaFree(r->counters); cudaFree(r->queue); cudaFree(r->lut);
     if (r->report) cudaFreeHost(r->report);
@@ -375,6 +431,22 @@ int pm_renderer_sync(pm_renderer *r, pm_frame_stats *stats) {
     const uint32_t retries_before = r->retries;
     st = finish_frames(r, false);
     if (st != PM_OK) return st;
+    if (r->debug) {
+        size_t nb = std::min<size_t>((size_t)r->n_pairs / 256 + 1, 1u << 19);
+        std::vector<unsigned long long> d(2 * nb);
+        cudaMemcpy(d.data(), r->debug, 2 * nb * 8, cudaMemcpyDeviceToHost);
+        unsigned long long t0 = ~0ull, t1 = 0;
+        for (size_t i = 0; i < nb; i++) { t0 = std::min(t0, d[2 * i]); t1 = std::max(t1, d[2 * i + 1]); }
+        std::vector<size_t> order(nb);
+        for (size_t i = 0; i < nb; i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return d[2 * a + 1] > d[2 * b + 1]; });
+        fprintf(stderr, "[PM_DEBUG_SEG] k_seg span %.1f us over %zu CTAs\n", (t1 - t0) * 1e-3, nb);
+        for (size_t i = 0; i < std::min<size_t>(nb, 6); i++)
+            fprintf(stderr, "[PM_DEBUG_SEG]   block %zu: start +%.1f us, end +%.1f us\n", order[i], (d[2 * order[i]] - t0) * 1e-3, (d[2 * order[i] + 1] - t0) * 1e-3);
+        std::vector<unsigned long long> init(2 * nb);
+        for (size_t i = 0; i < nb; i++) { init[2 * i] = ~0ull; init[2 * i + 1] = 0; }
+        cudaMemcpy(r->debug, init.data(), 2 * nb * 8, cudaMemcpyHostToDevice);
+    }
     if (stats) {
         memset(stats, 0, sizeof *stats);
         uint32_t n = std::min<uint32_t>(r->frames_unsynced, EVENT_RING);
@@ -395,7 +467,7 @@ int pm_renderer_sync(pm_renderer *r, pm_frame_stats *stats) {
         stats->n_tiles = (r->tile_y1 - r->tile_y0) * r->n_tx;
         stats->n_overflow_records = r->report->n_overflow;
         stats->n_complex_tiles = r->report->n_complex;
-        stats->n_launches = 2;
+        stats->n_launches = 3;  /* k_seg, k_row, k_fine (+ one memset node) */
         stats->retries = r->retries - retries_before;
     }
     r->frames_unsynced = 0;

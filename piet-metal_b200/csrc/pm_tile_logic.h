@@ -161,70 +161,95 @@ PM_HD bool pm_tile_span(float lo_x, float hi_x, uint32_t t_lo, uint32_t t_hi, ui
     return true;
 }
 
+// x extent of the segment inside the horizontal band [ya, yb], widened by a margin that covers the
+// rounding of the corner-sign expressions: their absolute error is below 4 eps (|a| X + |b| Y + |c|)
+// with X, Y <= 65536, i.e. a corner farther than 0.033 (1 + |dx/dy|) px from the line has the sign
+// exact arithmetic gives it; the margin used is 2 + |dx/dy| / 4 px.  A tile whose x range does not
+// touch this extent cannot get a command from the segment in this band: all four corner signs
+// agree and the left-edge crossing lies outside the band.
+PM_HD void pm_seg_band_x(const PmSeg &g, float ya, float yb, float *lo, float *hi) {
+    *lo = g.mnx;
+    *hi = g.mxx;
+    if (g.a == 0.0f) return;
+    float yt = fmaxf(ya, g.mny), ybm = fminf(yb, g.mxy);
+    float inv = (g.ex - g.sx) / g.a;  // dx / dy
+    float x1 = g.sx + (yt - g.sy) * inv, x2 = g.sx + (ybm - g.sy) * inv;
+    float m = 2.0f + 0.25f * fabsf(inv);
+    if (!(m < 65536.0f)) return;  // near-horizontal (or NaN): keep the whole extent
+    *lo = fmaxf(fminf(x1, x2) - m, g.mnx);
+    *hi = fminf(fmaxf(x1, x2) + m, g.mxx);
+}
+
+// Tiles [*ta, *tb] of the row at y0 that can receive a command from the segment (a superset; the
+// exact tests follow per tile).  False if there is none.
+PM_HD bool pm_fill_candidate_span(const PmSeg &g, float y0, uint32_t t_lo, uint32_t t_hi, uint32_t *ta, uint32_t *tb) {
+    if (!pm_fill_row_overlap(g, y0)) return false;
+    float band_lo, band_hi;
+    pm_seg_band_x(g, y0, y0 + 16.0f, &band_lo, &band_hi);
+    return pm_tile_span(band_lo, band_hi, t_lo, t_hi, ta, tb);
+}
+
+// The exact tests of one candidate tile: x-overlap guard, strip vote, tile test (metal:265-353).
+// Sink::fill(t, seg_index, emit, g): one Fill (+FillEdge) command for tile t.
+template <class Sink>
+PM_HD void pm_fill_candidate_tile(Sink &sink, const PmSeg &g, float y0, uint32_t t, uint32_t seg_index) {
+    float x0 = (float)(t * PM_TILE_W);
+    if (!(g.mnx < x0 + 16.0f && g.mxx > x0)) return;  // every emitting branch carries this guard
+    if (!pm_fill_strip_vote(g, y0, (float)((t / PM_GROUP_TILES_X) * PM_STRIP_PX))) return;
+    PmFillEmit e = pm_fill_tile_test(g, x0, y0);
+    if (e.kind != PM_EMIT_NONE) sink.fill(t, seg_index, e, g);
+}
+
+// Backdrop contribution of the segment to the tiles [t_lo, t_hi] of the row at y0 (metal:331-333).
+// Sink::backdrop(ta, tb, delta): backdrop += delta for tiles ta..tb (inclusive).
+template <class Sink>
+PM_HD void pm_fill_backdrop_row(Sink &sink, const PmSeg &g, float y0, uint32_t t_lo, uint32_t t_hi, uint32_t n_tiles_x) {
+    if (!pm_fill_row_overlap(g, y0) || !(g.mny <= y0)) return;  // the segment must reach the row's top line
+    float sa = pm_sign(g.a);
+    if (sa == 0.0f) return;
+    uint32_t t_first = pm_fill_backdrop_first_tile(g, y0, n_tiles_x);
+    if (t_first < t_lo) t_first = t_lo;
+    if (t_first > t_hi) return;
+    const int delta = sa > 0.0f ? -1 : 1;  // backdrop -= s00, s00 == sign(a) here
+    // A tile only sees the segment if its 256-px strip voted for it (metal:302):
+    //   vote(S) = mnx < sx0+256  &&  (side(S) || (crosses(S) && mxx > sx0)).
+    // side(S) is monotone in S like the tile test, mnx < sx0+256 is a suffix too, and
+    // crosses(S) && mxx > sx0 can only hold up to the strip containing mxx: so the voting strips
+    // are a suffix [s_suf, ..) plus a few strips evaluated one by one.
+    const uint32_t n_strips = (n_tiles_x + PM_GROUP_TILES_X - 1) / PM_GROUP_TILES_X;
+    const uint32_t s_lo = t_first / PM_GROUP_TILES_X, s_hi = t_hi / PM_GROUP_TILES_X;
+    uint32_t s_side = pm_fill_strip_side_first(g, y0, n_strips);
+    uint32_t s_a = g.mnx < 256.0f ? 0u : (uint32_t)fminf(floorf(g.mnx * (1.0f / 256.0f)), 4096.0f);
+    uint32_t s_suf = s_side > s_a ? s_side : s_a;
+    if (s_suf < s_lo) s_suf = s_lo;
+    if (g.mxx > 0.0f) {
+        uint32_t s_b = (uint32_t)fminf(ceilf(g.mxx * (1.0f / 256.0f)), 4096.0f) - 1u;  // last strip with sx0 < mxx
+        uint32_t s_end = s_suf;  // exclusive
+        if (s_end > s_hi + 1) s_end = s_hi + 1;
+        if (s_end > s_b + 1) s_end = s_b + 1;
+        for (uint32_t strip = s_lo > s_a ? s_lo : s_a; strip < s_end; strip++) {
+            if (!pm_fill_strip_vote(g, y0, (float)(strip * PM_STRIP_PX))) continue;
+            uint32_t a0 = strip * PM_GROUP_TILES_X, a1 = a0 + PM_GROUP_TILES_X - 1;
+            if (a0 < t_first) a0 = t_first;
+            if (a1 > t_hi) a1 = t_hi;
+            sink.backdrop(a0, a1, delta);
+        }
+    }
+    if (s_suf <= s_hi) {
+        uint32_t a0 = s_suf * PM_GROUP_TILES_X;
+        if (a0 < t_first) a0 = t_first;
+        sink.backdrop(a0, t_hi, delta);
+    }
+}
+
 // All effects of one fill segment on the tiles [t_lo, t_hi] of the tile row starting at y0.
-// Sink::fill(t, seg_index, emit, g)   one Fill (+FillEdge) command for tile t
-// Sink::backdrop(ta, tb, delta)      backdrop += delta for tiles ta..tb (inclusive)
 template <class Sink>
 PM_HD void pm_fill_segment_row(Sink &sink, const PmSeg &g, float y0, uint32_t t_lo, uint32_t t_hi, uint32_t n_tiles_x,
                                uint32_t seg_index) {
-    if (!pm_fill_row_overlap(g, y0)) return;
-    // commands: only tiles overlapping the segment's x range can receive one
     uint32_t ta = 1, tb = 0;
-    pm_tile_span(g.mnx, g.mxx, t_lo, t_hi, &ta, &tb);
-    uint32_t voted_strip = 0xffffffffu;
-    bool vote = false;
-    for (uint32_t t = ta; t <= tb; t++) {
-        float x0 = (float)(t * PM_TILE_W);
-        if (!(g.mnx < x0 + 16.0f && g.mxx > x0)) continue;
-        uint32_t strip = t / PM_GROUP_TILES_X;
-        if (strip != voted_strip) {
-            vote = pm_fill_strip_vote(g, y0, (float)(strip * PM_STRIP_PX));
-            voted_strip = strip;
-        }
-        if (!vote) continue;
-        PmFillEmit e = pm_fill_tile_test(g, x0, y0);
-        if (e.kind != PM_EMIT_NONE) sink.fill(t, seg_index, e, g);
-    }
-    // backdrop: the segment reaches the row's top line
-    if (g.mny <= y0) {
-        float sa = pm_sign(g.a);
-        if (sa != 0.0f) {
-            uint32_t t_first = pm_fill_backdrop_first_tile(g, y0, n_tiles_x);
-            if (t_first < t_lo) t_first = t_lo;
-            if (t_first <= t_hi) {
-                const int delta = sa > 0.0f ? -1 : 1;  // backdrop -= s00, s00 == sign(a) here
-                // A tile only sees the segment if its 256-px strip voted for it (metal:302):
-                //   vote(S) = mnx < sx0+256  &&  (side(S) || (crosses(S) && mxx > sx0)).
-                // side(S) is monotone in S like the tile test, mnx < sx0+256 is a suffix too, and
-                // crosses(S) && mxx > sx0 can only hold up to the strip containing mxx: so the
-                // voting strips are a suffix [s_suf, ..) plus a few strips evaluated one by one.
-                const uint32_t n_strips = (n_tiles_x + PM_GROUP_TILES_X - 1) / PM_GROUP_TILES_X;
-                const uint32_t s_lo = t_first / PM_GROUP_TILES_X, s_hi = t_hi / PM_GROUP_TILES_X;
-                uint32_t s_side = pm_fill_strip_side_first(g, y0, n_strips);
-                uint32_t s_a = g.mnx < 256.0f ? 0u : (uint32_t)fminf(floorf(g.mnx * (1.0f / 256.0f)), 4096.0f);
-                uint32_t s_suf = s_side > s_a ? s_side : s_a;
-                if (s_suf < s_lo) s_suf = s_lo;
-                if (g.mxx > 0.0f) {
-                    uint32_t s_b = (uint32_t)fminf(ceilf(g.mxx * (1.0f / 256.0f)), 4096.0f) - 1u;  // last strip with sx0 < mxx
-                    uint32_t s_end = s_suf;  // exclusive
-                    if (s_end > s_hi + 1) s_end = s_hi + 1;
-                    if (s_end > s_b + 1) s_end = s_b + 1;
-                    for (uint32_t strip = s_lo > s_a ? s_lo : s_a; strip < s_end; strip++) {
-                        if (!pm_fill_strip_vote(g, y0, (float)(strip * PM_STRIP_PX))) continue;
-                        uint32_t a0 = strip * PM_GROUP_TILES_X, a1 = a0 + PM_GROUP_TILES_X - 1;
-                        if (a0 < t_first) a0 = t_first;
-                        if (a1 > t_hi) a1 = t_hi;
-                        sink.backdrop(a0, a1, delta);
-                    }
-                }
-                if (s_suf <= s_hi) {
-                    uint32_t a0 = s_suf * PM_GROUP_TILES_X;
-                    if (a0 < t_first) a0 = t_first;
-                    sink.backdrop(a0, t_hi, delta);
-                }
-            }
-        }
-    }
+    if (pm_fill_candidate_span(g, y0, t_lo, t_hi, &ta, &tb))
+        for (uint32_t t = ta; t <= tb; t++) pm_fill_candidate_tile(sink, g, y0, t, seg_index);
+    pm_fill_backdrop_row(sink, g, y0, t_lo, t_hi, n_tiles_x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -260,27 +285,29 @@ PM_HD bool pm_poly_group_vote(const PmSeg &g, float sx0, float sy0, float y0, fl
     return pm_stroke_cross(g, sx0, sx0 + 256.0f, lane_y0, lane_y0 + 16.0f, hw);
 }
 
+PM_HD bool pm_poly_candidate_span(const PmSeg &g, float y0, float hw, uint32_t t_lo, uint32_t t_hi, uint32_t *ta, uint32_t *tb) {
+    if (!(g.mxy > y0 - hw && g.mny < y0 + 16.0f + hw)) return false;
+    float band_lo, band_hi;  // the stroke-inflated tile reaches hw beyond the tile on every side
+    pm_seg_band_x(g, y0 - hw - 1.0f, y0 + 16.0f + hw + 1.0f, &band_lo, &band_hi);
+    return pm_tile_span(band_lo - hw - 1.0f, band_hi + hw + 1.0f, t_lo, t_hi, ta, tb);
+}
+
 // Sink::line(t, seg_index, g): one Line command for tile t
+template <class Sink>
+PM_HD void pm_poly_candidate_tile(Sink &sink, const PmSeg &g, float y0, float hw, uint32_t t, uint32_t seg_index, bool fix_precull) {
+    float x0 = (float)(t * PM_TILE_W);
+    if (!pm_poly_tile_overlap(g, x0, y0, hw)) return;
+    float sy0 = (float)(((uint32_t)y0) & ~(uint32_t)(PM_GROUP_PX_Y - 1));
+    if (!pm_poly_group_vote(g, (float)((t / PM_GROUP_TILES_X) * PM_STRIP_PX), sy0, y0, hw, seg_index, fix_precull)) return;
+    if (pm_stroke_cross(g, x0, x0 + 16.0f, y0, y0 + 16.0f, hw)) sink.line(t, seg_index, g);
+}
+
 template <class Sink>
 PM_HD void pm_poly_segment_row(Sink &sink, const PmSeg &g, float y0, float hw, uint32_t t_lo, uint32_t t_hi,
                                uint32_t seg_index, bool fix_precull) {
-    if (!(g.mxy > y0 - hw && g.mny < y0 + 16.0f + hw)) return;
     uint32_t ta = 1, tb = 0;
-    pm_tile_span(g.mnx - hw - 1.0f, g.mxx + hw + 1.0f, t_lo, t_hi, &ta, &tb);
-    float sy0 = (float)(((uint32_t)y0) & ~(uint32_t)(PM_GROUP_PX_Y - 1));
-    uint32_t voted_strip = 0xffffffffu;
-    bool vote = false;
-    for (uint32_t t = ta; t <= tb; t++) {
-        float x0 = (float)(t * PM_TILE_W);
-        if (!pm_poly_tile_overlap(g, x0, y0, hw)) continue;
-        uint32_t strip = t / PM_GROUP_TILES_X;
-        if (strip != voted_strip) {
-            vote = pm_poly_group_vote(g, (float)(strip * PM_STRIP_PX), sy0, y0, hw, seg_index, fix_precull);
-            voted_strip = strip;
-        }
-        if (!vote) continue;
-        if (pm_stroke_cross(g, x0, x0 + 16.0f, y0, y0 + 16.0f, hw)) sink.line(t, seg_index, g);
-    }
+    if (pm_poly_candidate_span(g, y0, hw, t_lo, t_hi, &ta, &tb))
+        for (uint32_t t = ta; t <= tb; t++) pm_poly_candidate_tile(sink, g, y0, hw, t, seg_index, fix_precull);
 }
 
 // ---------------------------------------------------------------------------------------------

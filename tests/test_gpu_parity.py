@@ -112,7 +112,7 @@ def test_render_host_roundtrip(pm, renderer):
     renderer.init_scene(scene)
     renderer.draw()
     assert np.array_equal(img, renderer.read_rgba8())
-    assert stats.n_launches == 2 and stats.n_complex_tiles > 0
+    assert stats.n_launches == 3 and stats.n_complex_tiles > 0
 
 
 def test_scene_device_pointer_path(pm, renderer):
