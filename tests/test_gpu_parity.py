@@ -202,3 +202,23 @@ def test_full_size_band_matches_oracle_8192(pm, oracle, renderer):
     gpu = gpu_render(renderer, scene, w, h, strip=(y0, y1))
     ref = oracle.render(scene, w, h, tile_y0=y0, tile_y1=y1, f32=True, items=True)
     check(gpu, ref, "tiger 8192 rows %d..%d" % (y0, y1))
+
+
+def test_config4_band_matches_oracle(pm, oracle, renderer):
+    """BASELINE config 4 (10k random filled Bezier paths, 8192^2): two tile rows against the oracle."""
+    w = h = 8192
+    scene = pm.build_scene(pm.SCENE_RAND_BEZIER, w, h)
+    y0, y1 = 300, 302
+    gpu = gpu_render(renderer, scene, w, h, strip=(y0, y1))
+    ref = oracle.render(scene, w, h, tile_y0=y0, tile_y1=y1, f32=True, items=True)
+    check(gpu, ref, "rand_bezier 8192 rows %d..%d" % (y0, y1))
+
+
+def test_config5_band_matches_oracle(pm, oracle, renderer):
+    """BASELINE config 5 (100k glyph-like outlines, 4096^2): four tile rows against the oracle."""
+    w = h = 4096
+    scene = pm.build_scene(pm.SCENE_GLYPHS, w, h)
+    y0, y1 = 100, 104
+    gpu = gpu_render(renderer, scene, w, h, strip=(y0, y1))
+    ref = oracle.render(scene, w, h, tile_y0=y0, tile_y1=y1, f32=True, items=True)
+    check(gpu, ref, "glyphs 4096 rows %d..%d" % (y0, y1))
