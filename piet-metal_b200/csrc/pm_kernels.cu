@@ -529,7 +529,7 @@ __device__ __noinline__ void fine_pairs(FineAcc &acc, bool mine, const PmRecord 
     int ra = 1, rb = 0;
     if (mine) {
         if (stroke) pm_line_rows(r.p[1], r.p[3], reach, tile_y0, &ra, &rb);
-        else pm_fill_rows(kind, r.p[1], r.p[3], r.edge_y, tile_y0, &ra, &rb);
+        else pm_fill_rows(r.p[1], r.p[3], tile_y0, &ra, &rb);
     }
     const int cnt = rb >= ra ? rb - ra + 1 : 0;
     int incl = cnt;
@@ -551,17 +551,24 @@ __device__ __noinline__ void fine_pairs(FineAcc &acc, bool mine, const PmRecord 
         }
         const int o_excl = __shfl_sync(PM_FULL_MASK, excl, lo);
         const int o_ra = __shfl_sync(PM_FULL_MASK, ra, lo);
-        const uint32_t o_kind = __shfl_sync(PM_FULL_MASK, kind, lo);
         float p[4];
         p[0] = __shfl_sync(PM_FULL_MASK, r.p[0], lo);
         p[1] = __shfl_sync(PM_FULL_MASK, r.p[1], lo);
         p[2] = __shfl_sync(PM_FULL_MASK, r.p[2], lo);
         p[3] = __shfl_sync(PM_FULL_MASK, r.p[3], lo);
-        const float o_edge = __shfl_sync(PM_FULL_MASK, r.edge_y, lo);
         if (q < total) {
             const int row = o_ra + (q - o_excl);
             if (stroke) pm_line_pair(acc, p, reach, row, tile_x0, tile_y0);
-            else pm_fill_pair(acc, o_kind, p, o_edge, row, tile_x0, tile_y0);
+            else pm_fill_pair(acc, p, row, tile_x0, tile_y0);
+        }
+    }
+    // FillEdge commands: one record at a time, lanes 0..15 take the 16 pixel rows
+    if (!stroke) {
+        for (uint32_t em = __ballot_sync(PM_FULL_MASK, mine && kind != PM_REC_FILL); em != 0; em &= em - 1) {
+            const int src = __ffs(em) - 1;
+            const uint32_t e_kind = __shfl_sync(PM_FULL_MASK, kind, src);
+            const float e_y = __shfl_sync(PM_FULL_MASK, r.edge_y, src);
+            if (lane < 16) pm_fill_edge_row(acc, e_kind, e_y, (int)lane, tile_y0);
         }
     }
 }
@@ -569,11 +576,10 @@ __device__ __noinline__ void fine_pairs(FineAcc &acc, bool mine, const PmRecord 
 // One tile that owns records.  All 32 lanes execute this together.  Records are handled in chunks
 // of 32, one per lane; the first chunk (all of them, for nearly every tile) stays in registers.
 // Blend/store layout: lane l owns pixel row (l >> 1), pixels 8*(l & 1) .. +7.
-template <bool F32, bool EXACT>
-__device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t packed_tile, FineWarpSmem *w, const float *lut, uint32_t lane) {
+template <bool F32, bool EXACT, bool GENERAL>
+__device__ __forceinline__ void fine_complex_tile_impl(const PmFrameArgs &A, uint32_t packed_tile, u64 cw, u64 ow, FineWarpSmem *w, const float *lut, uint32_t lane) {
     const uint32_t trow = packed_tile >> 16, tx = packed_tile & 0xffffu;
     const uint32_t tile = trow * A.n_tx + tx;
-    const u64 cw = A.cnt[tile], ow = A.occ[tile];
     const uint32_t n = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
     const uint32_t occ_item1 = (uint32_t)(ow >> 32) == A.stamp ? (uint32_t)ow : 0u;
 
@@ -583,7 +589,7 @@ __device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t packed_tile, Fi
     const uint32_t n_inline = n < PM_TILE_SLOTS ? n : PM_TILE_SLOTS;
     uint32_t n_cached = n_inline;
     uint32_t tail = 0;  // 1 + pool index of the first record that did not fit the shared-memory index
-    if (n > PM_TILE_SLOTS) {
+    if (GENERAL && n > PM_TILE_SLOTS) {
         if (lane < PM_TILE_SLOTS) w->idx[lane] = tile * PM_TILE_SLOTS + lane;
         const u64 vw = A.ovf[tile];
         uint32_t cur = (uint32_t)(vw >> 32) == A.stamp ? (uint32_t)vw : 0u;
@@ -595,22 +601,22 @@ __device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t packed_tile, Fi
         tail = cur;
         __syncwarp();
     }
-    const uint32_t n_chunks = (n_cached + 31u) >> 5;
+    const uint32_t n_chunks = GENERAL ? (n_cached + 31u) >> 5 : 1u;
     // chunk 0 lives in registers for the whole tile
     PmRecord r0;
     r0.item = 0xffffffffu; r0.key = 0; r0.p[0] = r0.p[1] = r0.p[2] = r0.p[3] = 0.0f; r0.edge_y = 0.0f; r0.next = 0;
-    if (lane < n_cached) r0 = load_record(A.pool, n > PM_TILE_SLOTS ? w->idx[lane] : tile * PM_TILE_SLOTS + lane);
+    if (lane < n_cached) r0 = load_record(A.pool, (GENERAL && n > PM_TILE_SLOTS) ? w->idx[lane] : tile * PM_TILE_SLOTS + lane);
     if (r0.item < occ_item1) r0.item = 0xffffffffu;  // below the topmost opaque cover: rewound away (metal:132-135)
 
     bool has_draw = r0.item != 0xffffffffu && (r0.key & 15u) != PM_REC_SOLID;
-    for (uint32_t c = 1; c < n_chunks; c++) {
+    for (uint32_t c = 1; GENERAL && c < n_chunks; c++) {
         const uint32_t i = c * 32u + lane;
         if (i < n_cached) {
             const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[w->idx[i]]);
             if (ik.x >= occ_item1 && (ik.y & 15u) != PM_REC_SOLID) has_draw = true;
         }
     }
-    for (uint32_t cur = tail; cur != 0; cur = A.pool[cur - 1u].next) {
+    for (uint32_t cur = tail; GENERAL && cur != 0; cur = A.pool[cur - 1u].next) {
         const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[cur - 1u]);
         if (ik.x >= occ_item1 && (ik.y & 15u) != PM_REC_SOLID) has_draw = true;
     }
@@ -662,14 +668,14 @@ __device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t packed_tile, Fi
     bool first = true;
     for (;;) {
         uint32_t cur_item = (first || r0.item > last_item) ? r0.item : 0xffffffffu;
-        for (uint32_t c = 1; c < n_chunks; c++) {
+        for (uint32_t c = 1; GENERAL && c < n_chunks; c++) {
             const uint32_t i = c * 32u + lane;
             if (i < n_cached) {
                 const uint32_t it = A.pool[w->idx[i]].item;
                 if (it >= occ_item1 && (first || it > last_item) && it < cur_item) cur_item = it;
             }
         }
-        for (uint32_t cur = tail; cur != 0; cur = A.pool[cur - 1u].next) {
+        for (uint32_t cur = tail; GENERAL && cur != 0; cur = A.pool[cur - 1u].next) {
             const uint32_t it = A.pool[cur - 1u].item;
             if (it >= occ_item1 && (first || it > last_item) && it < cur_item) cur_item = it;
         }
@@ -681,14 +687,14 @@ __device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t packed_tile, Fi
         // the item's closing record says what it is (DrawFill / Stroke / Circle / Solid)
         uint32_t t_kind = 0, t_w0 = 0, t_w1 = 0;
         if (r0.item == cur_item && (r0.key & 15u) >= PM_REC_CIRCLE) { t_kind = r0.key & 15u; t_w0 = pm_f2u(r0.p[0]); t_w1 = pm_f2u(r0.p[1]); }
-        for (uint32_t c = 1; c < n_chunks; c++) {
+        for (uint32_t c = 1; GENERAL && c < n_chunks; c++) {
             const uint32_t i = c * 32u + lane;
             if (i < n_cached) {
                 const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[w->idx[i]]);
                 if (a.x == cur_item && (a.y & 15u) >= PM_REC_CIRCLE) { t_kind = a.y & 15u; t_w0 = a.z; t_w1 = a.w; }
             }
         }
-        for (uint32_t cur = tail; cur != 0; cur = A.pool[cur - 1u].next) {
+        for (uint32_t cur = tail; GENERAL && cur != 0; cur = A.pool[cur - 1u].next) {
             const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[cur - 1u]);
             if (a.x == cur_item && (a.y & 15u) >= PM_REC_CIRCLE) { t_kind = a.y & 15u; t_w0 = a.z; t_w1 = a.w; }
         }
@@ -710,7 +716,7 @@ __device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t packed_tile, Fi
             // phase A: coverage of the item's segments, 32 records at a time
             for (uint32_t c = 0; c < n_chunks; c++) {
                 PmRecord rc = r0;
-                if (c > 0) {
+                if (GENERAL && c > 0) {
                     const uint32_t i = c * 32u + lane;
                     rc.item = 0xffffffffu;
                     if (i < n_cached) rc = load_record(A.pool, w->idx[i]);
@@ -718,7 +724,7 @@ __device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t packed_tile, Fi
                 const bool mine = rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE;
                 if (__any_sync(PM_FULL_MASK, mine)) fine_pairs(acc, mine, rc, stroke, reach, tile_x0, tile_y0, lane);
             }
-            for (uint32_t cur = tail; cur != 0;) {  // records beyond the shared-memory index, one at a time
+            for (uint32_t cur = tail; GENERAL && cur != 0;) {  // records beyond the shared-memory index, one at a time
                 PmRecord rc = load_record(A.pool, cur - 1u);
                 cur = rc.next;
                 if (rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE) fine_pairs(acc, lane == 0, rc, stroke, reach, tile_x0, tile_y0, lane);
@@ -774,6 +780,13 @@ __device__ void fine_complex_tile(const PmFrameArgs &A, uint32_t packed_tile, Fi
     }
     __stcs(reinterpret_cast<uint4 *>(dst), make_uint4(packed[0], packed[1], packed[2], packed[3]));
     __stcs(reinterpret_cast<uint4 *>(dst) + 1, make_uint4(packed[4], packed[5], packed[6], packed[7]));
+}
+
+// One copy of the tile code for every record count: a second, leaner copy for small tiles was tried
+// and lost -- the kernel is instruction-cache bound and two warm copies thrash it.
+template <bool F32, bool EXACT>
+__device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t packed_tile, u64 cw, u64 ow, FineWarpSmem *w, const float *lut, uint32_t lane) {
+    fine_complex_tile_impl<F32, EXACT, true>(A, packed_tile, cw, ow, w, lut, lane);
 }
 
 // 32 consecutive tiles of one tile row; the solid ones are written row-wise: each store
@@ -840,13 +853,20 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArg
     const bool prefer_complex = warp < PM_FINE_COMPLEX_WARPS;
     while (complex_left || batches_left) {
         const bool take_complex = complex_left && (prefer_complex || !batches_left);
-        uint32_t q = 0;
-        if (lane == 0) q = atomicAdd(take_complex ? &A.queue->complex_next : &A.queue->batch_next, 1u);
-        q = __shfl_sync(PM_FULL_MASK, q, 0);
         if (take_complex) {
+            // one tile per queue access: heavy tiles (coincident outlines) sit next to each other in the
+            // list and must be spread over as many warps as possible
+            uint32_t q = 0;
+            if (lane == 0) q = atomicAdd(&A.queue->complex_next, 1u);
+            q = __shfl_sync(PM_FULL_MASK, q, 0);
             if (q >= n_complex) { complex_left = false; continue; }
-            fine_complex_tile<F32, EXACT>(A, A.complex_list[q], w, s_lut, lane);
+            const uint32_t pk = A.complex_list[q];
+            const uint32_t tile = (pk >> 16) * A.n_tx + (pk & 0xffffu);
+            fine_complex_tile<F32, EXACT>(A, pk, A.cnt[tile], A.occ[tile], w, s_lut, lane);
         } else {
+            uint32_t q = 0;
+            if (lane == 0) q = atomicAdd(&A.queue->batch_next, 1u);
+            q = __shfl_sync(PM_FULL_MASK, q, 0);
             if (q >= n_batches) { batches_left = false; continue; }
             fine_solid_batch<F32>(A, q, batches_per_row, lane);
         }

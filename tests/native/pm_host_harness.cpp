@@ -74,8 +74,10 @@ void apply_group(TileAcc &t, const std::vector<PmRecord> &recs, size_t j0, size_
         for (size_t j = j0; j + 1 < j1; j++) {
             const PmRecord &q = recs[j];
             int ra, rb;
-            pm_fill_rows(q.key & 15u, q.p[1], q.p[3], q.edge_y, tile_y0, &ra, &rb);
-            for (int row = ra; row <= rb; row++) pm_fill_pair(t, q.key & 15u, q.p, q.edge_y, row, tile_x0, tile_y0);
+            pm_fill_rows(q.p[1], q.p[3], tile_y0, &ra, &rb);
+            for (int row = ra; row <= rb; row++) pm_fill_pair(t, q.p, row, tile_x0, tile_y0);
+            if ((q.key & 15u) != PM_REC_FILL)
+                for (int row = 0; row < 16; row++) pm_fill_edge_row(t, q.key & 15u, q.edge_y, row, tile_y0);
         }
         unpack(lut, pm_f2u(last.p[1]), fg);
         const int backdrop = (int)pm_f2u(last.p[0]);
