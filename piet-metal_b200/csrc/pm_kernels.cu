@@ -127,7 +127,8 @@ __device__ __forceinline__ u64 block_scan_excl(u64 v, u64 *warp_excl, u64 *block
 }
 
 __global__ void __launch_bounds__(1024) k_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0,
-                                               uint32_t tile_y1, uint32_t n_tx, u64 *plan_a, u64 *plan_b, PmPlanResult *result) {
+                                               uint32_t tile_y1, uint32_t n_tx, u64 *plan_a, u64 *plan_b, uint2 *row_info,
+                                               uint32_t row_info_cap, PmPlanResult *result) {
     __shared__ u64 warp_excl[32];
     __shared__ u64 total_a, total_b, carry_a, carry_b;
     const uint32_t tid = threadIdx.x;
@@ -146,7 +147,18 @@ __global__ void __launch_bounds__(1024) k_plan(const uint8_t *scene, uint32_t n_
         }
         const u64 ea = carry_a + block_scan_excl(ca, warp_excl, &total_a);
         const u64 eb = carry_b + block_scan_excl(cb, warp_excl, &total_b);
-        if (i < n_items) { plan_a[i] = ea; plan_b[i] = eb; }
+        if (i < n_items) {
+            plan_a[i] = ea;
+            plan_b[i] = eb;
+            // second pass (row_info given): tabulate the item's (tile row, 32-tile chunk) units for k_row
+            if (row_info && ca != 0) {
+                const ItemSpan sp = item_span(scene, items_ix, i, tile_y0, tile_y1, n_tx);
+                const uint32_t chunks = (sp.t_hi - sp.t_lo + 32u) / 32u;
+                uint32_t u = (uint32_t)(ea >> 32);
+                for (uint32_t r = 0; r < sp.rows; r++)
+                    for (uint32_t c = 0; c < chunks && u < row_info_cap; c++, u++) row_info[u] = make_uint2(i, ((sp.r_lo + r) << 16) | c);
+            }
+        }
         // a carry out of the low half (or 2^31 in either half) would corrupt the packed prefixes
         if (((ea + ca) & 0x8000000080000000ull) != 0) result->error = 1;
         __syncthreads();
@@ -202,12 +214,18 @@ __device__ __forceinline__ uint32_t item_of_segment(const u64 *plan_a, uint32_t 
     return lo;
 }
 
-// pair_prefix[g] = number of (segment, tile row) pairs of the segments before g: k_seg runs one
-// thread per pair, so that a long segment crossing hundreds of rows is spread over as many threads.
-__global__ void __launch_bounds__(1024) k_plan_pairs(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0,
-                                                     uint32_t tile_y1, uint32_t n_tx, const u64 *plan_a, uint32_t n_segments,
-                                                     uint32_t *pair_prefix, uint32_t *seg_item, uint2 *pair_info, uint32_t pair_cap,
-                                                     PmPlanResult *result) {
+// Work decomposition of k_seg: one "piece" per (segment, tile row, candidate tile) -- plus one for a
+// (segment, tile row) that has no candidate tile but may still carry backdrop.  The candidate tiles
+// are the conservative span of pm_*_candidate_span; the exact tests run in k_seg every frame.
+// piece_info[q] = (segment, first << 31 | has_tile << 30 | tile row << 15 | tile column).
+// Pass 1 (piece_info == nullptr) only counts; pass 2 tabulates.  A long flat segment simply becomes
+// many pieces, a tall one too: no thread of k_seg does more than one tile's worth of work.
+#define PM_PIECE_FIRST 0x80000000u
+#define PM_PIECE_TILE 0x40000000u
+
+__global__ void __launch_bounds__(1024) k_plan_pieces(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0,
+                                                      uint32_t tile_y1, uint32_t n_tx, const u64 *plan_a, uint32_t n_segments,
+                                                      uint32_t *seg_item, uint2 *piece_info, uint32_t piece_cap, PmPlanResult *result) {
     __shared__ u64 warp_excl[32];
     __shared__ u64 total, carry;
     const uint32_t tid = threadIdx.x;
@@ -216,30 +234,43 @@ __global__ void __launch_bounds__(1024) k_plan_pairs(const uint8_t *scene, uint3
     for (uint32_t base = 0; base < n_segments; base += blockDim.x) {
         const uint32_t g = base + tid;
         u64 cnt = 0;
-        int ra = 0;
+        SegCtx c;
+        c.ra = 1; c.rb = 0;
         if (g < n_segments) {
             const uint32_t item = item_of_segment(plan_a, n_items, g);
-            const SegCtx c = load_segment(scene, items_ix, item, g - (uint32_t)plan_a[item], tile_y0, tile_y1, n_tx);
-            if (c.rb >= c.ra) cnt = (u64)(c.rb - c.ra + 1);
-            ra = c.ra;
+            c = load_segment(scene, items_ix, item, g - (uint32_t)plan_a[item], tile_y0, tile_y1, n_tx);
             seg_item[g] = item;
+            for (int r = c.ra; r <= c.rb; r++) {
+                uint32_t ta = 1, tb = 0;
+                const float y0 = (float)(r * PM_TILE_H);
+                const bool has = c.sp.tag == PM_ITEM_FILL ? pm_fill_candidate_span(c.sg, y0, c.sp.t_lo, c.sp.t_hi, &ta, &tb)
+                                                           : pm_poly_candidate_span(c.sg, y0, c.hw, c.sp.t_lo, c.sp.t_hi, &ta, &tb);
+                cnt += has ? (u64)(tb - ta + 1) : 1ull;
+            }
         }
         const u64 e = carry + block_scan_excl(cnt, warp_excl, &total);
-        if (g < n_segments) {
-            pair_prefix[g] = (uint32_t)e;
-            // second pass (pair_info given): the (segment, row) of every pair, so that k_seg needs no search
-            if (pair_info)
-                for (u64 j = 0; j < cnt && e + j < pair_cap; j++) pair_info[e + j] = make_uint2(g, (uint32_t)(ra + (int)j));
+        if (g < n_segments && piece_info) {
+            u64 q = e;
+            for (int r = c.ra; r <= c.rb; r++) {
+                uint32_t ta = 1, tb = 0;
+                const float y0 = (float)(r * PM_TILE_H);
+                const bool has = c.sp.tag == PM_ITEM_FILL ? pm_fill_candidate_span(c.sg, y0, c.sp.t_lo, c.sp.t_hi, &ta, &tb)
+                                                           : pm_poly_candidate_span(c.sg, y0, c.hw, c.sp.t_lo, c.sp.t_hi, &ta, &tb);
+                if (!has) {
+                    if (q < piece_cap) piece_info[q] = make_uint2(g, PM_PIECE_FIRST | ((uint32_t)r << 15));
+                    q++;
+                } else {
+                    for (uint32_t t = ta; t <= tb; t++, q++)
+                        if (q < piece_cap) piece_info[q] = make_uint2(g, (t == ta ? PM_PIECE_FIRST : 0u) | PM_PIECE_TILE | ((uint32_t)r << 15) | t);
+                }
+            }
         }
         if (e + cnt >= 0x80000000ull) result->error = 1;
         __syncthreads();
         if (tid == 0) carry += total;
         __syncthreads();
     }
-    if (tid == 0) {
-        pair_prefix[n_segments] = (uint32_t)carry;
-        result->n_pairs = (uint32_t)carry;
-    }
+    if (tid == 0) result->n_pieces = (uint32_t)carry;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -312,9 +343,9 @@ struct BinSink {
     }
 };
 
-// One thread per (segment, tile row) pair of the Fill / Poly items: the exact tile tests of
-// TestApp/PietRender.metal:248-445 for that segment in that row.  A pair whose segment can reach
-// more than 32 tiles of the row (a long, flat segment) hands its candidate tiles to the whole warp.
+// One thread per piece (see k_plan_pieces): the exact tile tests of TestApp/PietRender.metal:248-445
+// of one segment for one candidate tile; the first piece of a (segment, tile row) also adds the
+// row's backdrop intervals.
 __global__ void __launch_bounds__(256) k_seg(const PmFrameArgs A) {
     // PM_DEBUG_SEG=1: per-CTA [start, end] in globaltimer ns, two words per CTA
     struct Timer {
@@ -327,56 +358,21 @@ __global__ void __launch_bounds__(256) k_seg(const PmFrameArgs A) {
         A.queue->complex_next = 0;
         A.queue->batch_next = 0;
     }
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < A.n_pairs;
-    const bool fixp = (A.flags & PM_FLAG_FIX_POLY_PRECULL) != 0;
-    SegCtx c;
-    c.sp.tag = 0; c.sp.t_lo = c.sp.t_hi = c.sp.r_lo = 0; c.hw = 0.0f;
-    c.sg = pm_seg(0.0f, 0.0f, 0.0f, 0.0f);
-    uint32_t item = 0, k = 0, row = 0, ta = 1, tb = 0;
-    uint32_t *bd = A.bd;
-    if (valid) {
-        const uint2 pi = A.pair_info[p];  // (segment, tile row), tabulated by k_plan_pairs
-        const uint32_t g = pi.x;
-        item = A.seg_item[g];
-        k = g - (uint32_t)A.plan_a[item];
-        c = load_segment(A.scene, A.items_ix, item, k, A.tile_y0, A.tile_y0 + A.n_rows, A.n_tx);
-        row = pi.y;
-        bd = A.bd + A.plan_b[item] + (size_t)(row - c.sp.r_lo) * (c.sp.t_hi - c.sp.t_lo + 2u);
-    }
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= A.n_pieces) return;
+    const uint2 pi = A.piece_info[q];
+    const uint32_t g = pi.x;
+    const uint32_t item = A.seg_item[g];
+    const uint32_t k = g - (uint32_t)A.plan_a[item];
+    const SegCtx c = load_segment(A.scene, A.items_ix, item, k, A.tile_y0, A.tile_y0 + A.n_rows, A.n_tx);
+    const uint32_t row = (pi.y >> 15) & 0x7fffu, t = pi.y & 0x7fffu;
     const float y0 = (float)(row * PM_TILE_H);
-    const bool is_fill = c.sp.tag == PM_ITEM_FILL;
-    BinSink sink{A, bd, c.sp.t_lo, (row - A.tile_y0) * A.n_tx, item};
-    bool has_span = false;
-    if (valid) {
-        has_span = is_fill ? pm_fill_candidate_span(c.sg, y0, c.sp.t_lo, c.sp.t_hi, &ta, &tb)
-                           : pm_poly_candidate_span(c.sg, y0, c.hw, c.sp.t_lo, c.sp.t_hi, &ta, &tb);
-        if (is_fill) pm_fill_backdrop_row(sink, c.sg, y0, c.sp.t_lo, c.sp.t_hi, A.n_tx);
-    }
-    const bool wide = has_span && tb - ta >= 32u;
-    if (has_span && !wide) {
-        for (uint32_t t = ta; t <= tb; t++) {
-            if (is_fill) pm_fill_candidate_tile(sink, c.sg, y0, t, k);
-            else pm_poly_candidate_tile(sink, c.sg, y0, c.hw, t, k, fixp);
-        }
-    }
-    // wide spans: one at a time, 32 candidate tiles per step across the warp
-    for (uint32_t wide_mask = __ballot_sync(PM_FULL_MASK, wide); wide_mask != 0; wide_mask &= wide_mask - 1) {
-        const int src = __ffs(wide_mask) - 1;
-        const unsigned long long bd_bits = __shfl_sync(PM_FULL_MASK, (unsigned long long)(uintptr_t)bd, src);
-        BinSink ws{A, reinterpret_cast<uint32_t *>((uintptr_t)bd_bits), __shfl_sync(PM_FULL_MASK, c.sp.t_lo, src),
-                   __shfl_sync(PM_FULL_MASK, sink.row_tile0, src), __shfl_sync(PM_FULL_MASK, item, src)};
-        const PmSeg wg = pm_seg(__shfl_sync(PM_FULL_MASK, c.sg.sx, src), __shfl_sync(PM_FULL_MASK, c.sg.sy, src),
-                                __shfl_sync(PM_FULL_MASK, c.sg.ex, src), __shfl_sync(PM_FULL_MASK, c.sg.ey, src));
-        const float wy0 = __shfl_sync(PM_FULL_MASK, y0, src), whw = __shfl_sync(PM_FULL_MASK, c.hw, src);
-        const uint32_t wk = __shfl_sync(PM_FULL_MASK, k, src);
-        const uint32_t wta = __shfl_sync(PM_FULL_MASK, ta, src), wtb = __shfl_sync(PM_FULL_MASK, tb, src);
-        const bool wfill = __shfl_sync(PM_FULL_MASK, (int)is_fill, src) != 0;
-        for (uint32_t t = wta + lane; t <= wtb; t += 32) {
-            if (wfill) pm_fill_candidate_tile(ws, wg, wy0, t, wk);
-            else pm_poly_candidate_tile(ws, wg, wy0, whw, t, wk, fixp);
-        }
+    BinSink sink{A, A.bd + A.plan_b[item] + (size_t)(row - c.sp.r_lo) * (c.sp.t_hi - c.sp.t_lo + 2u), c.sp.t_lo, (row - A.tile_y0) * A.n_tx, item};
+    if (c.sp.tag == PM_ITEM_FILL) {
+        if (pi.y & PM_PIECE_FIRST) pm_fill_backdrop_row(sink, c.sg, y0, c.sp.t_lo, c.sp.t_hi, A.n_tx);
+        if (pi.y & PM_PIECE_TILE) pm_fill_candidate_tile(sink, c.sg, y0, t, k);
+    } else if (pi.y & PM_PIECE_TILE) {
+        pm_poly_candidate_tile(sink, c.sg, y0, c.hw, t, k, (A.flags & PM_FLAG_FIX_POLY_PRECULL) != 0);
     }
 }
 
@@ -389,17 +385,12 @@ __global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t unit = blockIdx.x * PM_ROW_WARPS + warp;
     if (unit >= A.n_row_units) return;
-    uint32_t lo = 0, hi = A.n_items;
-    while (hi - lo > 1) {  // item = largest i with row-chunk prefix <= unit
-        uint32_t mid = (lo + hi) >> 1;
-        if ((uint32_t)(A.plan_a[mid] >> 32) <= unit) lo = mid; else hi = mid;
-    }
-    const uint32_t item = lo;
+    const uint2 ri = A.row_info[unit];  // (item, tile row << 16 | chunk), tabulated by k_plan
+    const uint32_t item = ri.x;
     const ItemSpan sp = item_span(A.scene, A.items_ix, item, A.tile_y0, A.tile_y0 + A.n_rows, A.n_tx);
     const uint8_t *it = A.scene + A.items_ix + (size_t)item * PM_ITEM_SIZE;
-    const uint32_t span = sp.t_hi - sp.t_lo + 1, chunks = (span + 31u) / 32u;
-    const uint32_t local = unit - (uint32_t)(A.plan_a[item] >> 32);
-    const uint32_t row = sp.r_lo + local / chunks, j0 = (local % chunks) * 32u;
+    const uint32_t span = sp.t_hi - sp.t_lo + 1;
+    const uint32_t row = ri.y >> 16, j0 = (ri.y & 0xffffu) * 32u;
     const uint32_t t_lo = sp.t_lo;
     const float y0 = (float)(row * PM_TILE_H);
     const uint32_t *bd = A.bd + A.plan_b[item] + (size_t)(row - sp.r_lo) * (span + 1);
@@ -883,18 +874,19 @@ void pm_launch_validate(const uint8_t *scene, uint32_t scene_len, uint32_t *err,
 }
 
 void pm_launch_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1,
-                    uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, PmPlanResult *result, cudaStream_t s) {
-    k_plan<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, plan_b, result);
+                    uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, uint2 *row_info, uint32_t row_info_cap,
+                    PmPlanResult *result, cudaStream_t s) {
+    k_plan<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, plan_b, row_info, row_info_cap, result);
 }
 
-void pm_launch_plan_pairs(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
-                          const unsigned long long *plan_a, uint32_t n_segments, uint32_t *pair_prefix, uint32_t *seg_item,
-                          uint2 *pair_info, uint32_t pair_cap, PmPlanResult *result, cudaStream_t s) {
-    k_plan_pairs<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, n_segments, pair_prefix, seg_item, pair_info, pair_cap, result);
+void pm_launch_plan_pieces(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
+                           const unsigned long long *plan_a, uint32_t n_segments, uint32_t *seg_item, uint2 *piece_info,
+                           uint32_t piece_cap, PmPlanResult *result, cudaStream_t s) {
+    k_plan_pieces<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, n_segments, seg_item, piece_info, piece_cap, result);
 }
 
 void pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, cudaStream_t s) {
-    uint32_t grid_seg = (a.n_pairs + 255u) / 256u;
+    uint32_t grid_seg = (a.n_pieces + 255u) / 256u;
     if (grid_seg == 0) grid_seg = 1;  // still clears the fill kernel's queues
     k_seg<<<grid_seg, 256, 0, s>>>(a);
     if (a.n_row_units) k_row<<<(a.n_row_units + PM_ROW_WARPS - 1) / PM_ROW_WARPS, PM_ROW_WARPS * 32, 0, s>>>(a);

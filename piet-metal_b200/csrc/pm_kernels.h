@@ -33,10 +33,11 @@ struct PmFrameArgs {
     uint32_t items_ix;
     const unsigned long long *plan_a;  // per item: rows-before << 32 | segments-before (n_items + 1 entries)
     const unsigned long long *plan_b;  // per item: backdrop-scratch words before it
-    const uint2 *pair_info;            // per (segment, tile row) pair: segment index, tile row
+    const uint2 *piece_info;           // per k_seg thread: segment, flags | tile row << 15 | tile column (k_plan_pieces)
     const uint32_t *seg_item;          // per segment: its item
+    const uint2 *row_info;             // per k_row unit: item, tile row << 16 | 32-tile chunk
     uint32_t n_segments;        // segments of the Fill / Poly items that touch the strip
-    uint32_t n_pairs;           // k_seg threads
+    uint32_t n_pieces;          // k_seg threads
     uint32_t n_row_units;       // k_row warps: (item, tile row) pairs inside the strip
     uint32_t *bd;               // backdrop scratch, all zero between frames
     uint32_t tile_y0;           // first tile row of the strip
@@ -62,16 +63,17 @@ struct PmFrameArgs {
     const float *srgb_lut;      // 512 floats: [0,256) sRGB byte -> linear, [256,512) alpha byte / 255
 };
 
-struct PmPlanResult { uint32_t n_segments; uint32_t n_rows; unsigned long long bd_words; uint32_t error; uint32_t n_pairs; };
+struct PmPlanResult { uint32_t n_segments; uint32_t n_rows; unsigned long long bd_words; uint32_t error; uint32_t n_pieces; };
 
 // Validates an encoded scene on the device.  *err (device) becomes non-zero if a ref or count is
 // out of bounds or a coordinate is not finite.
 void pm_launch_validate(const uint8_t *scene, uint32_t scene_len, uint32_t *err, cudaStream_t s);
 // Fills plan_a / plan_b [0..n_items] and result (device) for the given strip.
 void pm_launch_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1,
-                    uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, PmPlanResult *result, cudaStream_t s);
-void pm_launch_plan_pairs(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
-                          const unsigned long long *plan_a, uint32_t n_segments, uint32_t *pair_prefix, uint32_t *seg_item,
-                          uint2 *pair_info, uint32_t pair_cap, PmPlanResult *result, cudaStream_t s);
+                    uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, uint2 *row_info, uint32_t row_info_cap,
+                    PmPlanResult *result, cudaStream_t s);
+void pm_launch_plan_pieces(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
+                           const unsigned long long *plan_a, uint32_t n_segments, uint32_t *seg_item, uint2 *piece_info,
+                           uint32_t piece_cap, PmPlanResult *result, cudaStream_t s);
 // One frame: binning (k_seg, k_row) then fill/blend (k_fine).  `mid` (optional) is recorded before k_fine.
 void pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, cudaStream_t s);

@@ -54,11 +54,11 @@ struct pm_renderer {
     uint32_t scene_len = 0, n_items = 0, items_ix = 0;
     unsigned long long *plan_a = nullptr, *plan_b = nullptr;  // per-item prefixes (pm_kernels.cu, k_plan)
     size_t plan_cap = 0;
-    uint32_t n_segments = 0, n_row_units = 0, n_pairs = 0;
-    uint32_t *pair_prefix = nullptr, *seg_item = nullptr;
-    size_t pair_cap = 0;
-    uint2 *pair_info = nullptr;
-    size_t pair_info_cap = 0;
+    uint32_t n_segments = 0, n_row_units = 0, n_pieces = 0;
+    uint32_t *seg_item = nullptr;
+    size_t seg_cap = 0;
+    uint2 *piece_info = nullptr, *row_info = nullptr;
+    size_t piece_cap = 0, row_info_cap = 0;
     uint32_t *bd = nullptr;  // backdrop scratch, zero between frames
     unsigned long long *debug = nullptr;
     size_t bd_cap = 0, bd_words = 0;
@@ -156,39 +156,48 @@ int alloc_surface(pm_renderer *r) {
 }
 
 int run_plan(pm_renderer *r) {
-    PM_CUDA(cudaMemsetAsync(r->dev_plan, 0, sizeof(PmPlanResult), r->stream));
-    pm_launch_plan(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, r->plan_b, r->dev_plan, r->stream);
-    PM_CUDA(cudaGetLastError());
     PmPlanResult res;
-    PM_CUDA(cudaMemcpyAsync(&res, r->dev_plan, sizeof res, cudaMemcpyDeviceToHost, r->stream));
-    PM_CUDA(cudaStreamSynchronize(r->stream));
-    if (res.error) { g_last_error = "scene has more than 2^31 segments or (item, tile row) pairs"; return PM_ERR_INVALID_ARG; }
-    if (res.bd_words > (1ull << 31)) { g_last_error = "item bounding boxes cover more than 2^31 tiles in total"; return PM_ERR_NOMEM; }
-    r->n_segments = res.n_segments;
-    if ((size_t)res.n_segments + 1 > r->pair_cap) {
-        if (r->pair_prefix) PM_CUDA(cudaFree(r->pair_prefix));
-        if (r->seg_item) PM_CUDA(cudaFree(r->seg_item));
-        r->pair_prefix = r->seg_item = nullptr;
-        PM_CUDA(cudaMalloc(&r->pair_prefix, ((size_t)res.n_segments + 1) * sizeof(uint32_t)));
-        PM_CUDA(cudaMalloc(&r->seg_item, ((size_t)res.n_segments + 1) * sizeof(uint32_t)));
-        r->pair_cap = (size_t)res.n_segments + 1;
-    }
-    // pass 1 counts the (segment, tile row) pairs; pass 2 tabulates them
+    // pass 1 sizes the k_row unit table, pass 2 fills it
     for (int pass = 0; pass < 2; pass++) {
-        pm_launch_plan_pairs(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, res.n_segments, r->pair_prefix,
-                             r->seg_item, pass ? r->pair_info : nullptr, (uint32_t)r->pair_info_cap, r->dev_plan, r->stream);
+        PM_CUDA(cudaMemsetAsync(r->dev_plan, 0, sizeof(PmPlanResult), r->stream));
+        pm_launch_plan(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, r->plan_b,
+                       pass ? r->row_info : nullptr, (uint32_t)r->row_info_cap, r->dev_plan, r->stream);
         PM_CUDA(cudaGetLastError());
         PM_CUDA(cudaMemcpyAsync(&res, r->dev_plan, sizeof res, cudaMemcpyDeviceToHost, r->stream));
         PM_CUDA(cudaStreamSynchronize(r->stream));
-        if (res.error) { g_last_error = "scene has more than 2^31 (segment, tile row) pairs"; return PM_ERR_INVALID_ARG; }
-        if (pass == 0 && (size_t)res.n_pairs + 1 > r->pair_info_cap) {
-            if (r->pair_info) PM_CUDA(cudaFree(r->pair_info));
-            r->pair_info = nullptr;
-            PM_CUDA(cudaMalloc(&r->pair_info, ((size_t)res.n_pairs + 1) * sizeof(uint2)));
-            r->pair_info_cap = (size_t)res.n_pairs + 1;
+        if (res.error) break;
+        if (pass == 0 && (size_t)res.n_rows + 1 > r->row_info_cap) {
+            if (r->row_info) PM_CUDA(cudaFree(r->row_info));
+            r->row_info = nullptr;
+            PM_CUDA(cudaMalloc(&r->row_info, ((size_t)res.n_rows + 1) * sizeof(uint2)));
+            r->row_info_cap = (size_t)res.n_rows + 1;
         }
     }
-    r->n_pairs = res.n_pairs;
+    if (res.error) { g_last_error = "scene has more than 2^31 segments or (item, tile row) pairs"; return PM_ERR_INVALID_ARG; }
+    if (res.bd_words > (1ull << 31)) { g_last_error = "item bounding boxes cover more than 2^31 tiles in total"; return PM_ERR_NOMEM; }
+    r->n_segments = res.n_segments;
+    if ((size_t)res.n_segments + 1 > r->seg_cap) {
+        if (r->seg_item) PM_CUDA(cudaFree(r->seg_item));
+        r->seg_item = nullptr;
+        PM_CUDA(cudaMalloc(&r->seg_item, ((size_t)res.n_segments + 1) * sizeof(uint32_t)));
+        r->seg_cap = (size_t)res.n_segments + 1;
+    }
+    // pass 1 counts the k_seg pieces; pass 2 tabulates them
+    for (int pass = 0; pass < 2; pass++) {
+        pm_launch_plan_pieces(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, res.n_segments,
+                              r->seg_item, pass ? r->piece_info : nullptr, (uint32_t)r->piece_cap, r->dev_plan, r->stream);
+        PM_CUDA(cudaGetLastError());
+        PM_CUDA(cudaMemcpyAsync(&res, r->dev_plan, sizeof res, cudaMemcpyDeviceToHost, r->stream));
+        PM_CUDA(cudaStreamSynchronize(r->stream));
+        if (res.error) { g_last_error = "scene has more than 2^31 (segment, tile row, tile) pieces"; return PM_ERR_INVALID_ARG; }
+        if (pass == 0 && (size_t)res.n_pieces + 1 > r->piece_cap) {
+            if (r->piece_info) PM_CUDA(cudaFree(r->piece_info));
+            r->piece_info = nullptr;
+            PM_CUDA(cudaMalloc(&r->piece_info, ((size_t)res.n_pieces + 1) * sizeof(uint2)));
+            r->piece_cap = (size_t)res.n_pieces + 1;
+        }
+    }
+    r->n_pieces = res.n_pieces;
     if (getenv("PM_DEBUG_SEG")) {
         if (r->debug) cudaFree(r->debug);
         PM_CUDA(cudaMalloc(&r->debug, (size_t)(1u << 20) * 8));
@@ -227,7 +236,7 @@ int enqueue_frame(pm_renderer *r, bool debug_f32) {
     memset(&a, 0, sizeof a);
     a.scene = r->scene; a.scene_len = r->scene_len; a.n_items = r->n_items; a.items_ix = r->items_ix;
     a.plan_a = r->plan_a; a.plan_b = r->plan_b; a.n_segments = r->n_segments; a.n_row_units = r->n_row_units; a.bd = r->bd;
-    a.pair_info = r->pair_info; a.seg_item = r->seg_item; a.n_pairs = r->n_pairs;
+    a.piece_info = r->piece_info; a.seg_item = r->seg_item; a.n_pieces = r->n_pieces; a.row_info = r->row_info;
     a.tile_y0 = r->tile_y0; a.n_rows = r->tile_y1 - r->tile_y0; a.n_tx = r->n_tx;
     a.occ = r->occ; a.cnt = r->cnt; a.ovf = r->ovf;
     a.pool = r->pool; a.overflow_cap = r->overflow_cap; a.complex_list = r->complex_list;
@@ -366,7 +375,7 @@ void pm_renderer_destroy(pm_renderer *r) {
     if (!r) return;
     cudaSetDevice(r->device);
     if (r->stream) cudaStreamSynchronize(r->stream);
-    cudaFree(r->scene); cudaFree(r->plan_a); cudaFree(r->plan_b); cudaFree(r->bd); cudaFree(r->pair_prefix); cudaFree(r->seg_item); cudaFree(r->pair_info); cudaFree(r->debug); cudaFree(r->dev_err); cudaFree(r->dev_plan);
+    cudaFree(r->scene); cudaFree(r->plan_a); cudaFree(r->plan_b); cudaFree(r->bd); cudaFree(r->seg_item); cudaFree(r->piece_info); cudaFree(r->row_info); cudaFree(r->debug); cudaFree(r->dev_err); cudaFree(r->dev_plan);
     cudaFree(r->fb); cudaFree(r->fb32); cudaFree(r->occ); cudaFree(r->cnt); cudaFree(r->ovf); cudaFree(r->complex_list);
     cudaFree(r->pool); cudaFree(r->counters); cudaFree(r->queue); cudaFree(r->lut);
     if (r->report) cudaFreeHost(r->report);
@@ -432,7 +441,7 @@ int pm_renderer_sync(pm_renderer *r, pm_frame_stats *stats) {
     st = finish_frames(r, false);
     if (st != PM_OK) return st;
     if (r->debug) {
-        size_t nb = std::min<size_t>((size_t)r->n_pairs / 256 + 1, 1u << 19);
+        size_t nb = std::min<size_t>((size_t)r->n_pieces / 256 + 1, 1u << 19);
         std::vector<unsigned long long> d(2 * nb);
         cudaMemcpy(d.data(), r->debug, 2 * nb * 8, cudaMemcpyDeviceToHost);
         unsigned long long t0 = ~0ull, t1 = 0;
