@@ -318,6 +318,10 @@ struct BinSink {
         const uint4 *src = reinterpret_cast<const uint4 *>(&r);
         dst[0] = src[0];
         dst[1] = src[1];
+        if (pos == PM_TILE_SLOTS) {  // first overflow record: the tile is "heavy", the fill kernel renders those first
+            const uint32_t h = atomicAdd(&A.counters->n_heavy, 1u);
+            A.complex_list[A.n_rows * A.n_tx + h] = ((tile - t) / A.n_tx << 16) | t;
+        }
         if (pos == 0) {  // first record of the tile this frame: queue it for the fill kernel
             cg::coalesced_group g = cg::coalesced_threads();
             uint32_t base = 0;
@@ -357,6 +361,7 @@ __global__ void __launch_bounds__(256) k_seg(const PmFrameArgs A) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         A.queue->complex_next = 0;
         A.queue->batch_next = 0;
+        A.queue->heavy_next = 0;
     }
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= A.n_pieces) return;
@@ -639,13 +644,12 @@ __device__ __forceinline__ void fine_complex_tile_impl(const PmFrameArgs &A, uin
     float rgb[8][3];
     #pragma unroll
     for (int j = 0; j < 8; j++) rgb[j][0] = rgb[j][1] = rgb[j][2] = 1.0f;  // metal:470
-    if (occ_item1) {  // the rewound list starts with the cover's Cmd_Solid (metal:136-142, :546-551)
+    if (occ_item1) {  // the rewound list starts with the cover's Cmd_Solid (metal:136-142, :546-551): same for every pixel
         float fg[4];
         unpack_fg(lut, occ_rgba, fg);
+        const float b0 = pm_mix(1.0f, fg[0], fg[3]), b1 = pm_mix(1.0f, fg[1], fg[3]), b2 = pm_mix(1.0f, fg[2], fg[3]);
         #pragma unroll
-        for (int j = 0; j < 8; j++)
-            #pragma unroll
-            for (int k = 0; k < 3; k++) rgb[j][k] = pm_mix(rgb[j][k], fg[k], fg[3]);
+        for (int j = 0; j < 8; j++) { rgb[j][0] = b0; rgb[j][1] = b1; rgb[j][2] = b2; }
     }
     const float tile_x0 = (float)(tx * PM_TILE_W), tile_y0 = (float)((A.tile_y0 + trow) * PM_TILE_H);  // scene coordinates
     const float px0 = tile_x0 + (float)(half * 8u), py = tile_y0 + (float)prow;
@@ -806,7 +810,7 @@ __device__ void fine_solid_batch(const PmFrameArgs &A, uint32_t batch, uint32_t 
         if (!((solid_mask >> src) & 1u)) continue;
         const uint4 v = make_uint4(c, c, c, c);
         uint8_t *dst = A.fb + (size_t)(row * PM_TILE_H) * A.pitch + ((size_t)t0 * PM_TILE_W + (size_t)q * 128u + lane * 4u) * 4u;
-        #pragma unroll
+        #pragma unroll 4
         for (int y = 0; y < PM_TILE_H; y++) __stcs(reinterpret_cast<uint4 *>(dst + (size_t)y * A.pitch), v);  // streaming: keep L2 for the records
         if (F32) {
             float4 f = make_float4((float)(c & 0xff) / 255.0f, (float)((c >> 8) & 0xff) / 255.0f,
@@ -829,31 +833,47 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArg
     for (uint32_t i = threadIdx.x; i < 512; i += blockDim.x) s_lut[i] = A.srgb_lut[i];
     FineWarpSmem *w = &s_warp[warp];
     for (uint32_t i = lane; i < 16 * PM_ACC_STRIDE; i += 32) { w->acc[i] = 0; w->cov[i] = 0; w->dmin[i] = 1e9f; }
-    const uint32_t n_complex = A.counters->n_complex;
+    const uint32_t n_complex = A.counters->n_complex, n_heavy = A.counters->n_heavy;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         A.report->n_complex = n_complex;
         A.report->n_overflow = A.counters->n_overflow;
         A.report->frame = A.stamp;
         A.counters_next->n_complex = 0;
         A.counters_next->n_overflow = 0;
+        A.counters_next->n_heavy = 0;
     }
     __syncthreads();
     const uint32_t batches_per_row = (A.n_tx + 31u) / 32u;
     const uint32_t n_batches = batches_per_row * A.n_rows;
-    bool complex_left = true, batches_left = true;
+    bool complex_left = true, batches_left = true, heavy_left = true;
     const bool prefer_complex = warp < PM_FINE_COMPLEX_WARPS;
     while (complex_left || batches_left) {
         const bool take_complex = complex_left && (prefer_complex || !batches_left);
         if (take_complex) {
-            // one tile per queue access: heavy tiles (coincident outlines) sit next to each other in the
-            // list and must be spread over as many warps as possible
-            uint32_t q = 0;
-            if (lane == 0) q = atomicAdd(&A.queue->complex_next, 1u);
-            q = __shfl_sync(PM_FULL_MASK, q, 0);
-            if (q >= n_complex) { complex_left = false; continue; }
-            const uint32_t pk = A.complex_list[q];
-            const uint32_t tile = (pk >> 16) * A.n_tx + (pk & 0xffffu);
-            fine_complex_tile<F32, EXACT>(A, pk, A.cnt[tile], A.occ[tile], w, s_lut, lane);
+            // Tiles with records, one per queue access.  Pass 1 renders the heavy ones (more records than
+            // inline slots: coincident outlines, deep stacks), which binning listed separately; pass 2
+            // walks the full list and skips them.  Heavy tiles first keeps a 20-microsecond tile from
+            // starting when everybody else is done; one tile per access spreads list neighbours (which
+            // tend to be equally heavy) over as many warps as possible.
+            // (one call site for the tile code: the kernel is instruction-cache bound)
+            uint32_t pk = 0;
+            u64 cw = 0;
+            bool have = false;
+            {
+                const uint32_t n_list = heavy_left ? n_heavy : n_complex;
+                uint32_t q = 0;
+                if (lane == 0) q = atomicAdd(heavy_left ? &A.queue->heavy_next : &A.queue->complex_next, 1u);
+                q = __shfl_sync(PM_FULL_MASK, q, 0);
+                if (q >= n_list) {
+                    if (heavy_left) heavy_left = false; else complex_left = false;
+                    continue;
+                }
+                pk = A.complex_list[(heavy_left ? A.n_rows * A.n_tx : 0u) + q];
+                cw = A.cnt[(pk >> 16) * A.n_tx + (pk & 0xffffu)];
+                // pass 2 skips what pass 1 rendered (the stamp is this frame's: the tile is on the list)
+                have = heavy_left || (uint32_t)cw <= PM_TILE_SLOTS;
+            }
+            if (have) fine_complex_tile<F32, EXACT>(A, pk, cw, A.occ[(pk >> 16) * A.n_tx + (pk & 0xffffu)], w, s_lut, lane);
         } else {
             uint32_t q = 0;
             if (lane == 0) q = atomicAdd(&A.queue->batch_next, 1u);

@@ -10,13 +10,15 @@
 struct PmBinCounters {
     uint32_t n_complex;   // tiles that own at least one record
     uint32_t n_overflow;  // records that did not fit the inline slots of their tile
-    uint32_t pad[2];
+    uint32_t n_heavy;     // tiles with more records than inline slots
+    uint32_t pad;
 };
 // Work queues of the fill kernel; cleared by the binning kernel of the same frame.
 struct PmFineQueue {
-    uint32_t complex_next;
-    uint32_t batch_next;
-    uint32_t pad[2];
+    uint32_t complex_next;  // pass 2 over the tiles with records: the light ones
+    uint32_t batch_next;    // 32-tile batches of solid tiles
+    uint32_t heavy_next;    // pass 1 over the tiles with records: the heavy ones first (shorter tail)
+    uint32_t pad;
 };
 // Written by the device into mapped host memory at the end of every frame.
 struct PmFrameReport {
@@ -48,7 +50,7 @@ struct PmFrameArgs {
     unsigned long long *ovf;
     PmRecord *pool;             // [n_tiles * PM_TILE_SLOTS inline slots][overflow_cap records]
     uint32_t overflow_cap;
-    uint32_t *complex_list;     // n_rows * n_tx
+    uint32_t *complex_list;     // 2 * n_rows * n_tx: tiles with records, then (second half) the heavy ones among them
     PmBinCounters *counters;    // this frame's set
     PmBinCounters *counters_next;
     PmFineQueue *queue;
