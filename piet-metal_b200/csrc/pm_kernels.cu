@@ -127,8 +127,8 @@ __device__ __forceinline__ u64 block_scan_excl(u64 v, u64 *warp_excl, u64 *block
 }
 
 __global__ void __launch_bounds__(1024) k_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0,
-                                               uint32_t tile_y1, uint32_t n_tx, u64 *plan_a, u64 *plan_b, uint2 *row_info,
-                                               uint32_t row_info_cap, PmPlanResult *result) {
+                                               uint32_t tile_y1, uint32_t n_tx, u64 *plan_a, u64 *plan_b, PmItemInfo *item_info,
+                                               uint2 *row_info, uint32_t row_info_cap, PmPlanResult *result) {
     __shared__ u64 warp_excl[32];
     __shared__ u64 total_a, total_b, carry_a, carry_b;
     const uint32_t tid = threadIdx.x;
@@ -150,6 +150,12 @@ __global__ void __launch_bounds__(1024) k_plan(const uint8_t *scene, uint32_t n_
         if (i < n_items) {
             plan_a[i] = ea;
             plan_b[i] = eb;
+            {
+                const ItemSpan spi = item_span(scene, items_ix, i, tile_y0, tile_y1, n_tx);
+                PmItemInfo ii;
+                ii.t_lo = spi.t_lo; ii.t_hi = spi.t_hi; ii.r_lo = spi.r_lo; ii.rows = spi.rows; ii.bd_base = eb; ii.pad[0] = ii.pad[1] = 0;
+                item_info[i] = ii;
+            }
             // second pass (row_info given): tabulate the item's (tile row, 32-tile chunk) units for k_row
             if (row_info && ca != 0) {
                 const ItemSpan sp = item_span(scene, items_ix, i, tile_y0, tile_y1, n_tx);
@@ -225,7 +231,7 @@ __device__ __forceinline__ uint32_t item_of_segment(const u64 *plan_a, uint32_t 
 
 __global__ void __launch_bounds__(1024) k_plan_pieces(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0,
                                                       uint32_t tile_y1, uint32_t n_tx, const u64 *plan_a, uint32_t n_segments,
-                                                      uint32_t *seg_item, uint2 *piece_info, uint32_t piece_cap, PmPlanResult *result) {
+                                                      PmSegInfo *seg_info, uint2 *piece_info, uint32_t piece_cap, PmPlanResult *result) {
     __shared__ u64 warp_excl[32];
     __shared__ u64 total, carry;
     const uint32_t tid = threadIdx.x;
@@ -239,7 +245,10 @@ __global__ void __launch_bounds__(1024) k_plan_pieces(const uint8_t *scene, uint
         if (g < n_segments) {
             const uint32_t item = item_of_segment(plan_a, n_items, g);
             c = load_segment(scene, items_ix, item, g - (uint32_t)plan_a[item], tile_y0, tile_y1, n_tx);
-            seg_item[g] = item;
+            PmSegInfo si;
+            si.sx = c.sg.sx; si.sy = c.sg.sy; si.ex = c.sg.ex; si.ey = c.sg.ey;
+            si.item = item; si.k = g - (uint32_t)plan_a[item]; si.hw = c.hw; si.tag = c.sp.tag;
+            seg_info[g] = si;
             for (int r = c.ra; r <= c.rb; r++) {
                 uint32_t ta = 1, tb = 0;
                 const float y0 = (float)(r * PM_TILE_H);
@@ -366,18 +375,21 @@ __global__ void __launch_bounds__(256) k_seg(const PmFrameArgs A) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= A.n_pieces) return;
     const uint2 pi = A.piece_info[q];
-    const uint32_t g = pi.x;
-    const uint32_t item = A.seg_item[g];
-    const uint32_t k = g - (uint32_t)A.plan_a[item];
-    const SegCtx c = load_segment(A.scene, A.items_ix, item, k, A.tile_y0, A.tile_y0 + A.n_rows, A.n_tx);
+    const uint4 *sp4 = reinterpret_cast<const uint4 *>(&A.seg_info[pi.x]);
+    const uint4 s0 = sp4[0], s1 = sp4[1];  // sx sy ex ey | item k hw tag
+    const uint4 *ip4 = reinterpret_cast<const uint4 *>(&A.item_info[s1.x]);
+    const uint4 i0 = ip4[0], i1 = ip4[1];  // t_lo t_hi r_lo rows | bd_base
+    const PmSeg sg = pm_seg(pm_u2f(s0.x), pm_u2f(s0.y), pm_u2f(s0.z), pm_u2f(s0.w));
+    const uint32_t item = s1.x, k = s1.y, t_lo = i0.x, t_hi = i0.y, r_lo = i0.z;
+    const u64 bd_base = ((u64)i1.y << 32) | i1.x;
     const uint32_t row = (pi.y >> 15) & 0x7fffu, t = pi.y & 0x7fffu;
     const float y0 = (float)(row * PM_TILE_H);
-    BinSink sink{A, A.bd + A.plan_b[item] + (size_t)(row - c.sp.r_lo) * (c.sp.t_hi - c.sp.t_lo + 2u), c.sp.t_lo, (row - A.tile_y0) * A.n_tx, item};
-    if (c.sp.tag == PM_ITEM_FILL) {
-        if (pi.y & PM_PIECE_FIRST) pm_fill_backdrop_row(sink, c.sg, y0, c.sp.t_lo, c.sp.t_hi, A.n_tx);
-        if (pi.y & PM_PIECE_TILE) pm_fill_candidate_tile(sink, c.sg, y0, t, k);
+    BinSink sink{A, A.bd + bd_base + (size_t)(row - r_lo) * (t_hi - t_lo + 2u), t_lo, (row - A.tile_y0) * A.n_tx, item};
+    if (s1.w == PM_ITEM_FILL) {
+        if (pi.y & PM_PIECE_FIRST) pm_fill_backdrop_row(sink, sg, y0, t_lo, t_hi, A.n_tx);
+        if (pi.y & PM_PIECE_TILE) pm_fill_candidate_tile(sink, sg, y0, t, k);
     } else if (pi.y & PM_PIECE_TILE) {
-        pm_poly_candidate_tile(sink, c.sg, y0, c.hw, t, k, (A.flags & PM_FLAG_FIX_POLY_PRECULL) != 0);
+        pm_poly_candidate_tile(sink, sg, y0, pm_u2f(s1.z), t, k, (A.flags & PM_FLAG_FIX_POLY_PRECULL) != 0);
     }
 }
 
@@ -894,15 +906,15 @@ void pm_launch_validate(const uint8_t *scene, uint32_t scene_len, uint32_t *err,
 }
 
 void pm_launch_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1,
-                    uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, uint2 *row_info, uint32_t row_info_cap,
-                    PmPlanResult *result, cudaStream_t s) {
-    k_plan<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, plan_b, row_info, row_info_cap, result);
+                    uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, PmItemInfo *item_info, uint2 *row_info,
+                    uint32_t row_info_cap, PmPlanResult *result, cudaStream_t s) {
+    k_plan<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, plan_b, item_info, row_info, row_info_cap, result);
 }
 
 void pm_launch_plan_pieces(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
-                           const unsigned long long *plan_a, uint32_t n_segments, uint32_t *seg_item, uint2 *piece_info,
+                           const unsigned long long *plan_a, uint32_t n_segments, PmSegInfo *seg_info, uint2 *piece_info,
                            uint32_t piece_cap, PmPlanResult *result, cudaStream_t s) {
-    k_plan_pieces<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, n_segments, seg_item, piece_info, piece_cap, result);
+    k_plan_pieces<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, n_segments, seg_info, piece_info, piece_cap, result);
 }
 
 void pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, cudaStream_t s) {

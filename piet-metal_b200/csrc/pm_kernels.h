@@ -28,6 +28,11 @@ struct PmFrameReport {
     uint32_t pad;
 };
 
+// Plan-time copies of what k_seg needs about a segment / an item, laid out for two 16-byte loads each
+// (the scene's own layout would cost five dependent loads per thread, and k_seg is latency bound).
+struct alignas(16) PmSegInfo { float sx, sy, ex, ey; uint32_t item, k; float hw; uint32_t tag; };
+struct alignas(16) PmItemInfo { uint32_t t_lo, t_hi, r_lo, rows; unsigned long long bd_base; uint32_t pad[2]; };
+
 struct PmFrameArgs {
     const uint8_t *scene;       // encoded scene in device memory
     uint32_t scene_len;
@@ -36,7 +41,8 @@ struct PmFrameArgs {
     const unsigned long long *plan_a;  // per item: rows-before << 32 | segments-before (n_items + 1 entries)
     const unsigned long long *plan_b;  // per item: backdrop-scratch words before it
     const uint2 *piece_info;           // per k_seg thread: segment, flags | tile row << 15 | tile column (k_plan_pieces)
-    const uint32_t *seg_item;          // per segment: its item
+    const PmSegInfo *seg_info;         // per segment (k_plan_pieces)
+    const PmItemInfo *item_info;       // per item (k_plan)
     const uint2 *row_info;             // per k_row unit: item, tile row << 16 | 32-tile chunk
     uint32_t n_segments;        // segments of the Fill / Poly items that touch the strip
     uint32_t n_pieces;          // k_seg threads
@@ -72,10 +78,10 @@ struct PmPlanResult { uint32_t n_segments; uint32_t n_rows; unsigned long long b
 void pm_launch_validate(const uint8_t *scene, uint32_t scene_len, uint32_t *err, cudaStream_t s);
 // Fills plan_a / plan_b [0..n_items] and result (device) for the given strip.
 void pm_launch_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1,
-                    uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, uint2 *row_info, uint32_t row_info_cap,
-                    PmPlanResult *result, cudaStream_t s);
+                    uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, PmItemInfo *item_info, uint2 *row_info,
+                    uint32_t row_info_cap, PmPlanResult *result, cudaStream_t s);
 void pm_launch_plan_pieces(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
-                           const unsigned long long *plan_a, uint32_t n_segments, uint32_t *seg_item, uint2 *piece_info,
+                           const unsigned long long *plan_a, uint32_t n_segments, PmSegInfo *seg_info, uint2 *piece_info,
                            uint32_t piece_cap, PmPlanResult *result, cudaStream_t s);
 // One frame: binning (k_seg, k_row) then fill/blend (k_fine).  `mid` (optional) is recorded before k_fine.
 void pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, cudaStream_t s);

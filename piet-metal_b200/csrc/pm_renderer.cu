@@ -55,8 +55,9 @@ struct pm_renderer {
     unsigned long long *plan_a = nullptr, *plan_b = nullptr;  // per-item prefixes (pm_kernels.cu, k_plan)
     size_t plan_cap = 0;
     uint32_t n_segments = 0, n_row_units = 0, n_pieces = 0;
-    uint32_t *seg_item = nullptr;
+    PmSegInfo *seg_info = nullptr;
     size_t seg_cap = 0;
+    PmItemInfo *item_info = nullptr;
     uint2 *piece_info = nullptr, *row_info = nullptr;
     size_t piece_cap = 0, row_info_cap = 0;
     uint32_t *bd = nullptr;  // backdrop scratch, zero between frames
@@ -160,7 +161,7 @@ int run_plan(pm_renderer *r) {
     // pass 1 sizes the k_row unit table, pass 2 fills it
     for (int pass = 0; pass < 2; pass++) {
         PM_CUDA(cudaMemsetAsync(r->dev_plan, 0, sizeof(PmPlanResult), r->stream));
-        pm_launch_plan(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, r->plan_b,
+        pm_launch_plan(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, r->plan_b, r->item_info,
                        pass ? r->row_info : nullptr, (uint32_t)r->row_info_cap, r->dev_plan, r->stream);
         PM_CUDA(cudaGetLastError());
         PM_CUDA(cudaMemcpyAsync(&res, r->dev_plan, sizeof res, cudaMemcpyDeviceToHost, r->stream));
@@ -177,15 +178,15 @@ int run_plan(pm_renderer *r) {
     if (res.bd_words > (1ull << 31)) { g_last_error = "item bounding boxes cover more than 2^31 tiles in total"; return PM_ERR_NOMEM; }
     r->n_segments = res.n_segments;
     if ((size_t)res.n_segments + 1 > r->seg_cap) {
-        if (r->seg_item) PM_CUDA(cudaFree(r->seg_item));
-        r->seg_item = nullptr;
-        PM_CUDA(cudaMalloc(&r->seg_item, ((size_t)res.n_segments + 1) * sizeof(uint32_t)));
+        if (r->seg_info) PM_CUDA(cudaFree(r->seg_info));
+        r->seg_info = nullptr;
+        PM_CUDA(cudaMalloc(&r->seg_info, ((size_t)res.n_segments + 1) * sizeof(PmSegInfo)));
         r->seg_cap = (size_t)res.n_segments + 1;
     }
     // pass 1 counts the k_seg pieces; pass 2 tabulates them
     for (int pass = 0; pass < 2; pass++) {
         pm_launch_plan_pieces(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, res.n_segments,
-                              r->seg_item, pass ? r->piece_info : nullptr, (uint32_t)r->piece_cap, r->dev_plan, r->stream);
+                              r->seg_info, pass ? r->piece_info : nullptr, (uint32_t)r->piece_cap, r->dev_plan, r->stream);
         PM_CUDA(cudaGetLastError());
         PM_CUDA(cudaMemcpyAsync(&res, r->dev_plan, sizeof res, cudaMemcpyDeviceToHost, r->stream));
         PM_CUDA(cudaStreamSynchronize(r->stream));
@@ -236,7 +237,7 @@ int enqueue_frame(pm_renderer *r, bool debug_f32) {
     memset(&a, 0, sizeof a);
     a.scene = r->scene; a.scene_len = r->scene_len; a.n_items = r->n_items; a.items_ix = r->items_ix;
     a.plan_a = r->plan_a; a.plan_b = r->plan_b; a.n_segments = r->n_segments; a.n_row_units = r->n_row_units; a.bd = r->bd;
-    a.piece_info = r->piece_info; a.seg_item = r->seg_item; a.n_pieces = r->n_pieces; a.row_info = r->row_info;
+    a.piece_info = r->piece_info; a.seg_info = r->seg_info; a.item_info = r->item_info; a.n_pieces = r->n_pieces; a.row_info = r->row_info;
     a.tile_y0 = r->tile_y0; a.n_rows = r->tile_y1 - r->tile_y0; a.n_tx = r->n_tx;
     a.occ = r->occ; a.cnt = r->cnt; a.ovf = r->ovf;
     a.pool = r->pool; a.overflow_cap = r->overflow_cap; a.complex_list = r->complex_list;
@@ -305,6 +306,9 @@ int install_scene(pm_renderer *r, const void *src, size_t len, cudaMemcpyKind ki
         r->plan_a = r->plan_b = nullptr;
         PM_CUDA(cudaMalloc(&r->plan_a, ((size_t)r->n_items + 1) * sizeof(unsigned long long)));
         PM_CUDA(cudaMalloc(&r->plan_b, ((size_t)r->n_items + 1) * sizeof(unsigned long long)));
+        if (r->item_info) PM_CUDA(cudaFree(r->item_info));
+        r->item_info = nullptr;
+        PM_CUDA(cudaMalloc(&r->item_info, ((size_t)r->n_items + 1) * sizeof(PmItemInfo)));
         r->plan_cap = (size_t)r->n_items + 1;
     }
     r->have_scene = true;
@@ -375,7 +379,7 @@ void pm_renderer_destroy(pm_renderer *r) {
     if (!r) return;
     cudaSetDevice(r->device);
     if (r->stream) cudaStreamSynchronize(r->stream);
-    cudaFree(r->scene); cudaFree(r->plan_a); cudaFree(r->plan_b); cudaFree(r->bd); cudaFree(r->seg_item); cudaFree(r->piece_info); cudaFree(r->row_info); cudaFree(r->debug); cudaFree(r->dev_err); cudaFree(r->dev_plan);
+    cudaFree(r->scene); cudaFree(r->plan_a); cudaFree(r->plan_b); cudaFree(r->bd); cudaFree(r->seg_info); cudaFree(r->item_info); cudaFree(r->piece_info); cudaFree(r->row_info); cudaFree(r->debug); cudaFree(r->dev_err); cudaFree(r->dev_plan);
     cudaFree(r->fb); cudaFree(r->fb32); cudaFree(r->occ); cudaFree(r->cnt); cudaFree(r->ovf); cudaFree(r->complex_list);
     cudaFree(r->pool); cudaFree(r->counters); cudaFree(r->queue); cudaFree(r->lut);
     if (r->report) cudaFreeHost(r->report);
