@@ -120,19 +120,11 @@ float encode(float v) { return v < 0.0031308f ? 12.92f * v : 1.055f * powf(v, 1.
 
 struct pmh_tile_item { uint32_t item; int32_t backdrop; uint32_t effect; };
 
-extern "C" int pmh_render(const uint8_t *scene, size_t len, uint32_t width, uint32_t height, uint32_t tile_y0, uint32_t tile_y1,
-                          uint32_t flags, uint8_t *rgba8, size_t stride8, float *rgba32f, size_t stride32f_bytes,
-                          uint32_t *offsets, pmh_tile_item *items, size_t cap_items, size_t *n_items_out, uint32_t *solid) {
-    (void)len;
-    const uint32_t tile_y0_strip = tile_y0;
-    const uint32_t n_tx = (width + 15) / 16, n_ty = (height + 15) / 16;
-    if (tile_y1 > n_ty) tile_y1 = n_ty;
+namespace {
+// Binning of the strip [tile_y0, tile_y1): per-tile record lists and opaque covers.
+std::vector<std::vector<TileBin>> bin_scene(const uint8_t *scene, uint32_t n_tx, uint32_t tile_y0, uint32_t tile_y1, bool fix) {
     const uint32_t n_rows = tile_y1 - tile_y0;
     const uint32_t n_items = rd_u32(scene), items_ix = rd_u32(scene + 4);
-    const bool fix = (flags & 1u) != 0;
-    float lut[256];
-    for (int i = 0; i < 256; i++) lut[i] = pm_srgb_byte_to_linear((uint32_t)i);
-
     std::vector<std::vector<TileBin>> tiles(n_rows, std::vector<TileBin>(n_tx));
     std::vector<int> delta(n_tx + 2);
     std::vector<uint8_t> em(n_tx + 1);
@@ -203,6 +195,25 @@ extern "C" int pmh_render(const uint8_t *scene, size_t len, uint32_t width, uint
             }
         }
     }
+
+    return tiles;
+}
+}  // namespace
+
+extern "C" int pmh_render(const uint8_t *scene, size_t len, uint32_t width, uint32_t height, uint32_t tile_y0, uint32_t tile_y1,
+                          uint32_t flags, uint8_t *rgba8, size_t stride8, float *rgba32f, size_t stride32f_bytes,
+                          uint32_t *offsets, pmh_tile_item *items, size_t cap_items, size_t *n_items_out, uint32_t *solid) {
+    (void)len;
+    const uint32_t tile_y0_strip = tile_y0;
+    const uint32_t n_tx = (width + 15) / 16, n_ty = (height + 15) / 16;
+    if (tile_y1 > n_ty) tile_y1 = n_ty;
+    const uint32_t n_rows = tile_y1 - tile_y0;
+    const uint32_t n_items = rd_u32(scene), items_ix = rd_u32(scene + 4);
+    const bool fix = (flags & 1u) != 0;
+    float lut[256];
+    for (int i = 0; i < 256; i++) lut[i] = pm_srgb_byte_to_linear((uint32_t)i);
+
+    std::vector<std::vector<TileBin>> tiles = bin_scene(scene, n_tx, tile_y0, tile_y1, fix);
 
     // ---- fill/blend: per tile, as k_fine does ----
     size_t total = 0;
@@ -276,5 +287,80 @@ extern "C" int pmh_render(const uint8_t *scene, size_t len, uint32_t width, uint
     }
     if (offsets) offsets[(size_t)n_rows * n_tx] = (uint32_t)total;
     if (n_items_out) *n_items_out = total;
+    return 0;
+}
+
+// Workload statistics of the fill kernel for one scene (tools/tile_stats.py): how many records,
+// items, (record, pixel row) pairs and near pixels the tiles with records carry.
+//   out[0] tiles with records   out[1] records       out[2] items (groups)   out[3] fill pairs
+//   out[4] fill near pixels     out[5] line pairs    out[6] line pixels      out[7] fill-edge records
+//   out[8] has_draw tiles       out[9] max near px in one pair (sum over pairs of that max is out[10])
+//   hist_items[k]: tiles with k items (k capped at 31); hist_recs[k]: tiles with k records (capped 63)
+extern "C" int pmh_stats(const uint8_t *scene, uint32_t width, uint32_t height, uint32_t tile_y0, uint32_t tile_y1, uint64_t *out,
+                         uint64_t *hist_items, uint64_t *hist_recs) {
+    const uint32_t n_tx = (width + 15) / 16, n_ty = (height + 15) / 16;
+    if (tile_y1 > n_ty) tile_y1 = n_ty;
+    auto tiles = bin_scene(scene, n_tx, tile_y0, tile_y1, false);
+    struct Count {
+        uint64_t near = 0, pairs = 0, maxnear = 0, cur = 0;
+        void near_(int) { near++; cur++; }
+    };
+    struct FillCounter { uint64_t near = 0, cur = 0; void near_px(int, int, int) {} };
+    struct AccCount {
+        uint64_t n_near = 0, n_cover = 0, n_dist = 0;
+        void near(int, int, int) { n_near++; }
+        void cover(int, int, int) { n_cover++; }
+        void dist(int, int, float) { n_dist++; }
+    };
+    for (uint32_t r = 0; r < tile_y1 - tile_y0; r++)
+        for (uint32_t tx = 0; tx < n_tx; tx++) {
+            TileBin &tb = tiles[r][tx];
+            const uint32_t occ_item1 = (uint32_t)(tb.occ_color >> 32);
+            if (tb.recs.empty()) continue;
+            out[0]++;
+            std::vector<PmRecord> recs;
+            bool has_draw = false;
+            for (const PmRecord &q : tb.recs)
+                if (q.item >= occ_item1) { recs.push_back(q); if ((q.key & 15u) != PM_REC_SOLID) has_draw = true; }
+            hist_recs[std::min<size_t>(tb.recs.size(), 63)]++;
+            if (!has_draw) { hist_items[0]++; continue; }
+            out[8]++;
+            std::sort(recs.begin(), recs.end(), [](const PmRecord &a, const PmRecord &b) {
+                return (((uint64_t)a.item << 32) | a.key) < (((uint64_t)b.item << 32) | b.key);
+            });
+            out[1] += recs.size();
+            const float tile_x0 = (float)(tx * 16), ty0 = (float)((tile_y0 + r) * 16);
+            size_t n_groups = 0;
+            for (size_t j0 = 0; j0 < recs.size();) {
+                size_t j1 = j0 + 1;
+                while (j1 < recs.size() && recs[j1].item == recs[j0].item) j1++;
+                n_groups++;
+                const PmRecord &last = recs[j1 - 1];
+                const uint32_t kind = last.key & 15u;
+                for (size_t j = j0; j + 1 < j1; j++) {
+                    const PmRecord &q = recs[j];
+                    int ra, rb;
+                    if (kind == PM_REC_DRAWFILL) {
+                        pm_fill_rows(q.p[1], q.p[3], ty0, &ra, &rb);
+                        for (int row = ra; row <= rb; row++) {
+                            AccCount c;
+                            pm_fill_pair(c, q.p, row, tile_x0, ty0);
+                            out[3]++; out[4] += c.n_near; out[10] += c.n_near; if (c.n_near > out[9]) out[9] = c.n_near;
+                        }
+                        if ((q.key & 15u) != PM_REC_FILL) out[7]++;
+                    } else if (kind == PM_REC_STROKE) {
+                        pm_line_rows(q.p[1], q.p[3], last.p[0] + 0.5f, ty0, &ra, &rb);
+                        for (int row = ra; row <= rb; row++) {
+                            AccCount c;
+                            pm_line_pair(c, q.p, last.p[0] + 0.5f, row, tile_x0, ty0);
+                            out[5]++; out[6] += c.n_dist;
+                        }
+                    }
+                }
+                j0 = j1;
+            }
+            out[2] += n_groups;
+            hist_items[std::min<size_t>(n_groups, 31)]++;
+        }
     return 0;
 }
