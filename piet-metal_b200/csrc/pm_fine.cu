@@ -1,0 +1,598 @@
+// k_fine: the fill/blend kernel of the render path (sm_100a).  Compiled with -fmad=false like the
+// rest of the path (pm_tile_logic.h); the few places that want an FMA ask for one explicitly.
+//
+// renderKernel's arithmetic (TestApp/PietRender.metal:457-566) evaluated sparsely, one warp per
+// tile that owns records, fused with the solid-tile composite (metal:16-44): tiles without records
+// are written as 32-tile batches of full 512-byte rows.
+//
+// Per warp:
+//   * the tile's header words and its 16 inline record slots are fetched with cp.async into shared
+//     memory while the previous tile is being encoded and stored, so a tile starts without a
+//     dependent chain of global loads (queue -> list -> cnt/occ -> records);
+//   * coverage of one item is accumulated in shared memory in 8.24 fixed point by lanes that
+//     enumerate (record, pixel row) pairs (Cmd_Fill / Cmd_FillEdge, metal:508-534) or as the
+//     minimum distance to the item's segments (Cmd_Line, metal:495-498);
+//   * the linear colour of the tile's 256 pixels lives in a lane-private slice of shared memory
+//     (8 pixels per lane), which keeps the kernel at 64 registers = 32 resident warps per SM;
+//   * the sRGB encode and the 128-bit framebuffer stores happen once per tile.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/piet_metal_b200.h"
+#include "pm_kernels.h"
+#include "pm_pixel_logic.h"
+#include "pm_scene_format.h"
+#include "pm_tile_logic.h"
+
+#define PM_FULL_MASK 0xffffffffu
+
+namespace {
+
+typedef unsigned long long u64;
+
+#define PM_FINE_WARPS 8
+#define PM_FINE_COMPLEX_WARPS 6  // warps that prefer tiles with records; the rest prefer solid batches
+#define PM_FINE_LIST_CAP 96      // overflow records per tile indexed in shared memory; the rest is re-walked
+
+__constant__ float c_fine_lut[512];  // [0,256): sRGB byte -> linear; [256,512): alpha byte / 255
+
+__device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
+
+// Per-warp shared-memory state.
+//   acc / cov: coverage of the item being resolved, [pixel row][x] with the 4-pixel groups of a row
+//     XOR-swizzled by the row so that the row-wise 128-bit accesses of the resolve and the scattered
+//     atomics of the accumulation both spread over the banks.  For a stroke, acc holds the maximum
+//     of ~bits(distance) instead (0 = no segment near), so one zero fill serves both.
+//   rgb: lane-private, [channel][4-pixel group][lane].
+//   rec / hdr: the prefetched tile: 16 inline record slots and its cnt / occ / ovf words.
+struct FineWarpSmem {
+    int acc[256];
+    int cov[256];
+    float4 rgb[3][2][32];
+    uint4 rec[2 * PM_TILE_SLOTS];
+    u64 hdr[4];
+    uint32_t idx[PM_FINE_LIST_CAP];
+};
+
+__device__ __forceinline__ int fine_swz(int row, int j) { return row * 16 + (j ^ (((row >> 1) & 3) << 2)); }
+
+struct FineAcc {
+    FineWarpSmem *w;
+    __device__ __forceinline__ void near(int row, int j, int fx) { atomicAdd(&w->acc[fine_swz(row, j)], fx); }
+    __device__ __forceinline__ void cover(int row, int j, int fx) { atomicAdd(&w->cov[fine_swz(row, j)], fx); }
+    __device__ __forceinline__ void dist(int row, int j, float d) {  // d >= 0: unsigned order == float order
+        atomicMax(reinterpret_cast<unsigned int *>(&w->acc[fine_swz(row, j)]), ~__float_as_uint(d));
+    }
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// metal:563.  The debug render and PM_FLAG_EXACT_SRGB use this form.
+template <bool EXACT>
+__device__ __forceinline__ float linear_to_srgb(float v) {
+    if (v < 0.0031308f) return 12.92f * v;
+    float p;
+    if (EXACT) {
+        p = powf(v, 1.0f / 2.4f);
+    } else {  // ex2(lg2(v) / 2.4) on the SFU, a few 1e-7 from powf
+        float l;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(v));
+        l *= 1.0f / 2.4f;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(l));
+    }
+    return 1.055f * p - 0.055f;
+}
+
+// One channel, linear -> sRGB byte.  Default path: the scale to 0..255 folded into the curve and a
+// saturating convert (negative, NaN -> 0; > 1 -> 255), no branch.
+template <bool EXACT>
+__device__ __forceinline__ uint32_t srgb_byte(float v) {
+    if (EXACT) return pm_unorm8(linear_to_srgb<true>(v));
+    float l, p;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(v));
+    l *= 1.0f / 2.4f;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(l));
+    const float s = __fmaf_rn(p, 1.055f * 255.0f, -0.055f * 255.0f);
+    const float lin = v * (12.92f * 255.0f);
+    const float r = v < 0.0031308f ? lin : s;
+    uint32_t b;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(b) : "f"(r));
+    return b;
+}
+
+template <bool EXACT>
+__device__ __forceinline__ uint32_t encode_pixel(float r, float g, float b) {
+    return srgb_byte<EXACT>(r) | (srgb_byte<EXACT>(g) << 8) | (srgb_byte<EXACT>(b) << 16) | 0xff000000u;
+}
+
+// mix(x, y, a) with two FMAs, exact at a == 0 and a == 1 (metal:505, :543, :549: within an ulp or
+// two of x + (y - x) * a)
+__device__ __forceinline__ float mix_fma(float x, float y, float a) { return __fmaf_rn(a, y, __fmaf_rn(-a, x, x)); }
+
+__device__ __forceinline__ void unpack_fg(uint32_t rgba, float fg[4]) {  // unpack_unorm4x8_srgb_to_half
+    fg[0] = c_fine_lut[rgba & 0xffu];
+    fg[1] = c_fine_lut[(rgba >> 8) & 0xffu];
+    fg[2] = c_fine_lut[(rgba >> 16) & 0xffu];
+    fg[3] = c_fine_lut[256u + (rgba >> 24)];
+}
+
+__device__ __forceinline__ PmRecord record_from(const uint4 a, const uint4 b) {
+    PmRecord r;
+    r.item = a.x; r.key = a.y; r.p[0] = pm_u2f(a.z); r.p[1] = pm_u2f(a.w);
+    r.p[2] = pm_u2f(b.x); r.p[3] = pm_u2f(b.y); r.edge_y = pm_u2f(b.z); r.next = b.w;
+    return r;
+}
+__device__ __forceinline__ PmRecord load_record(const PmRecord *pool, uint32_t idx) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(&pool[idx]);
+    return record_from(src[0], src[1]);
+}
+
+// Phase A for up to 32 records held one per lane (`mine` = this lane holds a FILL*/LINE record of
+// the current item): the (record, pixel row) pairs are enumerated across the lanes and each lane
+// adds its pair's coverage / distance into shared memory.
+__device__ __noinline__ void fine_pairs(FineAcc &acc, bool mine, const PmRecord &r, bool stroke, float reach,
+                                        float tile_x0, float tile_y0, uint32_t lane) {
+    const uint32_t kind = r.key & 15u;
+    int ra = 1, rb = 0;
+    if (mine) {
+        if (stroke) pm_line_rows(r.p[1], r.p[3], reach, tile_y0, &ra, &rb);
+        else pm_fill_rows(r.p[1], r.p[3], tile_y0, &ra, &rb);
+    }
+    const int cnt = rb >= ra ? rb - ra + 1 : 0;
+    int incl = cnt;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(PM_FULL_MASK, incl, o);
+        if (lane >= (uint32_t)o) incl += v;
+    }
+    // exclusive prefix and first row in one word: monotone in the lane, so the owner search runs on it
+    const int key = ((incl - cnt) << 5) | ra;
+    const int total = __shfl_sync(PM_FULL_MASK, incl, 31);
+    for (int q = (int)lane; q - (int)lane < total; q += 32) {
+        // owner = last lane whose exclusive prefix is <= q
+        const int qk = (q << 5) | 31;
+        int lo = 0;
+        #pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int v = __shfl_sync(PM_FULL_MASK, key, lo + step);
+            if (v <= qk) lo += step;
+        }
+        const int o_key = __shfl_sync(PM_FULL_MASK, key, lo);
+        float p[4];
+        p[0] = __shfl_sync(PM_FULL_MASK, r.p[0], lo);
+        p[1] = __shfl_sync(PM_FULL_MASK, r.p[1], lo);
+        p[2] = __shfl_sync(PM_FULL_MASK, r.p[2], lo);
+        p[3] = __shfl_sync(PM_FULL_MASK, r.p[3], lo);
+        if (q < total) {
+            const int row = (o_key & 31) + (q - (o_key >> 5));
+            if (stroke) pm_line_pair(acc, p, reach, row, tile_x0, tile_y0);
+            else pm_fill_pair(acc, p, row, tile_x0, tile_y0);
+        }
+    }
+    // FillEdge commands: one record at a time, lanes 0..15 take the 16 pixel rows
+    if (!stroke) {
+        for (uint32_t em = __ballot_sync(PM_FULL_MASK, mine && kind != PM_REC_FILL); em != 0; em &= em - 1) {
+            const int src = __ffs(em) - 1;
+            const uint32_t e_kind = __shfl_sync(PM_FULL_MASK, kind, src);
+            const float e_y = __shfl_sync(PM_FULL_MASK, r.edge_y, src);
+            if (lane < 16) pm_fill_edge_row(acc, e_kind, e_y, (int)lane, tile_y0);
+        }
+    }
+}
+
+// Pipeline state of a warp that walks the list of tiles with records.
+struct FineNext {
+    uint32_t q;      // lane 0: the claimed queue position
+    uint32_t pk;     // packed (row, column) of the next tile
+    bool claimed;    // a queue position has been claimed and not resolved yet
+    bool have;       // pk is valid and its prefetch has been issued
+    bool pass2;      // next tile comes from the full list (skip it if pass 1 rendered it)
+};
+
+__device__ __forceinline__ void fine_claim(const PmFrameArgs &A, FineNext &nx, uint32_t lane) {
+    if (lane == 0) nx.q = atomicAdd(&A.queue->complex_next, 1u);
+    nx.claimed = true;
+}
+
+// Turns the claimed position into a tile and starts the copy of its header and inline records.
+// List order: the heavy tiles (more records than inline slots: coincident outlines, deep stacks)
+// first, then the full list, in which the heavy ones are skipped.  Heavy first keeps a long tile
+// from starting when everybody else is done.
+__device__ __forceinline__ void fine_resolve(const PmFrameArgs &A, FineNext &nx, FineWarpSmem *w, uint32_t n_heavy, uint32_t n_total, uint32_t lane) {
+    const uint32_t q = __shfl_sync(PM_FULL_MASK, nx.q, 0);
+    nx.claimed = false;
+    nx.have = q < n_total;
+    if (!nx.have) return;
+    nx.pass2 = q >= n_heavy;
+    nx.pk = nx.pass2 ? A.complex_list[q - n_heavy] : A.complex_list[A.n_rows * A.n_tx + q];
+    const size_t tile = (size_t)(nx.pk >> 16) * A.n_tx + (nx.pk & 0xffffu);
+    cp_async16(&w->rec[lane], reinterpret_cast<const uint4 *>(&A.pool[tile * PM_TILE_SLOTS]) + lane);
+    if (lane < 3) cp_async8(&w->hdr[lane], lane == 0 ? &A.cnt[tile] : (lane == 1 ? &A.occ[tile] : &A.ovf[tile]));
+    cp_async_commit();
+}
+
+// One tile that owns records; its header and inline records are in w->hdr / w->rec.  All 32 lanes
+// execute this together.  Records are handled in chunks of 32, one per lane; chunk 0 is the inline
+// slots.  Pixel layout: lane l owns pixel row (l >> 1), pixels 8*(l & 1) .. +7.
+// When the records are no longer needed, the next tile of the list is resolved and prefetched.
+template <bool F32, bool EXACT>
+__device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t packed_tile, bool skip_heavy, FineWarpSmem *w, uint32_t lane,
+                                                  FineNext &nx, uint32_t n_heavy, uint32_t n_total) {
+    const uint32_t trow = packed_tile >> 16, tx = packed_tile & 0xffffu;
+    cp_async_wait_all();
+    __syncwarp();
+    const u64 cw = w->hdr[0], ow = w->hdr[1];
+    const uint32_t n = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
+    const uint32_t occ_item1 = (uint32_t)(ow >> 32) == A.stamp ? (uint32_t)ow : 0u;
+    const bool heavy = n > PM_TILE_SLOTS;
+    if (heavy && skip_heavy) {  // pass 1 rendered it
+        fine_resolve(A, nx, w, n_heavy, n_total, lane);
+        return;
+    }
+    uint32_t occ_rgba = 0xffffffffu;  // solidColor starts as opaque white (metal:74)
+    if (occ_item1) occ_rgba = ld_u32(A.scene + A.items_ix + (size_t)(occ_item1 - 1u) * PM_ITEM_SIZE + PM_FILL_RGBA);
+
+    // index the overflow chain.  n_cached counts what was actually found (a frame whose overflow
+    // pool ran out has fewer links than cnt says; the host re-renders such a frame, it only must
+    // not fault).
+    const uint32_t n_inline = heavy ? PM_TILE_SLOTS : n;
+    uint32_t n_over = 0;
+    uint32_t tail = 0;  // 1 + pool index of the first record that did not fit the shared-memory index
+    if (heavy) {
+        const u64 vw = w->hdr[2];
+        uint32_t cur = (uint32_t)(vw >> 32) == A.stamp ? (uint32_t)vw : 0u;
+        while (cur != 0 && n_over < PM_FINE_LIST_CAP) {
+            if (lane == 0) w->idx[n_over] = cur - 1u;
+            cur = A.pool[cur - 1u].next;
+            n_over++;
+        }
+        tail = cur;
+        __syncwarp();
+    }
+    const uint32_t n_chunks = 1u + ((n_over + 31u) >> 5);  // chunk 0: inline slots; chunk c >= 1: idx[32 (c - 1) ..]
+
+    // this lane's inline record: item and key stay in registers, the geometry is re-read when needed
+    uint32_t my_item = 0xffffffffu, my_key = 0;
+    if (lane < n_inline) {
+        const uint2 ik = *reinterpret_cast<const uint2 *>(&w->rec[2 * lane]);
+        my_item = ik.x; my_key = ik.y;
+    }
+    if (my_item < occ_item1) my_item = 0xffffffffu;  // below the topmost opaque cover: rewound away (metal:132-135)
+
+    bool has_draw = my_item != 0xffffffffu && (my_key & 15u) != PM_REC_SOLID;
+    if (heavy) {
+        for (uint32_t i = lane; i < n_over; i += 32) {
+            const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[w->idx[i]]);
+            if (ik.x >= occ_item1 && (ik.y & 15u) != PM_REC_SOLID) has_draw = true;
+        }
+        for (uint32_t cur = tail; cur != 0; cur = A.pool[cur - 1u].next) {
+            const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[cur - 1u]);
+            if (ik.x >= occ_item1 && (ik.y & 15u) != PM_REC_SOLID) has_draw = true;
+        }
+    }
+    has_draw = __any_sync(PM_FULL_MASK, has_draw);
+
+    const uint32_t prow = lane >> 1, half = lane & 1u;
+    uint8_t *dst = A.fb + (size_t)(trow * PM_TILE_H + prow) * A.pitch + (size_t)(tx * PM_TILE_W + half * 8u) * 4u;
+    float4 *dst32 = nullptr;
+    if (F32) dst32 = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(A.fb32) + (size_t)(trow * PM_TILE_H + prow) * A.pitch32) +
+                     (tx * PM_TILE_W + half * 8u);
+
+    if (!has_draw) {
+        // Only Solid commands after the last rewind: the tile Bails and shows solidColor (metal:145-147, :34-44)
+        fine_resolve(A, nx, w, n_heavy, n_total, lane);
+        const uint32_t c = occ_rgba;
+        const uint4 v = make_uint4(c, c, c, c);
+        __stcs(reinterpret_cast<uint4 *>(dst), v);
+        __stcs(reinterpret_cast<uint4 *>(dst) + 1, v);
+        if (F32) {
+            const float4 f = make_float4((float)(c & 0xff) / 255.0f, (float)((c >> 8) & 0xff) / 255.0f,
+                                         (float)((c >> 16) & 0xff) / 255.0f, (float)(c >> 24) / 255.0f);
+            for (int j = 0; j < 8; j++) dst32[j] = f;
+        }
+        return;
+    }
+
+    {   // the rewound list starts with the cover's Cmd_Solid (metal:136-142, :546-551) over white (metal:470)
+        float b0 = 1.0f, b1 = 1.0f, b2 = 1.0f;
+        if (occ_item1) {
+            float fg[4];
+            unpack_fg(occ_rgba, fg);
+            b0 = mix_fma(1.0f, fg[0], fg[3]); b1 = mix_fma(1.0f, fg[1], fg[3]); b2 = mix_fma(1.0f, fg[2], fg[3]);
+        }
+        #pragma unroll
+        for (int g = 0; g < 2; g++) {
+            w->rgb[0][g][lane] = make_float4(b0, b0, b0, b0);
+            w->rgb[1][g][lane] = make_float4(b1, b1, b1, b1);
+            w->rgb[2][g][lane] = make_float4(b2, b2, b2, b2);
+        }
+    }
+    const float tile_x0 = (float)(tx * PM_TILE_W), tile_y0 = (float)((A.tile_y0 + trow) * PM_TILE_H);  // scene coordinates
+    FineAcc acc{w};
+    // this lane's two 4-pixel groups of the coverage arrays
+    int4 *const my_acc0 = reinterpret_cast<int4 *>(&w->acc[fine_swz((int)prow, (int)half * 8)]);
+    int4 *const my_acc1 = reinterpret_cast<int4 *>(&w->acc[fine_swz((int)prow, (int)half * 8 + 4)]);
+    int4 *const my_cov0 = reinterpret_cast<int4 *>(&w->cov[fine_swz((int)prow, (int)half * 8)]);
+    int4 *const my_cov1 = reinterpret_cast<int4 *>(&w->cov[fine_swz((int)prow, (int)half * 8 + 4)]);
+
+    // items in painter's order: repeatedly take the smallest item id above the last one done
+    uint32_t last_item = 0;
+    bool first = true;
+    for (;;) {
+        uint32_t cur_item = (first || my_item > last_item) ? my_item : 0xffffffffu;
+        if (heavy) {
+            for (uint32_t i = lane; i < n_over; i += 32) {
+                const uint32_t it = A.pool[w->idx[i]].item;
+                if (it >= occ_item1 && (first || it > last_item) && it < cur_item) cur_item = it;
+            }
+            for (uint32_t cur = tail; cur != 0; cur = A.pool[cur - 1u].next) {
+                const uint32_t it = A.pool[cur - 1u].item;
+                if (it >= occ_item1 && (first || it > last_item) && it < cur_item) cur_item = it;
+            }
+        }
+        cur_item = __reduce_min_sync(PM_FULL_MASK, cur_item);
+        if (cur_item == 0xffffffffu) break;
+        first = false;
+        last_item = cur_item;
+
+        // the item's closing record says what it is (DrawFill / Stroke / Circle / Solid)
+        uint32_t t_kind = 0, t_w0 = 0, t_w1 = 0;
+        {
+            const uint32_t m = __ballot_sync(PM_FULL_MASK, my_item == cur_item && (my_key & 15u) >= PM_REC_CIRCLE);
+            if (m) {  // among the inline records: everybody reads it from shared memory
+                const uint4 a = w->rec[2 * (__ffs(m) - 1)];
+                t_kind = a.y & 15u; t_w0 = a.z; t_w1 = a.w;
+            } else if (heavy) {
+                for (uint32_t i = lane; i < n_over; i += 32) {
+                    const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[w->idx[i]]);
+                    if (a.x == cur_item && (a.y & 15u) >= PM_REC_CIRCLE) { t_kind = a.y & 15u; t_w0 = a.z; t_w1 = a.w; }
+                }
+                for (uint32_t cur = tail; cur != 0; cur = A.pool[cur - 1u].next) {
+                    const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[cur - 1u]);
+                    if (a.x == cur_item && (a.y & 15u) >= PM_REC_CIRCLE) { t_kind = a.y & 15u; t_w0 = a.z; t_w1 = a.w; }
+                }
+                const uint32_t src = __ffs(__ballot_sync(PM_FULL_MASK, t_kind != 0));
+                if (src == 0) continue;  // cannot happen for a well-formed list
+                t_kind = __shfl_sync(PM_FULL_MASK, t_kind, src - 1);
+                t_w0 = __shfl_sync(PM_FULL_MASK, t_w0, src - 1);
+                t_w1 = __shfl_sync(PM_FULL_MASK, t_w1, src - 1);
+            } else {
+                continue;  // cannot happen for a well-formed list
+            }
+        }
+
+        // per-pixel blend factor of this item for the lane's 8 pixels
+        float fg[4] = {0.0f, 0.0f, 0.0f, 1.0f};  // Cmd_Circle paints black (metal:491)
+        float alpha[8];
+        if (t_kind == PM_REC_DRAWFILL || t_kind == PM_REC_STROKE) {
+            const bool stroke = t_kind == PM_REC_STROKE;
+            const float half_width = pm_u2f(t_w0);
+            const float reach = half_width + 0.5f;
+            // phase A: coverage of the item's segments, 32 records at a time
+            {
+                const bool mine = my_item == cur_item && (my_key & 15u) <= PM_REC_LINE;
+                if (__any_sync(PM_FULL_MASK, mine)) {
+                    PmRecord rc;
+                    rc.item = my_item; rc.key = my_key;
+                    const uint4 a = w->rec[2 * (lane & (PM_TILE_SLOTS - 1))], b = w->rec[2 * (lane & (PM_TILE_SLOTS - 1)) + 1];
+                    rc.p[0] = pm_u2f(a.z); rc.p[1] = pm_u2f(a.w); rc.p[2] = pm_u2f(b.x); rc.p[3] = pm_u2f(b.y);
+                    rc.edge_y = pm_u2f(b.z); rc.next = 0;
+                    fine_pairs(acc, mine, rc, stroke, reach, tile_x0, tile_y0, lane);
+                }
+            }
+            if (heavy) {
+                for (uint32_t c = 1; c < n_chunks; c++) {
+                    const uint32_t i = (c - 1u) * 32u + lane;
+                    PmRecord rc;
+                    rc.item = 0xffffffffu; rc.key = 0; rc.p[0] = rc.p[1] = rc.p[2] = rc.p[3] = 0.0f; rc.edge_y = 0.0f; rc.next = 0;
+                    if (i < n_over) rc = load_record(A.pool, w->idx[i]);
+                    const bool mine = rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE;
+                    if (__any_sync(PM_FULL_MASK, mine)) fine_pairs(acc, mine, rc, stroke, reach, tile_x0, tile_y0, lane);
+                }
+                for (uint32_t cur = tail; cur != 0;) {  // records beyond the shared-memory index, one at a time
+                    PmRecord rc = load_record(A.pool, cur - 1u);
+                    cur = rc.next;
+                    if (rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE) fine_pairs(acc, lane == 0, rc, stroke, reach, tile_x0, tile_y0, lane);
+                }
+            }
+            __syncwarp();
+            // phase B: resolve this lane's 8 pixels and clear them for the next item
+            unpack_fg(t_w1, fg);
+            const int4 a0 = *my_acc0, a1 = *my_acc1;
+            *my_acc0 = make_int4(0, 0, 0, 0);
+            *my_acc1 = make_int4(0, 0, 0, 0);
+            const int accs[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            if (!stroke) {
+                const int4 c0 = *my_cov0, c1 = *my_cov1;
+                *my_cov0 = make_int4(0, 0, 0, 0);
+                *my_cov1 = make_int4(0, 0, 0, 0);
+                const int covs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                int run = 0;
+                #pragma unroll
+                for (int j = 0; j < 8; j++) run += covs[j];
+                const int other = __shfl_xor_sync(PM_FULL_MASK, run, 1);
+                run = half ? other : 0;  // covers of the left half carry into the right half
+                const int backdrop = (int)t_w0;
+                #pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    run += covs[j];
+                    alpha[j] = fg[3] * pm_resolve_fill_alpha(accs[j] + run, backdrop);
+                }
+            } else {
+                #pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float df = accs[j] ? __uint_as_float(~(uint32_t)accs[j]) : 1e9f;
+                    alpha[j] = fg[3] * pm_saturate(half_width + 0.5f - df);  // renderDf, metal:58-60
+                }
+            }
+            __syncwarp();
+        } else if (t_kind == PM_REC_CIRCLE) {
+            const float px0 = tile_x0 + (float)(half * 8u), py = tile_y0 + (float)prow;
+            #pragma unroll 1
+            for (int j = 0; j < 8; j++) {
+                const float a = pm_px_circle_alpha(t_w0, t_w1, px0 + (float)j, py);
+                #pragma unroll
+                for (int jj = 0; jj < 8; jj++) if (jj == j) alpha[jj] = a;
+            }
+        } else {  // PM_REC_SOLID: a translucent full cover
+            unpack_fg(t_w1, fg);
+            #pragma unroll
+            for (int j = 0; j < 8; j++) alpha[j] = fg[3];
+        }
+        // blend (metal:505, :543, :549)
+        #pragma unroll
+        for (int g = 0; g < 2; g++)
+            #pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float4 v = w->rgb[k][g][lane];
+                v.x = mix_fma(v.x, fg[k], alpha[4 * g + 0]);
+                v.y = mix_fma(v.y, fg[k], alpha[4 * g + 1]);
+                v.z = mix_fma(v.z, fg[k], alpha[4 * g + 2]);
+                v.w = mix_fma(v.w, fg[k], alpha[4 * g + 3]);
+                w->rgb[k][g][lane] = v;
+            }
+    }
+
+    // the records are done with: fetch the next tile while this one is encoded and stored
+    __syncwarp();
+    fine_resolve(A, nx, w, n_heavy, n_total, lane);
+
+    #pragma unroll
+    for (int g = 0; g < 2; g++) {
+        const float4 r = w->rgb[0][g][lane], gg = w->rgb[1][g][lane], b = w->rgb[2][g][lane];
+        const uint4 px = make_uint4(encode_pixel<EXACT>(r.x, gg.x, b.x), encode_pixel<EXACT>(r.y, gg.y, b.y),
+                                    encode_pixel<EXACT>(r.z, gg.z, b.z), encode_pixel<EXACT>(r.w, gg.w, b.w));
+        __stcs(reinterpret_cast<uint4 *>(dst) + g, px);
+        if (F32) {  // debug render: the un-quantised values
+            dst32[4 * g + 0] = make_float4(linear_to_srgb<EXACT>(r.x), linear_to_srgb<EXACT>(gg.x), linear_to_srgb<EXACT>(b.x), 1.0f);
+            dst32[4 * g + 1] = make_float4(linear_to_srgb<EXACT>(r.y), linear_to_srgb<EXACT>(gg.y), linear_to_srgb<EXACT>(b.y), 1.0f);
+            dst32[4 * g + 2] = make_float4(linear_to_srgb<EXACT>(r.z), linear_to_srgb<EXACT>(gg.z), linear_to_srgb<EXACT>(b.z), 1.0f);
+            dst32[4 * g + 3] = make_float4(linear_to_srgb<EXACT>(r.w), linear_to_srgb<EXACT>(gg.w), linear_to_srgb<EXACT>(b.w), 1.0f);
+        }
+    }
+}
+
+// 32 consecutive tiles of one tile row; the solid ones are written row-wise: each store
+// instruction covers 512 contiguous bytes (128 pixels) of one pixel row.
+template <bool F32>
+__device__ __forceinline__ void fine_solid_batch(const PmFrameArgs &A, uint32_t batch, uint32_t batches_per_row, uint32_t lane) {
+    const uint32_t row = batch / batches_per_row;
+    const uint32_t t0 = (batch - row * batches_per_row) * 32u;
+    const uint32_t t = t0 + lane;
+    const bool valid = t < A.n_tx;
+    bool solid = false;
+    uint32_t colour = 0xffffffffu;  // solidColor starts as opaque white (metal:74)
+    if (valid) {
+        const size_t tile = (size_t)row * A.n_tx + t;
+        const u64 cw = A.cnt[tile], ow = A.occ[tile];
+        solid = !((uint32_t)(cw >> 32) == A.stamp && (uint32_t)cw != 0u);
+        if (solid && (uint32_t)(ow >> 32) == A.stamp && (uint32_t)ow != 0u)
+            colour = ld_u32(A.scene + A.items_ix + (size_t)((uint32_t)ow - 1u) * PM_ITEM_SIZE + PM_FILL_RGBA);
+    }
+    const uint32_t solid_mask = __ballot_sync(PM_FULL_MASK, solid);
+    if (solid_mask == 0) return;
+    #pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        const uint32_t src = (uint32_t)q * 8u + (lane >> 2);
+        const uint32_t c = __shfl_sync(PM_FULL_MASK, colour, src);
+        if (!((solid_mask >> src) & 1u)) continue;
+        const uint4 v = make_uint4(c, c, c, c);
+        uint8_t *dst = A.fb + (size_t)(row * PM_TILE_H) * A.pitch + ((size_t)t0 * PM_TILE_W + (size_t)q * 128u + lane * 4u) * 4u;
+        #pragma unroll 4
+        for (int y = 0; y < PM_TILE_H; y++) __stcs(reinterpret_cast<uint4 *>(dst + (size_t)y * A.pitch), v);  // streaming: keep L2 for the records
+        if (F32) {
+            float4 f = make_float4((float)(c & 0xff) / 255.0f, (float)((c >> 8) & 0xff) / 255.0f,
+                                   (float)((c >> 16) & 0xff) / 255.0f, (float)(c >> 24) / 255.0f);
+            for (int y = 0; y < PM_TILE_H; y++)
+                for (int xx = 0; xx < 4; xx++) {
+                    float4 *d = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(A.fb32) +
+                        (size_t)(row * PM_TILE_H + y) * A.pitch32) + (t0 * PM_TILE_W + q * 128u + lane * 4u + xx);
+                    *d = f;
+                }
+        }
+    }
+}
+
+template <bool F32, bool EXACT>
+__global__ void __launch_bounds__(PM_FINE_WARPS * 32, 4) k_fine(const PmFrameArgs A) {
+    __shared__ __align__(16) FineWarpSmem s_warp[PM_FINE_WARPS];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    FineWarpSmem *w = &s_warp[warp];
+    for (uint32_t i = lane; i < 256; i += 32) { w->acc[i] = 0; w->cov[i] = 0; }
+    const uint32_t n_complex = A.counters->n_complex, n_heavy = A.counters->n_heavy;
+    const uint32_t n_total = n_complex + n_heavy;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        A.report->n_complex = n_complex;
+        A.report->n_overflow = A.counters->n_overflow;
+        A.report->frame = A.stamp;
+        A.counters_next->n_complex = 0;
+        A.counters_next->n_overflow = 0;
+        A.counters_next->n_heavy = 0;
+    }
+    __syncwarp();
+    const uint32_t batches_per_row = (A.n_tx + 31u) / 32u;
+    const uint32_t n_batches = batches_per_row * A.n_rows;
+    bool complex_left = true, batches_left = true;
+    const bool prefer_complex = warp < PM_FINE_COMPLEX_WARPS;
+    FineNext nx;
+    nx.q = 0; nx.pk = 0; nx.claimed = false; nx.have = false; nx.pass2 = false;
+    while (complex_left || batches_left) {
+        const bool take_complex = complex_left && (prefer_complex || !batches_left);
+        if (take_complex) {
+            // (one call site for the tile code: the kernel is sensitive to its instruction footprint)
+            if (!nx.have) {  // cold start of the pipeline
+                fine_claim(A, nx, lane);
+                fine_resolve(A, nx, w, n_heavy, n_total, lane);
+                if (!nx.have) { complex_left = false; continue; }
+            }
+            const uint32_t pk = nx.pk;
+            const bool skip_heavy = nx.pass2;
+            nx.have = false;
+            fine_claim(A, nx, lane);  // the position after this tile; resolved once this tile's records are done with
+            fine_complex_tile<F32, EXACT>(A, pk, skip_heavy, w, lane, nx, n_heavy, n_total);
+            if (!nx.have) complex_left = false;
+        } else {
+            uint32_t q = 0;
+            if (lane == 0) q = atomicAdd(&A.queue->batch_next, 1u);
+            q = __shfl_sync(PM_FULL_MASK, q, 0);
+            if (q >= n_batches) { batches_left = false; continue; }
+            fine_solid_batch<F32>(A, q, batches_per_row, lane);
+        }
+    }
+}
+
+}  // namespace
+
+int pm_fine_setup(const float *lut512) {
+    cudaError_t e = cudaMemcpyToSymbol(c_fine_lut, lut512, 512 * sizeof(float));
+    if (e != cudaSuccess) return (int)e;
+    // 4 CTAs of 48 KB per SM: ask for the largest shared-memory carve-out
+    cudaFuncSetAttribute(k_fine<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_fine<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_fine<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_fine<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return (int)cudaGetLastError();
+}
+
+void pm_launch_fine(const PmFrameArgs &a, int sm_count, cudaStream_t s) {
+    // persistent: enough CTAs to fill every SM, work pulled from two queues
+    const int grid = sm_count * 4;
+    const bool exact = (a.flags & PM_FLAG_EXACT_SRGB) != 0;
+    if (a.fb32) {  // debug render with the fp32 parity buffer
+        if (exact) k_fine<true, true><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
+        else       k_fine<true, false><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
+    } else {
+        if (exact) k_fine<false, true><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
+        else       k_fine<false, false><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
+    }
+}

@@ -5,11 +5,7 @@
 //   k_bin        one warp per (item, tile row): exact tile tests of TestApp/PietRender.metal:160-454
 //                evaluated per segment and row; appends per-tile records, accumulates backdrops,
 //                resolves opaque full covers with a 64-bit atomic max   (per frame)
-//   k_fine       fill/blend: one warp per tile with records -- renderKernel's arithmetic
-//                (metal:457-566) evaluated sparsely: lanes take (record, pixel row) pairs and add
-//                fixed-point coverage into shared memory, then 8 pixels per lane are blended in
-//                registers and stored -- and 32-tile batches of solid tiles written with full
-//                512-byte rows of 128-bit stores (the fused solid-tile composite, metal:16-44)
+//   k_fine       fill/blend: see pm_fine.cu
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -463,439 +459,6 @@ __global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) 
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// k_fine
-// ---------------------------------------------------------------------------------------------
-#define PM_FINE_WARPS 8
-#define PM_FINE_COMPLEX_WARPS 6    // warps that prefer tiles with records; the rest prefer solid batches
-#define PM_FINE_LIST_CAP 256       // records per tile indexed in shared memory; the rest is re-walked
-#define PM_ACC_STRIDE 17
-
-// Per-warp shared-memory state of the tile being rendered.
-struct FineWarpSmem {
-    int acc[16 * PM_ACC_STRIDE];     // near-pixel coverage, 8.24 fixed point
-    int cov[16 * PM_ACC_STRIDE];     // per-row cover deltas (pixel x and everything right of it)
-    float dmin[16 * PM_ACC_STRIDE];  // stroke distance field
-    uint32_t idx[PM_FINE_LIST_CAP];  // pool indices of the tile's records
-};
-
-struct FineAcc {
-    FineWarpSmem *w;
-    __device__ __forceinline__ void near(int row, int j, int fx) { atomicAdd(&w->acc[row * PM_ACC_STRIDE + j], fx); }
-    __device__ __forceinline__ void cover(int row, int j, int fx) { atomicAdd(&w->cov[row * PM_ACC_STRIDE + j], fx); }
-    __device__ __forceinline__ void dist(int row, int j, float d) {  // d >= 0: unsigned order == float order
-        atomicMin(reinterpret_cast<unsigned int *>(&w->dmin[row * PM_ACC_STRIDE + j]), __float_as_uint(d));
-    }
-};
-
-template <bool EXACT>
-__device__ __forceinline__ float linear_to_srgb(float v) {  // metal:563
-    if (v < 0.0031308f) return 12.92f * v;
-    // default: ex2(lg2(v) / 2.4) on the SFU, a few 1e-7 from powf; PM_FLAG_EXACT_SRGB asks for powf
-    float p;
-    if (EXACT) {
-        p = powf(v, 1.0f / 2.4f);
-    } else {  // v in [0.003, ~1]: no denormals, no special cases
-        float l;
-        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(v));
-        l *= 1.0f / 2.4f;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(l));
-    }
-    return 1.055f * p - 0.055f;
-}
-
-// Linear -> sRGB for one pixel, packed RGBA8 (alpha 255).  Out of line: 8 call sites per tile.
-template <bool EXACT>
-__device__ __noinline__ uint32_t encode_pixel(float r, float g, float b) {
-    return pm_unorm8(linear_to_srgb<EXACT>(r)) | (pm_unorm8(linear_to_srgb<EXACT>(g)) << 8) |
-           (pm_unorm8(linear_to_srgb<EXACT>(b)) << 16) | 0xff000000u;
-}
-
-// lut[0..255]: sRGB byte -> linear; lut[256..511]: alpha byte / 255 (unpack_unorm4x8_srgb_to_half)
-__device__ __forceinline__ void unpack_fg(const float *lut, uint32_t rgba, float fg[4]) {
-    fg[0] = lut[rgba & 0xffu];
-    fg[1] = lut[(rgba >> 8) & 0xffu];
-    fg[2] = lut[(rgba >> 16) & 0xffu];
-    fg[3] = lut[256u + (rgba >> 24)];
-}
-
-__device__ __forceinline__ PmRecord load_record(const PmRecord *pool, uint32_t idx) {
-    PmRecord r;
-    const uint4 *src = reinterpret_cast<const uint4 *>(&pool[idx]);
-    uint4 a = src[0], b = src[1];
-    r.item = a.x; r.key = a.y; r.p[0] = pm_u2f(a.z); r.p[1] = pm_u2f(a.w);
-    r.p[2] = pm_u2f(b.x); r.p[3] = pm_u2f(b.y); r.edge_y = pm_u2f(b.z); r.next = b.w;
-    return r;
-}
-
-// Phase A for up to 32 records held one per lane (`mine` = this lane holds a FILL*/LINE record of
-// the current item): the (record, pixel row) pairs are enumerated across the lanes and each lane
-// adds its pair's coverage / distance into shared memory.
-__device__ __noinline__ void fine_pairs(FineAcc &acc, bool mine, const PmRecord &r, bool stroke, float reach,
-                                        float tile_x0, float tile_y0, uint32_t lane) {
-    const uint32_t kind = r.key & 15u;
-    int ra = 1, rb = 0;
-    if (mine) {
-        if (stroke) pm_line_rows(r.p[1], r.p[3], reach, tile_y0, &ra, &rb);
-        else pm_fill_rows(r.p[1], r.p[3], tile_y0, &ra, &rb);
-    }
-    const int cnt = rb >= ra ? rb - ra + 1 : 0;
-    int incl = cnt;
-    #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(PM_FULL_MASK, incl, o);
-        if (lane >= (uint32_t)o) incl += v;
-    }
-    const int excl = incl - cnt;
-    const int total = __shfl_sync(PM_FULL_MASK, incl, 31);
-    for (int q = (int)lane; q - (int)lane < total; q += 32) {
-        // owner = last lane whose exclusive prefix is <= q
-        int lo = 0;
-        #pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            int cand = lo + step;
-            int v = __shfl_sync(PM_FULL_MASK, excl, cand & 31);
-            if (cand < 32 && v <= q) lo = cand;
-        }
-        const int o_excl = __shfl_sync(PM_FULL_MASK, excl, lo);
-        const int o_ra = __shfl_sync(PM_FULL_MASK, ra, lo);
-        float p[4];
-        p[0] = __shfl_sync(PM_FULL_MASK, r.p[0], lo);
-        p[1] = __shfl_sync(PM_FULL_MASK, r.p[1], lo);
-        p[2] = __shfl_sync(PM_FULL_MASK, r.p[2], lo);
-        p[3] = __shfl_sync(PM_FULL_MASK, r.p[3], lo);
-        if (q < total) {
-            const int row = o_ra + (q - o_excl);
-            if (stroke) pm_line_pair(acc, p, reach, row, tile_x0, tile_y0);
-            else pm_fill_pair(acc, p, row, tile_x0, tile_y0);
-        }
-    }
-    // FillEdge commands: one record at a time, lanes 0..15 take the 16 pixel rows
-    if (!stroke) {
-        for (uint32_t em = __ballot_sync(PM_FULL_MASK, mine && kind != PM_REC_FILL); em != 0; em &= em - 1) {
-            const int src = __ffs(em) - 1;
-            const uint32_t e_kind = __shfl_sync(PM_FULL_MASK, kind, src);
-            const float e_y = __shfl_sync(PM_FULL_MASK, r.edge_y, src);
-            if (lane < 16) pm_fill_edge_row(acc, e_kind, e_y, (int)lane, tile_y0);
-        }
-    }
-}
-
-// One tile that owns records.  All 32 lanes execute this together.  Records are handled in chunks
-// of 32, one per lane; the first chunk (all of them, for nearly every tile) stays in registers.
-// Blend/store layout: lane l owns pixel row (l >> 1), pixels 8*(l & 1) .. +7.
-template <bool F32, bool EXACT, bool GENERAL>
-__device__ __forceinline__ void fine_complex_tile_impl(const PmFrameArgs &A, uint32_t packed_tile, u64 cw, u64 ow, FineWarpSmem *w, const float *lut, uint32_t lane) {
-    const uint32_t trow = packed_tile >> 16, tx = packed_tile & 0xffffu;
-    const uint32_t tile = trow * A.n_tx + tx;
-    const uint32_t n = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
-    const uint32_t occ_item1 = (uint32_t)(ow >> 32) == A.stamp ? (uint32_t)ow : 0u;
-
-    // index the records: inline slots first, then the overflow chain.  n_cached counts what was
-    // actually found (a frame whose overflow pool ran out has fewer links than cnt says; the host
-    // re-renders such a frame, it only must not fault).
-    const uint32_t n_inline = n < PM_TILE_SLOTS ? n : PM_TILE_SLOTS;
-    uint32_t n_cached = n_inline;
-    uint32_t tail = 0;  // 1 + pool index of the first record that did not fit the shared-memory index
-    if (GENERAL && n > PM_TILE_SLOTS) {
-        if (lane < PM_TILE_SLOTS) w->idx[lane] = tile * PM_TILE_SLOTS + lane;
-        const u64 vw = A.ovf[tile];
-        uint32_t cur = (uint32_t)(vw >> 32) == A.stamp ? (uint32_t)vw : 0u;
-        while (cur != 0 && n_cached < PM_FINE_LIST_CAP) {
-            if (lane == 0) w->idx[n_cached] = cur - 1u;
-            cur = A.pool[cur - 1u].next;
-            n_cached++;
-        }
-        tail = cur;
-        __syncwarp();
-    }
-    const uint32_t n_chunks = GENERAL ? (n_cached + 31u) >> 5 : 1u;
-    // chunk 0 lives in registers for the whole tile
-    PmRecord r0;
-    r0.item = 0xffffffffu; r0.key = 0; r0.p[0] = r0.p[1] = r0.p[2] = r0.p[3] = 0.0f; r0.edge_y = 0.0f; r0.next = 0;
-    if (lane < n_cached) r0 = load_record(A.pool, (GENERAL && n > PM_TILE_SLOTS) ? w->idx[lane] : tile * PM_TILE_SLOTS + lane);
-    if (r0.item < occ_item1) r0.item = 0xffffffffu;  // below the topmost opaque cover: rewound away (metal:132-135)
-
-    bool has_draw = r0.item != 0xffffffffu && (r0.key & 15u) != PM_REC_SOLID;
-    for (uint32_t c = 1; GENERAL && c < n_chunks; c++) {
-        const uint32_t i = c * 32u + lane;
-        if (i < n_cached) {
-            const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[w->idx[i]]);
-            if (ik.x >= occ_item1 && (ik.y & 15u) != PM_REC_SOLID) has_draw = true;
-        }
-    }
-    for (uint32_t cur = tail; GENERAL && cur != 0; cur = A.pool[cur - 1u].next) {
-        const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[cur - 1u]);
-        if (ik.x >= occ_item1 && (ik.y & 15u) != PM_REC_SOLID) has_draw = true;
-    }
-    has_draw = __any_sync(PM_FULL_MASK, has_draw);
-
-    const uint32_t prow = lane >> 1, half = lane & 1u;
-    uint8_t *dst = A.fb + (size_t)(trow * PM_TILE_H + prow) * A.pitch + (size_t)(tx * PM_TILE_W + half * 8u) * 4u;
-    float4 *dst32 = nullptr;
-    if (F32) dst32 = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(A.fb32) + (size_t)(trow * PM_TILE_H + prow) * A.pitch32) +
-                     (tx * PM_TILE_W + half * 8u);
-
-    uint32_t occ_rgba = 0xffffffffu;  // solidColor starts as opaque white (metal:74)
-    if (occ_item1) occ_rgba = ld_u32(A.scene + A.items_ix + (size_t)(occ_item1 - 1u) * PM_ITEM_SIZE + PM_FILL_RGBA);
-
-    if (!has_draw) {
-        // Only Solid commands after the last rewind: the tile Bails and shows solidColor (metal:145-147, :34-44)
-        const uint32_t c = occ_rgba;
-        const uint4 v = make_uint4(c, c, c, c);
-        __stcs(reinterpret_cast<uint4 *>(dst), v);
-        __stcs(reinterpret_cast<uint4 *>(dst) + 1, v);
-        if (F32) {
-            const float4 f = make_float4((float)(c & 0xff) / 255.0f, (float)((c >> 8) & 0xff) / 255.0f,
-                                         (float)((c >> 16) & 0xff) / 255.0f, (float)(c >> 24) / 255.0f);
-            for (int j = 0; j < 8; j++) dst32[j] = f;
-        }
-        return;
-    }
-
-    float rgb[8][3];
-    #pragma unroll
-    for (int j = 0; j < 8; j++) rgb[j][0] = rgb[j][1] = rgb[j][2] = 1.0f;  // metal:470
-    if (occ_item1) {  // the rewound list starts with the cover's Cmd_Solid (metal:136-142, :546-551): same for every pixel
-        float fg[4];
-        unpack_fg(lut, occ_rgba, fg);
-        const float b0 = pm_mix(1.0f, fg[0], fg[3]), b1 = pm_mix(1.0f, fg[1], fg[3]), b2 = pm_mix(1.0f, fg[2], fg[3]);
-        #pragma unroll
-        for (int j = 0; j < 8; j++) { rgb[j][0] = b0; rgb[j][1] = b1; rgb[j][2] = b2; }
-    }
-    const float tile_x0 = (float)(tx * PM_TILE_W), tile_y0 = (float)((A.tile_y0 + trow) * PM_TILE_H);  // scene coordinates
-    const float px0 = tile_x0 + (float)(half * 8u), py = tile_y0 + (float)prow;
-    FineAcc acc{w};
-    int *my_acc = &w->acc[prow * PM_ACC_STRIDE + half * 8u];
-    int *my_cov = &w->cov[prow * PM_ACC_STRIDE + half * 8u];
-    float *my_dmin = &w->dmin[prow * PM_ACC_STRIDE + half * 8u];
-
-    // items in painter's order: repeatedly take the smallest item id above the last one done
-    uint32_t last_item = 0;
-    bool first = true;
-    for (;;) {
-        uint32_t cur_item = (first || r0.item > last_item) ? r0.item : 0xffffffffu;
-        for (uint32_t c = 1; GENERAL && c < n_chunks; c++) {
-            const uint32_t i = c * 32u + lane;
-            if (i < n_cached) {
-                const uint32_t it = A.pool[w->idx[i]].item;
-                if (it >= occ_item1 && (first || it > last_item) && it < cur_item) cur_item = it;
-            }
-        }
-        for (uint32_t cur = tail; GENERAL && cur != 0; cur = A.pool[cur - 1u].next) {
-            const uint32_t it = A.pool[cur - 1u].item;
-            if (it >= occ_item1 && (first || it > last_item) && it < cur_item) cur_item = it;
-        }
-        cur_item = __reduce_min_sync(PM_FULL_MASK, cur_item);
-        if (cur_item == 0xffffffffu) break;
-        first = false;
-        last_item = cur_item;
-
-        // the item's closing record says what it is (DrawFill / Stroke / Circle / Solid)
-        uint32_t t_kind = 0, t_w0 = 0, t_w1 = 0;
-        if (r0.item == cur_item && (r0.key & 15u) >= PM_REC_CIRCLE) { t_kind = r0.key & 15u; t_w0 = pm_f2u(r0.p[0]); t_w1 = pm_f2u(r0.p[1]); }
-        for (uint32_t c = 1; GENERAL && c < n_chunks; c++) {
-            const uint32_t i = c * 32u + lane;
-            if (i < n_cached) {
-                const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[w->idx[i]]);
-                if (a.x == cur_item && (a.y & 15u) >= PM_REC_CIRCLE) { t_kind = a.y & 15u; t_w0 = a.z; t_w1 = a.w; }
-            }
-        }
-        for (uint32_t cur = tail; GENERAL && cur != 0; cur = A.pool[cur - 1u].next) {
-            const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[cur - 1u]);
-            if (a.x == cur_item && (a.y & 15u) >= PM_REC_CIRCLE) { t_kind = a.y & 15u; t_w0 = a.z; t_w1 = a.w; }
-        }
-        {
-            const uint32_t src = __ffs(__ballot_sync(PM_FULL_MASK, t_kind != 0));
-            if (src == 0) continue;  // cannot happen for a well-formed list
-            t_kind = __shfl_sync(PM_FULL_MASK, t_kind, src - 1);
-            t_w0 = __shfl_sync(PM_FULL_MASK, t_w0, src - 1);
-            t_w1 = __shfl_sync(PM_FULL_MASK, t_w1, src - 1);
-        }
-
-        // per-pixel blend factor of this item for the lane's 8 pixels, then one shared blend
-        float fg[4] = {0.0f, 0.0f, 0.0f, 1.0f};  // Cmd_Circle paints black (metal:491)
-        float alpha[8];
-        if (t_kind == PM_REC_DRAWFILL || t_kind == PM_REC_STROKE) {
-            const bool stroke = t_kind == PM_REC_STROKE;
-            const float half_width = pm_u2f(t_w0);
-            const float reach = half_width + 0.5f;
-            // phase A: coverage of the item's segments, 32 records at a time
-            for (uint32_t c = 0; c < n_chunks; c++) {
-                PmRecord rc = r0;
-                if (GENERAL && c > 0) {
-                    const uint32_t i = c * 32u + lane;
-                    rc.item = 0xffffffffu;
-                    if (i < n_cached) rc = load_record(A.pool, w->idx[i]);
-                }
-                const bool mine = rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE;
-                if (__any_sync(PM_FULL_MASK, mine)) fine_pairs(acc, mine, rc, stroke, reach, tile_x0, tile_y0, lane);
-            }
-            for (uint32_t cur = tail; GENERAL && cur != 0;) {  // records beyond the shared-memory index, one at a time
-                PmRecord rc = load_record(A.pool, cur - 1u);
-                cur = rc.next;
-                if (rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE) fine_pairs(acc, lane == 0, rc, stroke, reach, tile_x0, tile_y0, lane);
-            }
-            __syncwarp();
-            // phase B: resolve this lane's 8 pixels
-            unpack_fg(lut, t_w1, fg);
-            if (!stroke) {
-                int covs[8], accs[8], run = 0;
-                #pragma unroll
-                for (int j = 0; j < 8; j++) { covs[j] = my_cov[j]; accs[j] = my_acc[j]; my_cov[j] = 0; my_acc[j] = 0; run += covs[j]; }
-                const int other = __shfl_xor_sync(PM_FULL_MASK, run, 1);
-                run = half ? other : 0;  // covers of the left half carry into the right half
-                const int backdrop = (int)t_w0;
-                #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    run += covs[j];
-                    alpha[j] = fg[3] * pm_resolve_fill_alpha(accs[j] + run, backdrop);
-                }
-            } else {
-                #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float df = my_dmin[j];
-                    my_dmin[j] = 1e9f;
-                    alpha[j] = fg[3] * pm_saturate(half_width + 0.5f - df);  // renderDf, metal:58-60
-                }
-            }
-            __syncwarp();
-        } else if (t_kind == PM_REC_CIRCLE) {
-            #pragma unroll 1
-            for (int j = 0; j < 8; j++) {
-                const float a = pm_px_circle_alpha(t_w0, t_w1, px0 + (float)j, py);
-                #pragma unroll
-                for (int jj = 0; jj < 8; jj++) if (jj == j) alpha[jj] = a;
-            }
-        } else {  // PM_REC_SOLID: a translucent full cover
-            unpack_fg(lut, t_w1, fg);
-            #pragma unroll
-            for (int j = 0; j < 8; j++) alpha[j] = fg[3];
-        }
-        #pragma unroll
-        for (int j = 0; j < 8; j++)
-            #pragma unroll
-            for (int k = 0; k < 3; k++) rgb[j][k] = pm_mix(rgb[j][k], fg[k], alpha[j]);
-    }
-
-    uint32_t packed[8];
-    #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        packed[j] = encode_pixel<EXACT>(rgb[j][0], rgb[j][1], rgb[j][2]);
-        if (F32)  // debug render: the un-quantised values
-            dst32[j] = make_float4(linear_to_srgb<EXACT>(rgb[j][0]), linear_to_srgb<EXACT>(rgb[j][1]), linear_to_srgb<EXACT>(rgb[j][2]), 1.0f);
-    }
-    __stcs(reinterpret_cast<uint4 *>(dst), make_uint4(packed[0], packed[1], packed[2], packed[3]));
-    __stcs(reinterpret_cast<uint4 *>(dst) + 1, make_uint4(packed[4], packed[5], packed[6], packed[7]));
-}
-
-// One copy of the tile code for every record count: a second, leaner copy for small tiles was tried
-// and lost -- the kernel is instruction-cache bound and two warm copies thrash it.
-template <bool F32, bool EXACT>
-__device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t packed_tile, u64 cw, u64 ow, FineWarpSmem *w, const float *lut, uint32_t lane) {
-    fine_complex_tile_impl<F32, EXACT, true>(A, packed_tile, cw, ow, w, lut, lane);
-}
-
-// 32 consecutive tiles of one tile row; the solid ones are written row-wise: each store
-// instruction covers 512 contiguous bytes (128 pixels) of one pixel row.
-template <bool F32>
-__device__ void fine_solid_batch(const PmFrameArgs &A, uint32_t batch, uint32_t batches_per_row, uint32_t lane) {
-    const uint32_t row = batch / batches_per_row;
-    const uint32_t t0 = (batch - row * batches_per_row) * 32u;
-    const uint32_t t = t0 + lane;
-    const bool valid = t < A.n_tx;
-    bool solid = false;
-    uint32_t colour = 0xffffffffu;  // solidColor starts as opaque white (metal:74)
-    if (valid) {
-        const size_t tile = (size_t)row * A.n_tx + t;
-        const u64 cw = A.cnt[tile], ow = A.occ[tile];
-        solid = !((uint32_t)(cw >> 32) == A.stamp && (uint32_t)cw != 0u);
-        if (solid && (uint32_t)(ow >> 32) == A.stamp && (uint32_t)ow != 0u)
-            colour = ld_u32(A.scene + A.items_ix + (size_t)((uint32_t)ow - 1u) * PM_ITEM_SIZE + PM_FILL_RGBA);
-    }
-    const uint32_t solid_mask = __ballot_sync(PM_FULL_MASK, solid);
-    if (solid_mask == 0) return;
-    #pragma unroll 1
-    for (int q = 0; q < 4; q++) {
-        const uint32_t src = (uint32_t)q * 8u + (lane >> 2);
-        const uint32_t c = __shfl_sync(PM_FULL_MASK, colour, src);
-        if (!((solid_mask >> src) & 1u)) continue;
-        const uint4 v = make_uint4(c, c, c, c);
-        uint8_t *dst = A.fb + (size_t)(row * PM_TILE_H) * A.pitch + ((size_t)t0 * PM_TILE_W + (size_t)q * 128u + lane * 4u) * 4u;
-        #pragma unroll 4
-        for (int y = 0; y < PM_TILE_H; y++) __stcs(reinterpret_cast<uint4 *>(dst + (size_t)y * A.pitch), v);  // streaming: keep L2 for the records
-        if (F32) {
-            float4 f = make_float4((float)(c & 0xff) / 255.0f, (float)((c >> 8) & 0xff) / 255.0f,
-                                   (float)((c >> 16) & 0xff) / 255.0f, (float)(c >> 24) / 255.0f);
-            for (int y = 0; y < PM_TILE_H; y++)
-                for (int xx = 0; xx < 4; xx++) {
-                    float4 *d = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(A.fb32) +
-                        (size_t)(row * PM_TILE_H + y) * A.pitch32) + (t0 * PM_TILE_W + q * 128u + lane * 4u + xx);
-                    *d = f;
-                }
-        }
-    }
-}
-
-template <bool F32, bool EXACT>
-__global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArgs A) {
-    __shared__ float s_lut[512];
-    __shared__ FineWarpSmem s_warp[PM_FINE_WARPS];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t i = threadIdx.x; i < 512; i += blockDim.x) s_lut[i] = A.srgb_lut[i];
-    FineWarpSmem *w = &s_warp[warp];
-    for (uint32_t i = lane; i < 16 * PM_ACC_STRIDE; i += 32) { w->acc[i] = 0; w->cov[i] = 0; w->dmin[i] = 1e9f; }
-    const uint32_t n_complex = A.counters->n_complex, n_heavy = A.counters->n_heavy;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        A.report->n_complex = n_complex;
-        A.report->n_overflow = A.counters->n_overflow;
-        A.report->frame = A.stamp;
-        A.counters_next->n_complex = 0;
-        A.counters_next->n_overflow = 0;
-        A.counters_next->n_heavy = 0;
-    }
-    __syncthreads();
-    const uint32_t batches_per_row = (A.n_tx + 31u) / 32u;
-    const uint32_t n_batches = batches_per_row * A.n_rows;
-    bool complex_left = true, batches_left = true, heavy_left = true;
-    const bool prefer_complex = warp < PM_FINE_COMPLEX_WARPS;
-    while (complex_left || batches_left) {
-        const bool take_complex = complex_left && (prefer_complex || !batches_left);
-        if (take_complex) {
-            // Tiles with records, one per queue access.  Pass 1 renders the heavy ones (more records than
-            // inline slots: coincident outlines, deep stacks), which binning listed separately; pass 2
-            // walks the full list and skips them.  Heavy tiles first keeps a 20-microsecond tile from
-            // starting when everybody else is done; one tile per access spreads list neighbours (which
-            // tend to be equally heavy) over as many warps as possible.
-            // (one call site for the tile code: the kernel is instruction-cache bound)
-            uint32_t pk = 0;
-            u64 cw = 0;
-            bool have = false;
-            {
-                const uint32_t n_list = heavy_left ? n_heavy : n_complex;
-                uint32_t q = 0;
-                if (lane == 0) q = atomicAdd(heavy_left ? &A.queue->heavy_next : &A.queue->complex_next, 1u);
-                q = __shfl_sync(PM_FULL_MASK, q, 0);
-                if (q >= n_list) {
-                    if (heavy_left) heavy_left = false; else complex_left = false;
-                    continue;
-                }
-                pk = A.complex_list[(heavy_left ? A.n_rows * A.n_tx : 0u) + q];
-                cw = A.cnt[(pk >> 16) * A.n_tx + (pk & 0xffffu)];
-                // pass 2 skips what pass 1 rendered (the stamp is this frame's: the tile is on the list)
-                have = heavy_left || (uint32_t)cw <= PM_TILE_SLOTS;
-            }
-            if (have) fine_complex_tile<F32, EXACT>(A, pk, cw, A.occ[(pk >> 16) * A.n_tx + (pk & 0xffffu)], w, s_lut, lane);
-        } else {
-            uint32_t q = 0;
-            if (lane == 0) q = atomicAdd(&A.queue->batch_next, 1u);
-            q = __shfl_sync(PM_FULL_MASK, q, 0);
-            if (q >= n_batches) { batches_left = false; continue; }
-            fine_solid_batch<F32>(A, q, batches_per_row, lane);
-        }
-    }
-}
-
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -923,14 +486,5 @@ void pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, cudaSt
     k_seg<<<grid_seg, 256, 0, s>>>(a);
     if (a.n_row_units) k_row<<<(a.n_row_units + PM_ROW_WARPS - 1) / PM_ROW_WARPS, PM_ROW_WARPS * 32, 0, s>>>(a);
     if (mid) cudaEventRecord(mid, s);
-    // persistent fill kernel: enough CTAs to fill every SM, work pulled from two queues
-    int grid = sm_count * 4;
-    const bool exact = (a.flags & PM_FLAG_EXACT_SRGB) != 0;
-    if (a.fb32) {  // debug render with the fp32 parity buffer
-        if (exact) k_fine<true, true><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
-        else       k_fine<true, false><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
-    } else {
-        if (exact) k_fine<false, true><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
-        else       k_fine<false, false><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
-    }
+    pm_launch_fine(a, sm_count, s);
 }
