@@ -35,8 +35,6 @@ typedef unsigned long long u64;
 #define PM_FINE_COMPLEX_WARPS 6  // warps that prefer tiles with records; the rest prefer solid batches
 #define PM_FINE_LIST_CAP 96      // overflow records per tile indexed in shared memory; the rest is re-walked
 
-__constant__ float c_fine_lut[512];  // [0,256): sRGB byte -> linear; [256,512): alpha byte / 255
-
 __device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
 
 // Per-warp shared-memory state.
@@ -45,13 +43,13 @@ __device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return *reinterpr
 //     atomics of the accumulation both spread over the banks.  For a stroke, acc holds the maximum
 //     of ~bits(distance) instead (0 = no segment near), so one zero fill serves both.
 //   rgb: lane-private, [channel][4-pixel group][lane].
-//   rec / hdr: the prefetched tile: 16 inline record slots and its cnt / occ / ovf words.
+//   rec / hdr: two prefetch buffers, each the 16 inline record slots of a tile and its cnt / occ / ovf words.
 struct FineWarpSmem {
     int acc[256];
     int cov[256];
     float4 rgb[3][2][32];
-    uint4 rec[2 * PM_TILE_SLOTS];
-    u64 hdr[4];
+    uint4 rec[2][2 * PM_TILE_SLOTS];
+    u64 hdr[2][4];
     uint32_t idx[PM_FINE_LIST_CAP];
 };
 
@@ -119,11 +117,13 @@ __device__ __forceinline__ uint32_t encode_pixel(float r, float g, float b) {
 // two of x + (y - x) * a)
 __device__ __forceinline__ float mix_fma(float x, float y, float a) { return __fmaf_rn(a, y, __fmaf_rn(-a, x, x)); }
 
-__device__ __forceinline__ void unpack_fg(uint32_t rgba, float fg[4]) {  // unpack_unorm4x8_srgb_to_half
-    fg[0] = c_fine_lut[rgba & 0xffu];
-    fg[1] = c_fine_lut[(rgba >> 8) & 0xffu];
-    fg[2] = c_fine_lut[(rgba >> 16) & 0xffu];
-    fg[3] = c_fine_lut[256u + (rgba >> 24)];
+// unpack_unorm4x8_srgb_to_half; lut[0..255]: sRGB byte -> linear, lut[256..511]: alpha byte / 255
+// (2 KB of global memory that lives in L1: the index is the same for the whole warp)
+__device__ __forceinline__ void unpack_fg(const float *lut, uint32_t rgba, float fg[4]) {
+    fg[0] = __ldg(&lut[rgba & 0xffu]);
+    fg[1] = __ldg(&lut[(rgba >> 8) & 0xffu]);
+    fg[2] = __ldg(&lut[(rgba >> 16) & 0xffu]);
+    fg[3] = __ldg(&lut[256u + (rgba >> 24)]);
 }
 
 __device__ __forceinline__ PmRecord record_from(const uint4 a, const uint4 b) {
@@ -190,66 +190,79 @@ __device__ __noinline__ void fine_pairs(FineAcc &acc, bool mine, const PmRecord 
     }
 }
 
-// Pipeline state of a warp that walks the list of tiles with records.
+// Pipeline state of a warp that walks the list of tiles with records.  While tile i is rendered, the
+// header and inline records of tile i+1 are in flight into the other half of the shared-memory
+// buffer, and the queue position of tile i+2 has been claimed; its list entry is loaded when the
+// coverage of tile i is done.  No global-memory latency of the chain
+//   queue counter -> list entry -> cnt / occ / record slots
+// is exposed once the pipeline runs.
+// List order: the heavy tiles (more records than inline slots: coincident outlines, deep stacks)
+// first, then the full list, in which the heavy ones are skipped.  Heavy first keeps a long tile
+// from starting when everybody else is done.
 struct FineNext {
-    uint32_t q;      // lane 0: the claimed queue position
-    uint32_t pk;     // packed (row, column) of the next tile
-    bool claimed;    // a queue position has been claimed and not resolved yet
-    bool have;       // pk is valid and its prefetch has been issued
-    bool pass2;      // next tile comes from the full list (skip it if pass 1 rendered it)
+    uint32_t q;           // lane 0: the queue position claimed last
+    uint32_t pk1, pk2;    // packed (row, column) of the next tile and of the one after it
+    bool have1, have2;
 };
 
 __device__ __forceinline__ void fine_claim(const PmFrameArgs &A, FineNext &nx, uint32_t lane) {
     if (lane == 0) nx.q = atomicAdd(&A.queue->complex_next, 1u);
-    nx.claimed = true;
 }
-
-// Turns the claimed position into a tile and starts the copy of its header and inline records.
-// List order: the heavy tiles (more records than inline slots: coincident outlines, deep stacks)
-// first, then the full list, in which the heavy ones are skipped.  Heavy first keeps a long tile
-// from starting when everybody else is done.
-__device__ __forceinline__ void fine_resolve(const PmFrameArgs &A, FineNext &nx, FineWarpSmem *w, uint32_t n_heavy, uint32_t n_total, uint32_t lane) {
+// Turns the claimed position into a list entry: bit 15 of the column half marks "from the full list"
+__device__ __forceinline__ bool fine_entry(const PmFrameArgs &A, const FineNext &nx, uint32_t n_heavy, uint32_t n_total, uint32_t *pk) {
     const uint32_t q = __shfl_sync(PM_FULL_MASK, nx.q, 0);
-    nx.claimed = false;
-    nx.have = q < n_total;
-    if (!nx.have) return;
-    nx.pass2 = q >= n_heavy;
-    nx.pk = nx.pass2 ? A.complex_list[q - n_heavy] : A.complex_list[A.n_rows * A.n_tx + q];
-    const size_t tile = (size_t)(nx.pk >> 16) * A.n_tx + (nx.pk & 0xffffu);
-    cp_async16(&w->rec[lane], reinterpret_cast<const uint4 *>(&A.pool[tile * PM_TILE_SLOTS]) + lane);
-    if (lane < 3) cp_async8(&w->hdr[lane], lane == 0 ? &A.cnt[tile] : (lane == 1 ? &A.occ[tile] : &A.ovf[tile]));
+    if (q >= n_total) return false;
+    *pk = q >= n_heavy ? (__ldg(&A.complex_list[q - n_heavy]) | 0x8000u) : __ldg(&A.complex_list[A.n_rows * A.n_tx + q]);
+    return true;
+}
+// Starts the copy of a tile's header words and inline record slots into buffer `p`.
+__device__ __forceinline__ void fine_prefetch(const PmFrameArgs &A, FineWarpSmem *w, uint32_t p, uint32_t pk, uint32_t lane) {
+    const size_t tile = (size_t)(pk >> 16) * A.n_tx + (pk & 0x7fffu);
+    cp_async16(&w->rec[p][lane], reinterpret_cast<const uint4 *>(&A.pool[tile * PM_TILE_SLOTS]) + lane);
+    if (lane < 3) cp_async8(&w->hdr[p][lane], lane == 0 ? &A.cnt[tile] : (lane == 1 ? &A.occ[tile] : &A.ovf[tile]));
     cp_async_commit();
 }
+// the second half of a pipeline step: the claim made at the start of the tile has long returned
+__device__ __forceinline__ void fine_step2(const PmFrameArgs &A, FineNext &nx, uint32_t n_heavy, uint32_t n_total) {
+    if (nx.have1) nx.have2 = fine_entry(A, nx, n_heavy, n_total, &nx.pk2);
+}
 
-// One tile that owns records; its header and inline records are in w->hdr / w->rec.  All 32 lanes
+// One tile that owns records; its header and inline records are in buffer `p` of w.  All 32 lanes
 // execute this together.  Records are handled in chunks of 32, one per lane; chunk 0 is the inline
 // slots.  Pixel layout: lane l owns pixel row (l >> 1), pixels 8*(l & 1) .. +7.
-// When the records are no longer needed, the next tile of the list is resolved and prefetched.
 template <bool F32, bool EXACT>
-__device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t packed_tile, bool skip_heavy, FineWarpSmem *w, uint32_t lane,
+__device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t packed_tile, FineWarpSmem *w, uint32_t p, uint32_t lane,
                                                   FineNext &nx, uint32_t n_heavy, uint32_t n_total) {
-    const uint32_t trow = packed_tile >> 16, tx = packed_tile & 0xffffu;
+    const uint32_t trow = packed_tile >> 16, tx = packed_tile & 0x7fffu;
+    const bool skip_heavy = (packed_tile & 0x8000u) != 0;
     cp_async_wait_all();
     __syncwarp();
-    const u64 cw = w->hdr[0], ow = w->hdr[1];
+    // first half of the pipeline step: next tile's data on its way, the position after it claimed
+    nx.have2 = false;
+    if (nx.have1) {
+        fine_prefetch(A, w, p ^ 1u, nx.pk1, lane);
+        fine_claim(A, nx, lane);
+    }
+    const uint4 *rec = w->rec[p];
+    const u64 cw = w->hdr[p][0], ow = w->hdr[p][1];
     const uint32_t n = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
     const uint32_t occ_item1 = (uint32_t)(ow >> 32) == A.stamp ? (uint32_t)ow : 0u;
     const bool heavy = n > PM_TILE_SLOTS;
     if (heavy && skip_heavy) {  // pass 1 rendered it
-        fine_resolve(A, nx, w, n_heavy, n_total, lane);
+        fine_step2(A, nx, n_heavy, n_total);
         return;
     }
     uint32_t occ_rgba = 0xffffffffu;  // solidColor starts as opaque white (metal:74)
-    if (occ_item1) occ_rgba = ld_u32(A.scene + A.items_ix + (size_t)(occ_item1 - 1u) * PM_ITEM_SIZE + PM_FILL_RGBA);
+    if (occ_item1) occ_rgba = __ldg(reinterpret_cast<const uint32_t *>(A.scene + A.items_ix + (size_t)(occ_item1 - 1u) * PM_ITEM_SIZE + PM_FILL_RGBA));
 
-    // index the overflow chain.  n_cached counts what was actually found (a frame whose overflow
+    // index the overflow chain.  n_over counts what was actually found (a frame whose overflow
     // pool ran out has fewer links than cnt says; the host re-renders such a frame, it only must
     // not fault).
     const uint32_t n_inline = heavy ? PM_TILE_SLOTS : n;
     uint32_t n_over = 0;
     uint32_t tail = 0;  // 1 + pool index of the first record that did not fit the shared-memory index
     if (heavy) {
-        const u64 vw = w->hdr[2];
+        const u64 vw = w->hdr[p][2];
         uint32_t cur = (uint32_t)(vw >> 32) == A.stamp ? (uint32_t)vw : 0u;
         while (cur != 0 && n_over < PM_FINE_LIST_CAP) {
             if (lane == 0) w->idx[n_over] = cur - 1u;
@@ -264,7 +277,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
     // this lane's inline record: item and key stay in registers, the geometry is re-read when needed
     uint32_t my_item = 0xffffffffu, my_key = 0;
     if (lane < n_inline) {
-        const uint2 ik = *reinterpret_cast<const uint2 *>(&w->rec[2 * lane]);
+        const uint2 ik = *reinterpret_cast<const uint2 *>(&rec[2 * lane]);
         my_item = ik.x; my_key = ik.y;
     }
     if (my_item < occ_item1) my_item = 0xffffffffu;  // below the topmost opaque cover: rewound away (metal:132-135)
@@ -290,7 +303,6 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
 
     if (!has_draw) {
         // Only Solid commands after the last rewind: the tile Bails and shows solidColor (metal:145-147, :34-44)
-        fine_resolve(A, nx, w, n_heavy, n_total, lane);
         const uint32_t c = occ_rgba;
         const uint4 v = make_uint4(c, c, c, c);
         __stcs(reinterpret_cast<uint4 *>(dst), v);
@@ -300,14 +312,16 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
                                          (float)((c >> 16) & 0xff) / 255.0f, (float)(c >> 24) / 255.0f);
             for (int j = 0; j < 8; j++) dst32[j] = f;
         }
+        fine_step2(A, nx, n_heavy, n_total);
         return;
     }
 
+    const float *lut = A.srgb_lut;
     {   // the rewound list starts with the cover's Cmd_Solid (metal:136-142, :546-551) over white (metal:470)
         float b0 = 1.0f, b1 = 1.0f, b2 = 1.0f;
         if (occ_item1) {
             float fg[4];
-            unpack_fg(occ_rgba, fg);
+            unpack_fg(lut, occ_rgba, fg);
             b0 = mix_fma(1.0f, fg[0], fg[3]); b1 = mix_fma(1.0f, fg[1], fg[3]); b2 = mix_fma(1.0f, fg[2], fg[3]);
         }
         #pragma unroll
@@ -319,11 +333,8 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
     }
     const float tile_x0 = (float)(tx * PM_TILE_W), tile_y0 = (float)((A.tile_y0 + trow) * PM_TILE_H);  // scene coordinates
     FineAcc acc{w};
-    // this lane's two 4-pixel groups of the coverage arrays
-    int4 *const my_acc0 = reinterpret_cast<int4 *>(&w->acc[fine_swz((int)prow, (int)half * 8)]);
-    int4 *const my_acc1 = reinterpret_cast<int4 *>(&w->acc[fine_swz((int)prow, (int)half * 8 + 4)]);
-    int4 *const my_cov0 = reinterpret_cast<int4 *>(&w->cov[fine_swz((int)prow, (int)half * 8)]);
-    int4 *const my_cov1 = reinterpret_cast<int4 *>(&w->cov[fine_swz((int)prow, (int)half * 8 + 4)]);
+    // this lane's two 4-pixel groups of the coverage arrays (word offsets; cov = acc + 256)
+    const int my_off0 = fine_swz((int)prow, (int)half * 8), my_off1 = fine_swz((int)prow, (int)half * 8 + 4);
 
     // items in painter's order: repeatedly take the smallest item id above the last one done
     uint32_t last_item = 0;
@@ -350,7 +361,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
         {
             const uint32_t m = __ballot_sync(PM_FULL_MASK, my_item == cur_item && (my_key & 15u) >= PM_REC_CIRCLE);
             if (m) {  // among the inline records: everybody reads it from shared memory
-                const uint4 a = w->rec[2 * (__ffs(m) - 1)];
+                const uint4 a = rec[2 * (__ffs(m) - 1)];
                 t_kind = a.y & 15u; t_w0 = a.z; t_w1 = a.w;
             } else if (heavy) {
                 for (uint32_t i = lane; i < n_over; i += 32) {
@@ -371,12 +382,12 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
             }
         }
 
-        // per-pixel blend factor of this item for the lane's 8 pixels
         float fg[4] = {0.0f, 0.0f, 0.0f, 1.0f};  // Cmd_Circle paints black (metal:491)
-        float alpha[8];
-        if (t_kind == PM_REC_DRAWFILL || t_kind == PM_REC_STROKE) {
-            const bool stroke = t_kind == PM_REC_STROKE;
-            const float half_width = pm_u2f(t_w0);
+        const bool stroke = t_kind == PM_REC_STROKE, fill = t_kind == PM_REC_DRAWFILL;
+        const float half_width = pm_u2f(t_w0);
+        int run = 0;  // fill: cover entering this lane's pixels from the left
+        if (t_kind != PM_REC_CIRCLE) unpack_fg(lut, t_w1, fg);
+        if (fill || stroke) {
             const float reach = half_width + 0.5f;
             // phase A: coverage of the item's segments, 32 records at a time
             {
@@ -384,7 +395,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
                 if (__any_sync(PM_FULL_MASK, mine)) {
                     PmRecord rc;
                     rc.item = my_item; rc.key = my_key;
-                    const uint4 a = w->rec[2 * (lane & (PM_TILE_SLOTS - 1))], b = w->rec[2 * (lane & (PM_TILE_SLOTS - 1)) + 1];
+                    const uint4 a = rec[2 * (lane & (PM_TILE_SLOTS - 1))], b = rec[2 * (lane & (PM_TILE_SLOTS - 1)) + 1];
                     rc.p[0] = pm_u2f(a.z); rc.p[1] = pm_u2f(a.w); rc.p[2] = pm_u2f(b.x); rc.p[3] = pm_u2f(b.y);
                     rc.edge_y = pm_u2f(b.z); rc.next = 0;
                     fine_pairs(acc, mine, rc, stroke, reach, tile_x0, tile_y0, lane);
@@ -406,68 +417,63 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
                 }
             }
             __syncwarp();
-            // phase B: resolve this lane's 8 pixels and clear them for the next item
-            unpack_fg(t_w1, fg);
-            const int4 a0 = *my_acc0, a1 = *my_acc1;
-            *my_acc0 = make_int4(0, 0, 0, 0);
-            *my_acc1 = make_int4(0, 0, 0, 0);
-            const int accs[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            if (!stroke) {
-                const int4 c0 = *my_cov0, c1 = *my_cov1;
-                *my_cov0 = make_int4(0, 0, 0, 0);
-                *my_cov1 = make_int4(0, 0, 0, 0);
-                const int covs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                int run = 0;
-                #pragma unroll
-                for (int j = 0; j < 8; j++) run += covs[j];
-                const int other = __shfl_xor_sync(PM_FULL_MASK, run, 1);
-                run = half ? other : 0;  // covers of the left half carry into the right half
-                const int backdrop = (int)t_w0;
-                #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    run += covs[j];
-                    alpha[j] = fg[3] * pm_resolve_fill_alpha(accs[j] + run, backdrop);
-                }
-            } else {
-                #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float df = accs[j] ? __uint_as_float(~(uint32_t)accs[j]) : 1e9f;
-                    alpha[j] = fg[3] * pm_saturate(half_width + 0.5f - df);  // renderDf, metal:58-60
-                }
+            if (fill) {  // covers of the left half of the pixel row carry into the right half
+                const int4 c0 = *reinterpret_cast<const int4 *>(&w->cov[my_off0]), c1 = *reinterpret_cast<const int4 *>(&w->cov[my_off1]);
+                const int sum = ((c0.x + c0.y) + (c0.z + c0.w)) + ((c1.x + c1.y) + (c1.z + c1.w));
+                const int other = __shfl_xor_sync(PM_FULL_MASK, sum, 1);
+                run = half ? other : 0;
             }
-            __syncwarp();
-        } else if (t_kind == PM_REC_CIRCLE) {
-            const float px0 = tile_x0 + (float)(half * 8u), py = tile_y0 + (float)prow;
-            #pragma unroll 1
-            for (int j = 0; j < 8; j++) {
-                const float a = pm_px_circle_alpha(t_w0, t_w1, px0 + (float)j, py);
-                #pragma unroll
-                for (int jj = 0; jj < 8; jj++) if (jj == j) alpha[jj] = a;
-            }
-        } else {  // PM_REC_SOLID: a translucent full cover
-            unpack_fg(t_w1, fg);
-            #pragma unroll
-            for (int j = 0; j < 8; j++) alpha[j] = fg[3];
         }
-        // blend (metal:505, :543, :549)
-        #pragma unroll
-        for (int g = 0; g < 2; g++)
+        // phase B: resolve this lane's 8 pixels, clear their coverage for the next item, and blend
+        // (metal:505, :543, :549).  Two rounds of 4 pixels: the kernel is sensitive to its code size.
+        #pragma unroll 1
+        for (int g = 0; g < 2; g++) {
+            float al[4];
+            if (fill || stroke) {
+                int4 *pa = reinterpret_cast<int4 *>(&w->acc[g ? my_off1 : my_off0]);
+                const int4 a = *pa;
+                *pa = make_int4(0, 0, 0, 0);
+                if (fill) {
+                    int4 *pc = reinterpret_cast<int4 *>(&w->cov[g ? my_off1 : my_off0]);
+                    const int4 c = *pc;
+                    *pc = make_int4(0, 0, 0, 0);
+                    const int backdrop = (int)t_w0;
+                    run += c.x; al[0] = pm_resolve_fill_alpha(a.x + run, backdrop);
+                    run += c.y; al[1] = pm_resolve_fill_alpha(a.y + run, backdrop);
+                    run += c.z; al[2] = pm_resolve_fill_alpha(a.z + run, backdrop);
+                    run += c.w; al[3] = pm_resolve_fill_alpha(a.w + run, backdrop);
+                } else {  // renderDf, metal:58-60
+                    const float lim = half_width + 0.5f;
+                    al[0] = a.x ? pm_saturate(lim - __uint_as_float(~(uint32_t)a.x)) : 0.0f;
+                    al[1] = a.y ? pm_saturate(lim - __uint_as_float(~(uint32_t)a.y)) : 0.0f;
+                    al[2] = a.z ? pm_saturate(lim - __uint_as_float(~(uint32_t)a.z)) : 0.0f;
+                    al[3] = a.w ? pm_saturate(lim - __uint_as_float(~(uint32_t)a.w)) : 0.0f;
+                }
+            } else if (t_kind == PM_REC_CIRCLE) {
+                const float px0 = tile_x0 + (float)(half * 8u + 4u * (uint32_t)g), py = tile_y0 + (float)prow;
+                #pragma unroll
+                for (int j = 0; j < 4; j++) al[j] = pm_px_circle_alpha(t_w0, t_w1, px0 + (float)j, py);
+            } else {  // PM_REC_SOLID: a translucent full cover
+                al[0] = al[1] = al[2] = al[3] = 1.0f;
+            }
+            #pragma unroll
+            for (int j = 0; j < 4; j++) al[j] *= fg[3];
             #pragma unroll
             for (int k = 0; k < 3; k++) {
                 float4 v = w->rgb[k][g][lane];
-                v.x = mix_fma(v.x, fg[k], alpha[4 * g + 0]);
-                v.y = mix_fma(v.y, fg[k], alpha[4 * g + 1]);
-                v.z = mix_fma(v.z, fg[k], alpha[4 * g + 2]);
-                v.w = mix_fma(v.w, fg[k], alpha[4 * g + 3]);
+                v.x = mix_fma(v.x, fg[k], al[0]);
+                v.y = mix_fma(v.y, fg[k], al[1]);
+                v.z = mix_fma(v.z, fg[k], al[2]);
+                v.w = mix_fma(v.w, fg[k], al[3]);
                 w->rgb[k][g][lane] = v;
             }
+        }
+        __syncwarp();
     }
 
-    // the records are done with: fetch the next tile while this one is encoded and stored
-    __syncwarp();
-    fine_resolve(A, nx, w, n_heavy, n_total, lane);
+    fine_step2(A, nx, n_heavy, n_total);
 
-    #pragma unroll
+    #pragma unroll 1
     for (int g = 0; g < 2; g++) {
         const float4 r = w->rgb[0][g][lane], gg = w->rgb[1][g][lane], b = w->rgb[2][g][lane];
         const uint4 px = make_uint4(encode_pixel<EXACT>(r.x, gg.x, b.x), encode_pixel<EXACT>(r.y, gg.y, b.y),
@@ -525,9 +531,9 @@ __device__ __forceinline__ void fine_solid_batch(const PmFrameArgs &A, uint32_t 
 
 template <bool F32, bool EXACT>
 __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 4) k_fine(const PmFrameArgs A) {
-    __shared__ __align__(16) FineWarpSmem s_warp[PM_FINE_WARPS];
+    extern __shared__ __align__(16) unsigned char s_raw[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    FineWarpSmem *w = &s_warp[warp];
+    FineWarpSmem *w = reinterpret_cast<FineWarpSmem *>(s_raw) + warp;
     for (uint32_t i = lane; i < 256; i += 32) { w->acc[i] = 0; w->cov[i] = 0; }
     const uint32_t n_complex = A.counters->n_complex, n_heavy = A.counters->n_heavy;
     const uint32_t n_total = n_complex + n_heavy;
@@ -543,24 +549,30 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 4) k_fine(const PmFrameArg
     const uint32_t batches_per_row = (A.n_tx + 31u) / 32u;
     const uint32_t n_batches = batches_per_row * A.n_rows;
     bool complex_left = true, batches_left = true;
-    const bool prefer_complex = warp < PM_FINE_COMPLEX_WARPS;
+    // warps 3 and 7 (one of the SM's four schedulers) prefer the solid batches, the rest the tiles with records
+    const bool prefer_complex = (warp & 3u) != 3u;
     FineNext nx;
-    nx.q = 0; nx.pk = 0; nx.claimed = false; nx.have = false; nx.pass2 = false;
+    nx.q = 0; nx.pk1 = nx.pk2 = 0; nx.have1 = nx.have2 = false;
+    uint32_t pk_cur = 0, p = 0;
+    bool started = false;
     while (complex_left || batches_left) {
         const bool take_complex = complex_left && (prefer_complex || !batches_left);
         if (take_complex) {
             // (one call site for the tile code: the kernel is sensitive to its instruction footprint)
-            if (!nx.have) {  // cold start of the pipeline
+            if (!started) {  // fill the pipeline: this tile's data, the next tile's list entry
+                started = true;
                 fine_claim(A, nx, lane);
-                fine_resolve(A, nx, w, n_heavy, n_total, lane);
-                if (!nx.have) { complex_left = false; continue; }
+                if (!fine_entry(A, nx, n_heavy, n_total, &pk_cur)) { complex_left = false; continue; }
+                fine_prefetch(A, w, p, pk_cur, lane);
+                fine_claim(A, nx, lane);
+                nx.have1 = fine_entry(A, nx, n_heavy, n_total, &nx.pk1);
             }
-            const uint32_t pk = nx.pk;
-            const bool skip_heavy = nx.pass2;
-            nx.have = false;
-            fine_claim(A, nx, lane);  // the position after this tile; resolved once this tile's records are done with
-            fine_complex_tile<F32, EXACT>(A, pk, skip_heavy, w, lane, nx, n_heavy, n_total);
-            if (!nx.have) complex_left = false;
+            fine_complex_tile<F32, EXACT>(A, pk_cur, w, p, lane, nx, n_heavy, n_total);
+            p ^= 1u;
+            pk_cur = nx.pk1;
+            if (!nx.have1) complex_left = false;
+            nx.pk1 = nx.pk2;
+            nx.have1 = nx.have2;
         } else {
             uint32_t q = 0;
             if (lane == 0) q = atomicAdd(&A.queue->batch_next, 1u);
@@ -573,26 +585,35 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 4) k_fine(const PmFrameArg
 
 }  // namespace
 
-int pm_fine_setup(const float *lut512) {
-    cudaError_t e = cudaMemcpyToSymbol(c_fine_lut, lut512, 512 * sizeof(float));
-    if (e != cudaSuccess) return (int)e;
-    // 4 CTAs of 48 KB per SM: ask for the largest shared-memory carve-out
-    cudaFuncSetAttribute(k_fine<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(k_fine<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(k_fine<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(k_fine<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    return (int)cudaGetLastError();
+#define PM_FINE_SMEM (PM_FINE_WARPS * sizeof(FineWarpSmem))
+
+template <bool F32, bool EXACT>
+static cudaError_t fine_attr() {
+    cudaError_t e = cudaFuncSetAttribute(k_fine<F32, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PM_FINE_SMEM);
+    if (e != cudaSuccess) return e;
+    // 4 CTAs of ~52 KB per SM: ask for the largest shared-memory carve-out
+    return cudaFuncSetAttribute(k_fine<F32, EXACT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+int pm_fine_setup(void) {
+    cudaError_t e;
+    if ((e = fine_attr<false, false>()) != cudaSuccess) return (int)e;
+    if ((e = fine_attr<false, true>()) != cudaSuccess) return (int)e;
+    if ((e = fine_attr<true, false>()) != cudaSuccess) return (int)e;
+    if ((e = fine_attr<true, true>()) != cudaSuccess) return (int)e;
+    return 0;
 }
 
 void pm_launch_fine(const PmFrameArgs &a, int sm_count, cudaStream_t s) {
     // persistent: enough CTAs to fill every SM, work pulled from two queues
     const int grid = sm_count * 4;
+    const size_t smem = PM_FINE_SMEM;
     const bool exact = (a.flags & PM_FLAG_EXACT_SRGB) != 0;
     if (a.fb32) {  // debug render with the fp32 parity buffer
-        if (exact) k_fine<true, true><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
-        else       k_fine<true, false><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
+        if (exact) k_fine<true, true><<<grid, PM_FINE_WARPS * 32, smem, s>>>(a);
+        else       k_fine<true, false><<<grid, PM_FINE_WARPS * 32, smem, s>>>(a);
     } else {
-        if (exact) k_fine<false, true><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
-        else       k_fine<false, false><<<grid, PM_FINE_WARPS * 32, 0, s>>>(a);
+        if (exact) k_fine<false, true><<<grid, PM_FINE_WARPS * 32, smem, s>>>(a);
+        else       k_fine<false, false><<<grid, PM_FINE_WARPS * 32, smem, s>>>(a);
     }
 }

@@ -85,7 +85,7 @@ void pm_launch_plan_pieces(const uint8_t *scene, uint32_t n_items, uint32_t item
                            uint32_t piece_cap, PmPlanResult *result, cudaStream_t s);
 // One frame: binning (k_seg, k_row) then fill/blend (k_fine).  `mid` (optional) is recorded before k_fine.
 void pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, cudaStream_t s);
-// The fill/blend kernel alone (pm_fine.cu), and its one-time set-up on the current device: the
-// 512-entry colour table goes to constant memory.
+// The fill/blend kernel alone (pm_fine.cu), and its one-time set-up on the current device
+// (shared-memory attributes of the kernel).
 void pm_launch_fine(const PmFrameArgs &a, int sm_count, cudaStream_t s);
-int pm_fine_setup(const float *lut512);
+int pm_fine_setup(void);

@@ -369,7 +369,7 @@ int pm_renderer_create(pm_renderer **out, const pm_config *cfg) {
     float lut[512];  // [0,256): sRGB byte -> linear; [256,512): alpha byte / 255
     for (int i = 0; i < 256; i++) { lut[i] = pm_srgb_byte_to_linear((uint32_t)i); lut[256 + i] = (float)i / 255.0f; }
     PM_TRY(cudaMemcpyAsync(r->lut, lut, sizeof lut, cudaMemcpyHostToDevice, r->stream));
-    PM_TRY((cudaError_t)pm_fine_setup(lut));
+    PM_TRY((cudaError_t)pm_fine_setup());
     PM_TRY(cudaStreamSynchronize(r->stream));
 #undef PM_TRY
     *out = r;
