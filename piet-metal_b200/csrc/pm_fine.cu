@@ -51,6 +51,7 @@ struct FineWarpSmem {
     uint4 rec[2][2 * PM_TILE_SLOTS];
     u64 hdr[2][4];
     uint32_t idx[PM_FINE_LIST_CAP];
+    uint32_t pkq[4];  // [0..1]: list entries on their way (see FineNext)
 };
 
 __device__ __forceinline__ int fine_swz(int row, int j) { return row * 16 + (j ^ (((row >> 1) & 3) << 2)); }
@@ -71,6 +72,10 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -140,13 +145,14 @@ __device__ __forceinline__ PmRecord load_record(const PmRecord *pool, uint32_t i
 // Phase A for up to 32 records held one per lane (`mine` = this lane holds a FILL*/LINE record of
 // the current item): the (record, pixel row) pairs are enumerated across the lanes and each lane
 // adds its pair's coverage / distance into shared memory.
-__device__ __noinline__ void fine_pairs(FineAcc &acc, bool mine, const PmRecord &r, bool stroke, float reach,
-                                        float tile_x0, float tile_y0, uint32_t lane) {
-    const uint32_t kind = r.key & 15u;
+// (scalar arguments: a record passed by reference to an out-of-line function would go through local memory)
+__device__ __noinline__ void fine_pairs(FineWarpSmem *w, bool mine, uint32_t kind, float r_p0, float r_p1, float r_p2, float r_p3,
+                                        float r_edge_y, bool stroke, float reach, float tile_x0, float tile_y0, uint32_t lane) {
+    FineAcc acc{w};
     int ra = 1, rb = 0;
     if (mine) {
-        if (stroke) pm_line_rows(r.p[1], r.p[3], reach, tile_y0, &ra, &rb);
-        else pm_fill_rows(r.p[1], r.p[3], tile_y0, &ra, &rb);
+        if (stroke) pm_line_rows(r_p1, r_p3, reach, tile_y0, &ra, &rb);
+        else pm_fill_rows(r_p1, r_p3, tile_y0, &ra, &rb);
     }
     const int cnt = rb >= ra ? rb - ra + 1 : 0;
     int incl = cnt;
@@ -169,10 +175,10 @@ __device__ __noinline__ void fine_pairs(FineAcc &acc, bool mine, const PmRecord 
         }
         const int o_key = __shfl_sync(PM_FULL_MASK, key, lo);
         float p[4];
-        p[0] = __shfl_sync(PM_FULL_MASK, r.p[0], lo);
-        p[1] = __shfl_sync(PM_FULL_MASK, r.p[1], lo);
-        p[2] = __shfl_sync(PM_FULL_MASK, r.p[2], lo);
-        p[3] = __shfl_sync(PM_FULL_MASK, r.p[3], lo);
+        p[0] = __shfl_sync(PM_FULL_MASK, r_p0, lo);
+        p[1] = __shfl_sync(PM_FULL_MASK, r_p1, lo);
+        p[2] = __shfl_sync(PM_FULL_MASK, r_p2, lo);
+        p[3] = __shfl_sync(PM_FULL_MASK, r_p3, lo);
         if (q < total) {
             const int row = (o_key & 31) + (q - (o_key >> 5));
             if (stroke) pm_line_pair(acc, p, reach, row, tile_x0, tile_y0);
@@ -184,7 +190,7 @@ __device__ __noinline__ void fine_pairs(FineAcc &acc, bool mine, const PmRecord 
         for (uint32_t em = __ballot_sync(PM_FULL_MASK, mine && kind != PM_REC_FILL); em != 0; em &= em - 1) {
             const int src = __ffs(em) - 1;
             const uint32_t e_kind = __shfl_sync(PM_FULL_MASK, kind, src);
-            const float e_y = __shfl_sync(PM_FULL_MASK, r.edge_y, src);
+            const float e_y = __shfl_sync(PM_FULL_MASK, r_edge_y, src);
             if (lane < 16) pm_fill_edge_row(acc, e_kind, e_y, (int)lane, tile_y0);
         }
     }
@@ -201,46 +207,51 @@ __device__ __noinline__ void fine_pairs(FineAcc &acc, bool mine, const PmRecord 
 // from starting when everybody else is done.
 struct FineNext {
     uint32_t q;           // lane 0: the queue position claimed last
-    uint32_t pk1, pk2;    // packed (row, column) of the next tile and of the one after it
-    bool have1, have2;
+    bool have1, have2;    // the next tile / the one after it exist
+    bool full1, full2;    // ... and come from the full list (a heavy tile is skipped there: pass 1 rendered it)
 };
 
 __device__ __forceinline__ void fine_claim(const PmFrameArgs &A, FineNext &nx, uint32_t lane) {
     if (lane == 0) nx.q = atomicAdd(&A.queue->complex_next, 1u);
 }
-// Turns the claimed position into a list entry: bit 15 of the column half marks "from the full list"
-__device__ __forceinline__ bool fine_entry(const PmFrameArgs &A, const FineNext &nx, uint32_t n_heavy, uint32_t n_total, uint32_t *pk) {
-    const uint32_t q = __shfl_sync(PM_FULL_MASK, nx.q, 0);
+// Turns the claimed position into a list entry on its way into w->pkq[slot] (no register waits for it).
+// The empty asm keeps the compiler from hoisting the shuffle up to the atomic, which would expose its latency.
+__device__ __forceinline__ bool fine_entry(const PmFrameArgs &A, FineNext &nx, FineWarpSmem *w, uint32_t slot, uint32_t n_heavy, uint32_t n_total, bool *full) {
+    uint32_t qv = nx.q;
+    asm volatile("" : "+r"(qv) : : "memory");
+    const uint32_t q = __shfl_sync(PM_FULL_MASK, qv, 0);
     if (q >= n_total) return false;
-    *pk = q >= n_heavy ? (__ldg(&A.complex_list[q - n_heavy]) | 0x8000u) : __ldg(&A.complex_list[A.n_rows * A.n_tx + q]);
+    *full = q >= n_heavy;
+    cp_async4(&w->pkq[slot], *full ? &A.complex_list[q - n_heavy] : &A.complex_list[A.n_rows * A.n_tx + q]);
+    cp_async_commit();
     return true;
 }
 // Starts the copy of a tile's header words and inline record slots into buffer `p`.
 __device__ __forceinline__ void fine_prefetch(const PmFrameArgs &A, FineWarpSmem *w, uint32_t p, uint32_t pk, uint32_t lane) {
-    const size_t tile = (size_t)(pk >> 16) * A.n_tx + (pk & 0x7fffu);
+    const size_t tile = (size_t)(pk >> 16) * A.n_tx + (pk & 0xffffu);
     cp_async16(&w->rec[p][lane], reinterpret_cast<const uint4 *>(&A.pool[tile * PM_TILE_SLOTS]) + lane);
     if (lane < 3) cp_async8(&w->hdr[p][lane], lane == 0 ? &A.cnt[tile] : (lane == 1 ? &A.occ[tile] : &A.ovf[tile]));
     cp_async_commit();
 }
 // the second half of a pipeline step: the claim made at the start of the tile has long returned
-__device__ __forceinline__ void fine_step2(const PmFrameArgs &A, FineNext &nx, uint32_t n_heavy, uint32_t n_total) {
-    if (nx.have1) nx.have2 = fine_entry(A, nx, n_heavy, n_total, &nx.pk2);
+__device__ __forceinline__ void fine_step2(const PmFrameArgs &A, FineNext &nx, FineWarpSmem *w, uint32_t p, uint32_t n_heavy, uint32_t n_total) {
+    if (nx.have1) nx.have2 = fine_entry(A, nx, w, p, n_heavy, n_total, &nx.full2);
 }
 
 // One tile that owns records; its header and inline records are in buffer `p` of w.  All 32 lanes
 // execute this together.  Records are handled in chunks of 32, one per lane; chunk 0 is the inline
 // slots.  Pixel layout: lane l owns pixel row (l >> 1), pixels 8*(l & 1) .. +7.
 template <bool F32, bool EXACT>
-__device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t packed_tile, FineWarpSmem *w, uint32_t p, uint32_t lane,
-                                                  FineNext &nx, uint32_t n_heavy, uint32_t n_total) {
-    const uint32_t trow = packed_tile >> 16, tx = packed_tile & 0x7fffu;
-    const bool skip_heavy = (packed_tile & 0x8000u) != 0;
+__device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t packed_tile, bool skip_heavy, FineWarpSmem *w, uint32_t p, uint32_t lane,
+                                                  FineNext &nx, uint32_t *pk_next, uint32_t n_heavy, uint32_t n_total) {
+    const uint32_t trow = packed_tile >> 16, tx = packed_tile & 0xffffu;
     cp_async_wait_all();
     __syncwarp();
     // first half of the pipeline step: next tile's data on its way, the position after it claimed
     nx.have2 = false;
     if (nx.have1) {
-        fine_prefetch(A, w, p ^ 1u, nx.pk1, lane);
+        *pk_next = w->pkq[p ^ 1u];
+        fine_prefetch(A, w, p ^ 1u, *pk_next, lane);
         fine_claim(A, nx, lane);
     }
     const uint4 *rec = w->rec[p];
@@ -249,7 +260,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
     const uint32_t occ_item1 = (uint32_t)(ow >> 32) == A.stamp ? (uint32_t)ow : 0u;
     const bool heavy = n > PM_TILE_SLOTS;
     if (heavy && skip_heavy) {  // pass 1 rendered it
-        fine_step2(A, nx, n_heavy, n_total);
+        fine_step2(A, nx, w, p, n_heavy, n_total);
         return;
     }
     uint32_t occ_rgba = 0xffffffffu;  // solidColor starts as opaque white (metal:74)
@@ -312,7 +323,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
                                          (float)((c >> 16) & 0xff) / 255.0f, (float)(c >> 24) / 255.0f);
             for (int j = 0; j < 8; j++) dst32[j] = f;
         }
-        fine_step2(A, nx, n_heavy, n_total);
+        fine_step2(A, nx, w, p, n_heavy, n_total);
         return;
     }
 
@@ -332,7 +343,6 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
         }
     }
     const float tile_x0 = (float)(tx * PM_TILE_W), tile_y0 = (float)((A.tile_y0 + trow) * PM_TILE_H);  // scene coordinates
-    FineAcc acc{w};
     // this lane's two 4-pixel groups of the coverage arrays (word offsets; cov = acc + 256)
     const int my_off0 = fine_swz((int)prow, (int)half * 8), my_off1 = fine_swz((int)prow, (int)half * 8 + 4);
 
@@ -393,12 +403,9 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
             {
                 const bool mine = my_item == cur_item && (my_key & 15u) <= PM_REC_LINE;
                 if (__any_sync(PM_FULL_MASK, mine)) {
-                    PmRecord rc;
-                    rc.item = my_item; rc.key = my_key;
                     const uint4 a = rec[2 * (lane & (PM_TILE_SLOTS - 1))], b = rec[2 * (lane & (PM_TILE_SLOTS - 1)) + 1];
-                    rc.p[0] = pm_u2f(a.z); rc.p[1] = pm_u2f(a.w); rc.p[2] = pm_u2f(b.x); rc.p[3] = pm_u2f(b.y);
-                    rc.edge_y = pm_u2f(b.z); rc.next = 0;
-                    fine_pairs(acc, mine, rc, stroke, reach, tile_x0, tile_y0, lane);
+                    fine_pairs(w, mine, my_key & 15u, pm_u2f(a.z), pm_u2f(a.w), pm_u2f(b.x), pm_u2f(b.y), pm_u2f(b.z), stroke, reach,
+                               tile_x0, tile_y0, lane);
                 }
             }
             if (heavy) {
@@ -408,12 +415,14 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
                     rc.item = 0xffffffffu; rc.key = 0; rc.p[0] = rc.p[1] = rc.p[2] = rc.p[3] = 0.0f; rc.edge_y = 0.0f; rc.next = 0;
                     if (i < n_over) rc = load_record(A.pool, w->idx[i]);
                     const bool mine = rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE;
-                    if (__any_sync(PM_FULL_MASK, mine)) fine_pairs(acc, mine, rc, stroke, reach, tile_x0, tile_y0, lane);
+                    if (__any_sync(PM_FULL_MASK, mine))
+                        fine_pairs(w, mine, rc.key & 15u, rc.p[0], rc.p[1], rc.p[2], rc.p[3], rc.edge_y, stroke, reach, tile_x0, tile_y0, lane);
                 }
                 for (uint32_t cur = tail; cur != 0;) {  // records beyond the shared-memory index, one at a time
                     PmRecord rc = load_record(A.pool, cur - 1u);
                     cur = rc.next;
-                    if (rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE) fine_pairs(acc, lane == 0, rc, stroke, reach, tile_x0, tile_y0, lane);
+                    if (rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE)
+                        fine_pairs(w, lane == 0, rc.key & 15u, rc.p[0], rc.p[1], rc.p[2], rc.p[3], rc.edge_y, stroke, reach, tile_x0, tile_y0, lane);
                 }
             }
             __syncwarp();
@@ -471,7 +480,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
         __syncwarp();
     }
 
-    fine_step2(A, nx, n_heavy, n_total);
+    fine_step2(A, nx, w, p, n_heavy, n_total);
 
     #pragma unroll 1
     for (int g = 0; g < 2; g++) {
@@ -552,9 +561,9 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 4) k_fine(const PmFrameArg
     // warps 3 and 7 (one of the SM's four schedulers) prefer the solid batches, the rest the tiles with records
     const bool prefer_complex = (warp & 3u) != 3u;
     FineNext nx;
-    nx.q = 0; nx.pk1 = nx.pk2 = 0; nx.have1 = nx.have2 = false;
-    uint32_t pk_cur = 0, p = 0;
-    bool started = false;
+    nx.q = 0; nx.have1 = nx.have2 = nx.full1 = nx.full2 = false;
+    uint32_t pk_cur = 0, pk_next = 0, p = 0;
+    bool started = false, full_cur = false;
     while (complex_left || batches_left) {
         const bool take_complex = complex_left && (prefer_complex || !batches_left);
         if (take_complex) {
@@ -562,17 +571,21 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 4) k_fine(const PmFrameArg
             if (!started) {  // fill the pipeline: this tile's data, the next tile's list entry
                 started = true;
                 fine_claim(A, nx, lane);
-                if (!fine_entry(A, nx, n_heavy, n_total, &pk_cur)) { complex_left = false; continue; }
+                if (!fine_entry(A, nx, w, 2, n_heavy, n_total, &full_cur)) { complex_left = false; continue; }
+                cp_async_wait_all();
+                __syncwarp();
+                pk_cur = w->pkq[2];
                 fine_prefetch(A, w, p, pk_cur, lane);
                 fine_claim(A, nx, lane);
-                nx.have1 = fine_entry(A, nx, n_heavy, n_total, &nx.pk1);
+                nx.have1 = fine_entry(A, nx, w, p ^ 1u, n_heavy, n_total, &nx.full1);
             }
-            fine_complex_tile<F32, EXACT>(A, pk_cur, w, p, lane, nx, n_heavy, n_total);
+            fine_complex_tile<F32, EXACT>(A, pk_cur, full_cur, w, p, lane, nx, &pk_next, n_heavy, n_total);
             p ^= 1u;
-            pk_cur = nx.pk1;
+            pk_cur = pk_next;
+            full_cur = nx.full1;
             if (!nx.have1) complex_left = false;
-            nx.pk1 = nx.pk2;
             nx.have1 = nx.have2;
+            nx.full1 = nx.full2;
         } else {
             uint32_t q = 0;
             if (lane == 0) q = atomicAdd(&A.queue->batch_next, 1u);
