@@ -143,11 +143,17 @@ __device__ __forceinline__ PmRecord load_record(const PmRecord *pool, uint32_t i
 }
 
 // Phase A for up to 32 records held one per lane (`mine` = this lane holds a FILL*/LINE record of
-// the current item): the (record, pixel row) pairs are enumerated across the lanes and each lane
-// adds its pair's coverage / distance into shared memory.
-// (scalar arguments: a record passed by reference to an out-of-line function would go through local memory)
-__device__ __noinline__ void fine_pairs(FineWarpSmem *w, bool mine, uint32_t kind, float r_p0, float r_p1, float r_p2, float r_p3,
-                                        float r_edge_y, bool stroke, float reach, float tile_x0, float tile_y0, uint32_t lane) {
+// the current item).  Two levels of work distribution, because both the rows a segment crosses and
+// the pixels of a row that need arithmetic vary from 0 to 16:
+//   level 1: the (record, pixel row) pairs are enumerated across the lanes; a lane computes the
+//            row-dependent part of its pair, adds the row's cover delta, and finds the pixel span
+//            that needs per-pixel work (fill: the pixels near the segment; stroke: the pixels
+//            within reach of it);
+//   level 2: those (pair, pixel) units are enumerated across the lanes again, one pixel per lane.
+// Owner lookup at both levels: exclusive prefix and payload packed into one word that is
+// monotone in the lane, binary search with shuffles.
+__device__ __forceinline__ void fine_pairs(FineWarpSmem *w, bool mine, uint32_t kind, float r_p0, float r_p1, float r_p2, float r_p3,
+                                           float r_edge_y, bool stroke, float reach, float tile_x0, float tile_y0, uint32_t lane) {
     FineAcc acc{w};
     int ra = 1, rb = 0;
     if (mine) {
@@ -161,11 +167,11 @@ __device__ __noinline__ void fine_pairs(FineWarpSmem *w, bool mine, uint32_t kin
         int v = __shfl_up_sync(PM_FULL_MASK, incl, o);
         if (lane >= (uint32_t)o) incl += v;
     }
-    // exclusive prefix and first row in one word: monotone in the lane, so the owner search runs on it
-    const int key = ((incl - cnt) << 5) | ra;
+    const int key = ((incl - cnt) << 5) | ra;  // (pairs before this lane, first row)
     const int total = __shfl_sync(PM_FULL_MASK, incl, 31);
+    #pragma unroll 1
     for (int q = (int)lane; q - (int)lane < total; q += 32) {
-        // owner = last lane whose exclusive prefix is <= q
+        // level 1: owner = last lane whose exclusive prefix is <= q
         const int qk = (q << 5) | 31;
         int lo = 0;
         #pragma unroll
@@ -179,10 +185,62 @@ __device__ __noinline__ void fine_pairs(FineWarpSmem *w, bool mine, uint32_t kin
         p[1] = __shfl_sync(PM_FULL_MASK, r_p1, lo);
         p[2] = __shfl_sync(PM_FULL_MASK, r_p2, lo);
         p[3] = __shfl_sync(PM_FULL_MASK, r_p3, lo);
+        // this lane's pair: d0..d5 is what a pixel of it needs (stroke: the segment; fill: sx, ex and the row's window / t)
+        int row = 0, j0 = 0, npx = 0;
+        float d0 = p[0], d1 = p[1], d2 = p[2], d3 = p[3], d4 = 0.0f, d5 = 0.0f;
         if (q < total) {
-            const int row = (o_key & 31) + (q - (o_key >> 5));
-            if (stroke) pm_line_pair(acc, p, reach, row, tile_x0, tile_y0);
-            else pm_fill_pair(acc, p, row, tile_x0, tile_y0);
+            row = (o_key & 31) + (q - (o_key >> 5));
+            if (stroke) {
+                int ja, jb;
+                pm_line_pair_span(p, reach, row, tile_x0, tile_y0, &ja, &jb);
+                j0 = ja;
+                npx = jb >= ja ? jb - ja + 1 : 0;
+            } else {
+                PmFillRow fr;
+                int j_near, j_cover;
+                if (pm_fill_pair_row(p, row, tile_x0, tile_y0, &fr, &j_near, &j_cover)) {
+                    if (j_cover < 16) acc.cover(row, j_cover, pm_to_fx(fr.wx - fr.wy));
+                    j0 = j_near;
+                    npx = j_cover - j_near;
+                    d1 = p[2]; d2 = fr.wx; d3 = fr.wy; d4 = fr.tx; d5 = fr.ty;
+                }
+            }
+        }
+        // level 2
+        int incl2 = npx;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(PM_FULL_MASK, incl2, o);
+            if (lane >= (uint32_t)o) incl2 += v;
+        }
+        const int key2 = ((incl2 - npx) << 9) | (row << 5) | j0;  // (pixels before this lane, row, first pixel)
+        const int total2 = __shfl_sync(PM_FULL_MASK, incl2, 31);
+        #pragma unroll 1
+        for (int u = (int)lane; u - (int)lane < total2; u += 32) {
+            const int uk = (u << 9) | 511;
+            int lo2 = 0;
+            #pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int v = __shfl_sync(PM_FULL_MASK, key2, lo2 + step);
+                if (v <= uk) lo2 += step;
+            }
+            const int k2 = __shfl_sync(PM_FULL_MASK, key2, lo2);
+            const float e0 = __shfl_sync(PM_FULL_MASK, d0, lo2);
+            const float e1 = __shfl_sync(PM_FULL_MASK, d1, lo2);
+            const float e2 = __shfl_sync(PM_FULL_MASK, d2, lo2);
+            const float e3 = __shfl_sync(PM_FULL_MASK, d3, lo2);
+            const int prow = (k2 >> 5) & 15;
+            const int j = (k2 & 31) + (u - (k2 >> 9));
+            if (stroke) {
+                if (u < total2) acc.dist(prow, j, pm_px_line_dist(e0, e1, e2, e3, tile_x0 + (float)j, tile_y0 + (float)prow));
+            } else {
+                PmFillRow fr;
+                fr.wx = e2; fr.wy = e3;
+                fr.tx = __shfl_sync(PM_FULL_MASK, d4, lo2);
+                fr.ty = __shfl_sync(PM_FULL_MASK, d5, lo2);
+                fr.active = true;
+                if (u < total2) acc.near(prow, j, pm_fill_pair_px(e0, e1, tile_x0, j, fr));
+            }
         }
     }
     // FillEdge commands: one record at a time, lanes 0..15 take the 16 pixel rows
@@ -194,6 +252,14 @@ __device__ __noinline__ void fine_pairs(FineWarpSmem *w, bool mine, uint32_t kin
             if (lane < 16) pm_fill_edge_row(acc, e_kind, e_y, (int)lane, tile_y0);
         }
     }
+}
+
+// Out-of-line copy for the overflow records of heavy tiles (rare): the hot call site is inlined so that
+// nothing has to survive a call boundary -- in particular the pending queue claim, which would be
+// spilled, i.e. waited for, right after its atomic.
+__device__ __noinline__ void fine_pairs_cold(FineWarpSmem *w, bool mine, uint32_t kind, float r_p0, float r_p1, float r_p2, float r_p3,
+                                             float r_edge_y, bool stroke, float reach, float tile_x0, float tile_y0, uint32_t lane) {
+    fine_pairs(w, mine, kind, r_p0, r_p1, r_p2, r_p3, r_edge_y, stroke, reach, tile_x0, tile_y0, lane);
 }
 
 // Pipeline state of a warp that walks the list of tiles with records.  While tile i is rendered, the
@@ -212,7 +278,10 @@ struct FineNext {
 };
 
 __device__ __forceinline__ void fine_claim(const PmFrameArgs &A, FineNext &nx, uint32_t lane) {
-    if (lane == 0) nx.q = atomicAdd(&A.queue->complex_next, 1u);
+    // (atom.inc with a bound that is never reached, not atom.add: ptxas turns an add -- or an inc bounded by
+    // 2^32-1 -- on a warp-uniform address into a warp-aggregated atomic followed by a shuffle of its result,
+    // even from inline PTX, and that shuffle waits for the atomic right here)
+    if (lane == 0) asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(nx.q) : "l"(&A.queue->complex_next) : "memory");
 }
 // Turns the claimed position into a list entry on its way into w->pkq[slot] (no register waits for it).
 // The empty asm keeps the compiler from hoisting the shuffle up to the atomic, which would expose its latency.
@@ -416,13 +485,13 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
                     if (i < n_over) rc = load_record(A.pool, w->idx[i]);
                     const bool mine = rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE;
                     if (__any_sync(PM_FULL_MASK, mine))
-                        fine_pairs(w, mine, rc.key & 15u, rc.p[0], rc.p[1], rc.p[2], rc.p[3], rc.edge_y, stroke, reach, tile_x0, tile_y0, lane);
+                        fine_pairs_cold(w, mine, rc.key & 15u, rc.p[0], rc.p[1], rc.p[2], rc.p[3], rc.edge_y, stroke, reach, tile_x0, tile_y0, lane);
                 }
                 for (uint32_t cur = tail; cur != 0;) {  // records beyond the shared-memory index, one at a time
                     PmRecord rc = load_record(A.pool, cur - 1u);
                     cur = rc.next;
                     if (rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE)
-                        fine_pairs(w, lane == 0, rc.key & 15u, rc.p[0], rc.p[1], rc.p[2], rc.p[3], rc.edge_y, stroke, reach, tile_x0, tile_y0, lane);
+                        fine_pairs_cold(w, lane == 0, rc.key & 15u, rc.p[0], rc.p[1], rc.p[2], rc.p[3], rc.edge_y, stroke, reach, tile_x0, tile_y0, lane);
                 }
             }
             __syncwarp();
@@ -539,7 +608,7 @@ __device__ __forceinline__ void fine_solid_batch(const PmFrameArgs &A, uint32_t 
 }
 
 template <bool F32, bool EXACT>
-__global__ void __launch_bounds__(PM_FINE_WARPS * 32, 4) k_fine(const PmFrameArgs A) {
+__global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArgs A) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FineWarpSmem *w = reinterpret_cast<FineWarpSmem *>(s_raw) + warp;
