@@ -264,34 +264,34 @@ __device__ __noinline__ void fine_pairs_cold(FineWarpSmem *w, bool mine, uint32_
 
 // Pipeline state of a warp that walks the list of tiles with records.  While tile i is rendered, the
 // header and inline records of tile i+1 are in flight into the other half of the shared-memory
-// buffer, and the queue position of tile i+2 has been claimed; its list entry is loaded when the
-// coverage of tile i is done.  No global-memory latency of the chain
+// buffer; the queue position of tile i+2 is claimed when the coverage of tile i is done and its
+// list entry is requested after tile i has been stored.  No global-memory latency of the chain
 //   queue counter -> list entry -> cnt / occ / record slots
 // is exposed once the pipeline runs.
 // List order: the heavy tiles (more records than inline slots: coincident outlines, deep stacks)
 // first, then the full list, in which the heavy ones are skipped.  Heavy first keeps a long tile
 // from starting when everybody else is done.
 struct FineNext {
-    uint32_t q;           // lane 0: the queue position claimed last
     bool have1, have2;    // the next tile / the one after it exist
     bool full1, full2;    // ... and come from the full list (a heavy tile is skipped there: pass 1 rendered it)
 };
 
-__device__ __forceinline__ void fine_claim(const PmFrameArgs &A, FineNext &nx, uint32_t lane) {
+__device__ __forceinline__ uint32_t fine_claim(const PmFrameArgs &A, uint32_t lane) {
     // (atom.inc with a bound that is never reached, not atom.add: ptxas turns an add -- or an inc bounded by
     // 2^32-1 -- on a warp-uniform address into a warp-aggregated atomic followed by a shuffle of its result,
     // even from inline PTX, and that shuffle waits for the atomic right here)
-    if (lane == 0) asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(nx.q) : "l"(&A.queue->complex_next) : "memory");
+    uint32_t q = 0;
+    if (lane == 0) asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(q) : "l"(&A.queue->complex_next) : "memory");
+    return q;
 }
-// Turns the claimed position into a list entry on its way into w->pkq[slot] (no register waits for it).
-// The empty asm keeps the compiler from hoisting the shuffle up to the atomic, which would expose its latency.
-__device__ __forceinline__ bool fine_entry(const PmFrameArgs &A, FineNext &nx, FineWarpSmem *w, uint32_t slot, uint32_t n_heavy, uint32_t n_total, bool *full) {
-    uint32_t qv = nx.q;
-    asm volatile("" : "+r"(qv) : : "memory");
-    const uint32_t q = __shfl_sync(PM_FULL_MASK, qv, 0);
+// Turns the claimed position (lane 0's `claim`) into a list entry on its way into w->pkq[slot] (no register
+// waits for it).  The empty asm keeps the compiler from hoisting the shuffle up to the atomic.
+__device__ __forceinline__ bool fine_entry(const PmFrameArgs &A, uint32_t claim, FineWarpSmem *w, uint32_t slot, uint32_t n_heavy, uint32_t n_total, bool *full) {
+    asm volatile("" : "+r"(claim) : : "memory");
+    const uint32_t q = __shfl_sync(PM_FULL_MASK, claim, 0);
     if (q >= n_total) return false;
     *full = q >= n_heavy;
-    cp_async4(&w->pkq[slot], *full ? &A.complex_list[q - n_heavy] : &A.complex_list[A.n_rows * A.n_tx + q]);
+    if ((threadIdx.x & 31u) == 0) cp_async4(&w->pkq[slot], *full ? &A.complex_list[q - n_heavy] : &A.complex_list[A.n_rows * A.n_tx + q]);
     cp_async_commit();
     return true;
 }
@@ -302,9 +302,18 @@ __device__ __forceinline__ void fine_prefetch(const PmFrameArgs &A, FineWarpSmem
     if (lane < 3) cp_async8(&w->hdr[p][lane], lane == 0 ? &A.cnt[tile] : (lane == 1 ? &A.occ[tile] : &A.ovf[tile]));
     cp_async_commit();
 }
-// the second half of a pipeline step: the claim made at the start of the tile has long returned
-__device__ __forceinline__ void fine_step2(const PmFrameArgs &A, FineNext &nx, FineWarpSmem *w, uint32_t p, uint32_t n_heavy, uint32_t n_total) {
-    if (nx.have1) nx.have2 = fine_entry(A, nx, w, p, n_heavy, n_total, &nx.full2);
+// Pipeline step, part 1 (once the tile's own set-up is done): the next tile's list entry, requested
+// when the previous tile was stored, has arrived; start the copy of that tile's data.
+__device__ __forceinline__ void fine_step1(const PmFrameArgs &A, FineNext &nx, FineWarpSmem *w, uint32_t p, uint32_t *pk_next, uint32_t lane) {
+    if (!nx.have1) return;
+    cp_async_wait_all();
+    __syncwarp();
+    *pk_next = w->pkq[p ^ 1u];
+    fine_prefetch(A, w, p ^ 1u, *pk_next, lane);
+}
+// Pipeline step, parts 2 and 3: claim the position after the next tile; look its list entry up.
+__device__ __forceinline__ void fine_step3(const PmFrameArgs &A, FineNext &nx, uint32_t claim, FineWarpSmem *w, uint32_t p, uint32_t n_heavy, uint32_t n_total) {
+    if (nx.have1) nx.have2 = fine_entry(A, claim, w, p, n_heavy, n_total, &nx.full2);
 }
 
 // One tile that owns records; its header and inline records are in buffer `p` of w.  All 32 lanes
@@ -318,18 +327,14 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
     __syncwarp();
     // first half of the pipeline step: next tile's data on its way, the position after it claimed
     nx.have2 = false;
-    if (nx.have1) {
-        *pk_next = w->pkq[p ^ 1u];
-        fine_prefetch(A, w, p ^ 1u, *pk_next, lane);
-        fine_claim(A, nx, lane);
-    }
     const uint4 *rec = w->rec[p];
     const u64 cw = w->hdr[p][0], ow = w->hdr[p][1];
     const uint32_t n = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
     const uint32_t occ_item1 = (uint32_t)(ow >> 32) == A.stamp ? (uint32_t)ow : 0u;
     const bool heavy = n > PM_TILE_SLOTS;
     if (heavy && skip_heavy) {  // pass 1 rendered it
-        fine_step2(A, nx, w, p, n_heavy, n_total);
+        fine_step1(A, nx, w, p, pk_next, lane);
+        fine_step3(A, nx, nx.have1 ? fine_claim(A, lane) : 0u, w, p, n_heavy, n_total);
         return;
     }
     uint32_t occ_rgba = 0xffffffffu;  // solidColor starts as opaque white (metal:74)
@@ -392,7 +397,8 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
                                          (float)((c >> 16) & 0xff) / 255.0f, (float)(c >> 24) / 255.0f);
             for (int j = 0; j < 8; j++) dst32[j] = f;
         }
-        fine_step2(A, nx, w, p, n_heavy, n_total);
+        fine_step1(A, nx, w, p, pk_next, lane);
+        fine_step3(A, nx, nx.have1 ? fine_claim(A, lane) : 0u, w, p, n_heavy, n_total);
         return;
     }
 
@@ -411,6 +417,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
             w->rgb[2][g][lane] = make_float4(b2, b2, b2, b2);
         }
     }
+    fine_step1(A, nx, w, p, pk_next, lane);
     const float tile_x0 = (float)(tx * PM_TILE_W), tile_y0 = (float)((A.tile_y0 + trow) * PM_TILE_H);  // scene coordinates
     // this lane's two 4-pixel groups of the coverage arrays (word offsets; cov = acc + 256)
     const int my_off0 = fine_swz((int)prow, (int)half * 8), my_off1 = fine_swz((int)prow, (int)half * 8 + 4);
@@ -549,7 +556,10 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
         __syncwarp();
     }
 
-    fine_step2(A, nx, w, p, n_heavy, n_total);
+    // the position after the next tile is claimed here and looked up after the encode: the claim's result
+    // must stay in its register until then (anything that touches it -- a spill included -- waits for the
+    // atomic), and this is the stretch of the tile with the fewest live values
+    const uint32_t claim = nx.have1 ? fine_claim(A, lane) : 0u;
 
     #pragma unroll 1
     for (int g = 0; g < 2; g++) {
@@ -564,6 +574,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
             dst32[4 * g + 3] = make_float4(linear_to_srgb<EXACT>(r.w), linear_to_srgb<EXACT>(gg.w), linear_to_srgb<EXACT>(b.w), 1.0f);
         }
     }
+    fine_step3(A, nx, claim, w, p, n_heavy, n_total);
 }
 
 // 32 consecutive tiles of one tile row; the solid ones are written row-wise: each store
@@ -630,7 +641,7 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArg
     // warps 3 and 7 (one of the SM's four schedulers) prefer the solid batches, the rest the tiles with records
     const bool prefer_complex = (warp & 3u) != 3u;
     FineNext nx;
-    nx.q = 0; nx.have1 = nx.have2 = nx.full1 = nx.full2 = false;
+    nx.have1 = nx.have2 = nx.full1 = nx.full2 = false;
     uint32_t pk_cur = 0, pk_next = 0, p = 0;
     bool started = false, full_cur = false;
     while (complex_left || batches_left) {
@@ -639,14 +650,12 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArg
             // (one call site for the tile code: the kernel is sensitive to its instruction footprint)
             if (!started) {  // fill the pipeline: this tile's data, the next tile's list entry
                 started = true;
-                fine_claim(A, nx, lane);
-                if (!fine_entry(A, nx, w, 2, n_heavy, n_total, &full_cur)) { complex_left = false; continue; }
+                if (!fine_entry(A, fine_claim(A, lane), w, 2, n_heavy, n_total, &full_cur)) { complex_left = false; continue; }
                 cp_async_wait_all();
                 __syncwarp();
                 pk_cur = w->pkq[2];
                 fine_prefetch(A, w, p, pk_cur, lane);
-                fine_claim(A, nx, lane);
-                nx.have1 = fine_entry(A, nx, w, p ^ 1u, n_heavy, n_total, &nx.full1);
+                nx.have1 = fine_entry(A, fine_claim(A, lane), w, p ^ 1u, n_heavy, n_total, &nx.full1);
             }
             fine_complex_tile<F32, EXACT>(A, pk_cur, full_cur, w, p, lane, nx, &pk_next, n_heavy, n_total);
             p ^= 1u;
