@@ -272,24 +272,33 @@ __device__ __noinline__ void fine_pairs_cold(FineWarpSmem *w, bool mine, uint32_
 // first, then the full list, in which the heavy ones are skipped.  Heavy first keeps a long tile
 // from starting when everybody else is done.
 struct FineNext {
+    uint32_t home;        // the sub-queue this warp claims from
+    uint32_t dry;         // sub-queues found empty so far
     bool have1, have2;    // the next tile / the one after it exist
     bool full1, full2;    // ... and come from the full list (a heavy tile is skipped there: pass 1 rendered it)
 };
 
-__device__ __forceinline__ uint32_t fine_claim(const PmFrameArgs &A, uint32_t lane) {
+__device__ __forceinline__ uint32_t fine_claim(const PmFrameArgs &A, const FineNext &nx, uint32_t lane) {
     // (atom.inc with a bound that is never reached, not atom.add: ptxas turns an add -- or an inc bounded by
     // 2^32-1 -- on a warp-uniform address into a warp-aggregated atomic followed by a shuffle of its result,
     // even from inline PTX, and that shuffle waits for the atomic right here)
-    uint32_t q = 0;
-    if (lane == 0) asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(q) : "l"(&A.queue->complex_next) : "memory");
-    return q;
+    uint32_t k = 0;
+    if (lane == 0) asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(k) : "l"(&A.queue->sub[nx.home][0]) : "memory");
+    return k;
 }
-// Turns the claimed position (lane 0's `claim`) into a list entry on its way into w->pkq[slot] (no register
-// waits for it).  The empty asm keeps the compiler from hoisting the shuffle up to the atomic.
-__device__ __forceinline__ bool fine_entry(const PmFrameArgs &A, uint32_t claim, FineWarpSmem *w, uint32_t slot, uint32_t n_heavy, uint32_t n_total, bool *full) {
+// Turns the claim (lane 0's `claim` = k in the warp's current sub-queue) into a list entry on its way into
+// w->pkq[slot] (no register waits for it).  The empty asm keeps the compiler from hoisting the shuffle up
+// to the atomic.  A sub-queue that has run dry sends the warp on to the next one, until all are dry.
+__device__ __forceinline__ bool fine_entry(const PmFrameArgs &A, FineNext &nx, uint32_t claim, FineWarpSmem *w, uint32_t slot, uint32_t n_heavy, uint32_t n_total, bool *full) {
     asm volatile("" : "+r"(claim) : : "memory");
-    const uint32_t q = __shfl_sync(PM_FULL_MASK, claim, 0);
-    if (q >= n_total) return false;
+    uint32_t q = nx.home + PM_FINE_SUBQ * __shfl_sync(PM_FULL_MASK, claim, 0);
+    while (q >= n_total) {
+        if (++nx.dry >= PM_FINE_SUBQ) return false;
+        nx.home = (nx.home + 1u) & (PM_FINE_SUBQ - 1u);
+        uint32_t k = 0;
+        if ((threadIdx.x & 31u) == 0) k = atomicAdd(&A.queue->sub[nx.home][0], 1u);
+        q = nx.home + PM_FINE_SUBQ * __shfl_sync(PM_FULL_MASK, k, 0);
+    }
     *full = q >= n_heavy;
     if ((threadIdx.x & 31u) == 0) cp_async4(&w->pkq[slot], *full ? &A.complex_list[q - n_heavy] : &A.complex_list[A.n_rows * A.n_tx + q]);
     cp_async_commit();
@@ -313,7 +322,7 @@ __device__ __forceinline__ void fine_step1(const PmFrameArgs &A, FineNext &nx, F
 }
 // Pipeline step, parts 2 and 3: claim the position after the next tile; look its list entry up.
 __device__ __forceinline__ void fine_step3(const PmFrameArgs &A, FineNext &nx, uint32_t claim, FineWarpSmem *w, uint32_t p, uint32_t n_heavy, uint32_t n_total) {
-    if (nx.have1) nx.have2 = fine_entry(A, claim, w, p, n_heavy, n_total, &nx.full2);
+    if (nx.have1) nx.have2 = fine_entry(A, nx, claim, w, p, n_heavy, n_total, &nx.full2);
 }
 
 // One tile that owns records; its header and inline records are in buffer `p` of w.  All 32 lanes
@@ -334,7 +343,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
     const bool heavy = n > PM_TILE_SLOTS;
     if (heavy && skip_heavy) {  // pass 1 rendered it
         fine_step1(A, nx, w, p, pk_next, lane);
-        fine_step3(A, nx, nx.have1 ? fine_claim(A, lane) : 0u, w, p, n_heavy, n_total);
+        fine_step3(A, nx, nx.have1 ? fine_claim(A, nx, lane) : 0u, w, p, n_heavy, n_total);
         return;
     }
     uint32_t occ_rgba = 0xffffffffu;  // solidColor starts as opaque white (metal:74)
@@ -398,7 +407,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
             for (int j = 0; j < 8; j++) dst32[j] = f;
         }
         fine_step1(A, nx, w, p, pk_next, lane);
-        fine_step3(A, nx, nx.have1 ? fine_claim(A, lane) : 0u, w, p, n_heavy, n_total);
+        fine_step3(A, nx, nx.have1 ? fine_claim(A, nx, lane) : 0u, w, p, n_heavy, n_total);
         return;
     }
 
@@ -559,7 +568,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
     // the position after the next tile is claimed here and looked up after the encode: the claim's result
     // must stay in its register until then (anything that touches it -- a spill included -- waits for the
     // atomic), and this is the stretch of the tile with the fewest live values
-    const uint32_t claim = nx.have1 ? fine_claim(A, lane) : 0u;
+    const uint32_t claim = nx.have1 ? fine_claim(A, nx, lane) : 0u;
 
     #pragma unroll 1
     for (int g = 0; g < 2; g++) {
@@ -642,6 +651,7 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArg
     const bool prefer_complex = (warp & 3u) != 3u;
     FineNext nx;
     nx.have1 = nx.have2 = nx.full1 = nx.full2 = false;
+    nx.home = blockIdx.x & (PM_FINE_SUBQ - 1u); nx.dry = 0;
     uint32_t pk_cur = 0, pk_next = 0, p = 0;
     bool started = false, full_cur = false;
     while (complex_left || batches_left) {
@@ -650,12 +660,12 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArg
             // (one call site for the tile code: the kernel is sensitive to its instruction footprint)
             if (!started) {  // fill the pipeline: this tile's data, the next tile's list entry
                 started = true;
-                if (!fine_entry(A, fine_claim(A, lane), w, 2, n_heavy, n_total, &full_cur)) { complex_left = false; continue; }
+                if (!fine_entry(A, nx, fine_claim(A, nx, lane), w, 2, n_heavy, n_total, &full_cur)) { complex_left = false; continue; }
                 cp_async_wait_all();
                 __syncwarp();
                 pk_cur = w->pkq[2];
                 fine_prefetch(A, w, p, pk_cur, lane);
-                nx.have1 = fine_entry(A, fine_claim(A, lane), w, p ^ 1u, n_heavy, n_total, &nx.full1);
+                nx.have1 = fine_entry(A, nx, fine_claim(A, nx, lane), w, p ^ 1u, n_heavy, n_total, &nx.full1);
             }
             fine_complex_tile<F32, EXACT>(A, pk_cur, full_cur, w, p, lane, nx, &pk_next, n_heavy, n_total);
             p ^= 1u;

@@ -364,9 +364,8 @@ __global__ void __launch_bounds__(256) k_seg(const PmFrameArgs A) {
         __device__ ~Timer() { if (A.debug) atomicMax(&A.debug[2 * blockIdx.x + 1], now()); }
     } timer(A);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        A.queue->complex_next = 0;
         A.queue->batch_next = 0;
-        A.queue->heavy_next = 0;
+        for (int s = 0; s < PM_FINE_SUBQ; s++) A.queue->sub[s][0] = 0;
     }
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= A.n_pieces) return;

@@ -14,11 +14,14 @@ struct PmBinCounters {
     uint32_t pad;
 };
 // Work queues of the fill kernel; cleared by the binning kernel of the same frame.
+// The list of tiles with records is handed out through PM_FINE_SUBQ counters instead of one: position
+// s + PM_FINE_SUBQ * k belongs to counter s.  A single counter would see one atomic every few cycles,
+// which is what an L2 slice can do on one address: the claims would queue up for microseconds.
+#define PM_FINE_SUBQ 8
 struct PmFineQueue {
-    uint32_t complex_next;  // pass 2 over the tiles with records: the light ones
     uint32_t batch_next;    // 32-tile batches of solid tiles
-    uint32_t heavy_next;    // pass 1 over the tiles with records: the heavy ones first (shorter tail)
-    uint32_t pad;
+    uint32_t pad[63];
+    uint32_t sub[PM_FINE_SUBQ][64];  // [s][0]: next k of sub-queue s (each on a cache line of its own)
 };
 // Written by the device into mapped host memory at the end of every frame.
 struct PmFrameReport {
