@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpiet_metal_b200.so")
+LIB_PATH = os.environ.get("PM_LIB") or os.path.join(_HERE, "libpiet_metal_b200.so")  # PM_LIB: A/B builds of the same library
 
 PM_OK = 0
 PM_ERR_NO_DEVICE = -2

@@ -15,6 +15,13 @@
 //   * the linear colour of the tile's 256 pixels lives in a lane-private slice of shared memory
 //     (8 pixels per lane), which keeps the kernel at 64 registers = 32 resident warps per SM;
 //   * the sRGB encode and the 128-bit framebuffer stores happen once per tile.
+//
+// The kernel is issue-bound and very sensitive to its instruction footprint (L1.5 instruction cache:
+// ~20 KB of hot code is the knee) and to registers (80 = 3 CTAs/SM; at 64 the spills cost more than the
+// extra warps give).  Measured and rejected on the 8192^2 tiger: 64 registers / 4 CTAs per SM (+15 %
+// time), an out-of-line copy of the tile code for heavy tiles (+10 %: they are the long pole, and the
+// call boundary spills), prefetching the solid batches' words as well (+3 %: code size), one work
+// counter instead of eight (the L2 atomic unit saturates: claims take microseconds).
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,6 +40,15 @@ typedef unsigned long long u64;
 
 #define PM_FINE_WARPS 8
 #define PM_FINE_COMPLEX_WARPS 6  // warps that prefer tiles with records; the rest prefer solid batches
+#ifndef PM_FINE_TWO_LEVEL
+#define PM_FINE_TWO_LEVEL 1      // 1: (pair, pixel) units handed out to the lanes; 0: a lane walks the pixels of its pair
+#endif
+#ifndef PM_FINE_BATCH_PIPELINE
+#define PM_FINE_BATCH_PIPELINE 0 // 1: cnt / occ words of the solid batches prefetched too (measured: the extra code costs more
+#endif                           //    in instruction-cache misses than the hidden latency gains; the solid warps are not critical)
+#ifndef PM_FINE_EARLY_CLAIM
+#define PM_FINE_EARLY_CLAIM 0    // 1: the next-but-one tile is claimed at the start of a tile; 0: before the encode
+#endif
 #define PM_FINE_LIST_CAP 96      // overflow records per tile indexed in shared memory; the rest is re-walked
 
 __device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
@@ -51,7 +67,9 @@ struct FineWarpSmem {
     uint4 rec[2][2 * PM_TILE_SLOTS];
     u64 hdr[2][4];
     uint32_t idx[PM_FINE_LIST_CAP];
-    uint32_t pkq[4];  // [0..1]: list entries on their way (see FineNext)
+    uint32_t pkq[2];  // pipeline state of the walk over the tile list (see fine_entry)
+    uint32_t st;
+    uint32_t pad;
 };
 
 __device__ __forceinline__ int fine_swz(int row, int j) { return row * 16 + (j ^ (((row >> 1) & 3) << 2)); }
@@ -185,6 +203,7 @@ __device__ __forceinline__ void fine_pairs(FineWarpSmem *w, bool mine, uint32_t 
         p[1] = __shfl_sync(PM_FULL_MASK, r_p1, lo);
         p[2] = __shfl_sync(PM_FULL_MASK, r_p2, lo);
         p[3] = __shfl_sync(PM_FULL_MASK, r_p3, lo);
+#if PM_FINE_TWO_LEVEL
         // this lane's pair: d0..d5 is what a pixel of it needs (stroke: the segment; fill: sx, ex and the row's window / t)
         int row = 0, j0 = 0, npx = 0;
         float d0 = p[0], d1 = p[1], d2 = p[2], d3 = p[3], d4 = 0.0f, d5 = 0.0f;
@@ -242,6 +261,13 @@ __device__ __forceinline__ void fine_pairs(FineWarpSmem *w, bool mine, uint32_t 
                 if (u < total2) acc.near(prow, j, pm_fill_pair_px(e0, e1, tile_x0, j, fr));
             }
         }
+#else
+        if (q < total) {
+            const int row = (o_key & 31) + (q - (o_key >> 5));
+            if (stroke) pm_line_pair(acc, p, reach, row, tile_x0, tile_y0);
+            else pm_fill_pair(acc, p, row, tile_x0, tile_y0);
+        }
+#endif
     }
     // FillEdge commands: one record at a time, lanes 0..15 take the 16 pixel rows
     if (!stroke) {
@@ -271,38 +297,50 @@ __device__ __noinline__ void fine_pairs_cold(FineWarpSmem *w, bool mine, uint32_
 // List order: the heavy tiles (more records than inline slots: coincident outlines, deep stacks)
 // first, then the full list, in which the heavy ones are skipped.  Heavy first keeps a long tile
 // from starting when everybody else is done.
-struct FineNext {
-    uint32_t home;        // the sub-queue this warp claims from
-    uint32_t dry;         // sub-queues found empty so far
-    bool have1, have2;    // the next tile / the one after it exist
-    bool full1, full2;    // ... and come from the full list (a heavy tile is skipped there: pass 1 rendered it)
-};
+//
+// The pipeline's state lives in shared memory (w->st, w->pkq), not in registers: the tile code needs every
+// register it can get, and state that is spilled to local memory costs an L1 miss each time it is touched.
+//   w->pkq[b]  list entry (packed row, column) of the tile that uses prefetch buffer b next
+//   w->st      bit b: that tile exists; bit 2+b: it comes from the full list (a heavy tile is skipped
+//              there: pass 1 rendered it); bits 4..6: the sub-queue this warp claims from; bits 8..11:
+//              sub-queues found empty so far
+#define FINE_ST_VALID(b) (1u << (b))
+#define FINE_ST_FULL(b) (4u << (b))
+#define FINE_ST_HOME(st) (((st) >> 4) & (PM_FINE_SUBQ - 1u))
+#define FINE_ST_DRY(st) (((st) >> 8) & 15u)
 
-__device__ __forceinline__ uint32_t fine_claim(const PmFrameArgs &A, const FineNext &nx, uint32_t lane) {
+__device__ __forceinline__ uint32_t fine_claim(const PmFrameArgs &A, const FineWarpSmem *w, uint32_t lane) {
     // (atom.inc with a bound that is never reached, not atom.add: ptxas turns an add -- or an inc bounded by
     // 2^32-1 -- on a warp-uniform address into a warp-aggregated atomic followed by a shuffle of its result,
     // even from inline PTX, and that shuffle waits for the atomic right here)
     uint32_t k = 0;
-    if (lane == 0) asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(k) : "l"(&A.queue->sub[nx.home][0]) : "memory");
+    if (lane == 0) asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(k) : "l"(&A.queue->sub[FINE_ST_HOME(w->st)][0]) : "memory");
     return k;
 }
 // Turns the claim (lane 0's `claim` = k in the warp's current sub-queue) into a list entry on its way into
-// w->pkq[slot] (no register waits for it).  The empty asm keeps the compiler from hoisting the shuffle up
+// w->pkq[b] (no register waits for it).  The empty asm keeps the compiler from hoisting the shuffle up
 // to the atomic.  A sub-queue that has run dry sends the warp on to the next one, until all are dry.
-__device__ __forceinline__ bool fine_entry(const PmFrameArgs &A, FineNext &nx, uint32_t claim, FineWarpSmem *w, uint32_t slot, uint32_t n_heavy, uint32_t n_total, bool *full) {
+__device__ __forceinline__ void fine_entry(const PmFrameArgs &A, uint32_t claim, FineWarpSmem *w, uint32_t b, uint32_t n_heavy, uint32_t n_total) {
     asm volatile("" : "+r"(claim) : : "memory");
-    uint32_t q = nx.home + PM_FINE_SUBQ * __shfl_sync(PM_FULL_MASK, claim, 0);
-    while (q >= n_total) {
-        if (++nx.dry >= PM_FINE_SUBQ) return false;
-        nx.home = (nx.home + 1u) & (PM_FINE_SUBQ - 1u);
+    uint32_t st = w->st & ~(FINE_ST_VALID(b) | FINE_ST_FULL(b));
+    uint32_t home = FINE_ST_HOME(st), dry = FINE_ST_DRY(st);
+    uint32_t q = home + PM_FINE_SUBQ * __shfl_sync(PM_FULL_MASK, claim, 0);
+    while (q >= n_total && dry < PM_FINE_SUBQ) {
+        if (++dry >= PM_FINE_SUBQ) break;
+        home = (home + 1u) & (PM_FINE_SUBQ - 1u);
         uint32_t k = 0;
-        if ((threadIdx.x & 31u) == 0) k = atomicAdd(&A.queue->sub[nx.home][0], 1u);
-        q = nx.home + PM_FINE_SUBQ * __shfl_sync(PM_FULL_MASK, k, 0);
+        if ((threadIdx.x & 31u) == 0) k = atomicAdd(&A.queue->sub[home][0], 1u);
+        q = home + PM_FINE_SUBQ * __shfl_sync(PM_FULL_MASK, k, 0);
     }
-    *full = q >= n_heavy;
-    if ((threadIdx.x & 31u) == 0) cp_async4(&w->pkq[slot], *full ? &A.complex_list[q - n_heavy] : &A.complex_list[A.n_rows * A.n_tx + q]);
-    cp_async_commit();
-    return true;
+    st = (st & ~0xff0u) | (home << 4) | (dry << 8);
+    if (q < n_total) {
+        const bool full = q >= n_heavy;
+        st |= FINE_ST_VALID(b) | (full ? FINE_ST_FULL(b) : 0u);
+        if ((threadIdx.x & 31u) == 0) cp_async4(&w->pkq[b], full ? &A.complex_list[q - n_heavy] : &A.complex_list[A.n_rows * A.n_tx + q]);
+        cp_async_commit();
+    }
+    __syncwarp();
+    w->st = st;
 }
 // Starts the copy of a tile's header words and inline record slots into buffer `p`.
 __device__ __forceinline__ void fine_prefetch(const PmFrameArgs &A, FineWarpSmem *w, uint32_t p, uint32_t pk, uint32_t lane) {
@@ -313,37 +351,50 @@ __device__ __forceinline__ void fine_prefetch(const PmFrameArgs &A, FineWarpSmem
 }
 // Pipeline step, part 1 (once the tile's own set-up is done): the next tile's list entry, requested
 // when the previous tile was stored, has arrived; start the copy of that tile's data.
-__device__ __forceinline__ void fine_step1(const PmFrameArgs &A, FineNext &nx, FineWarpSmem *w, uint32_t p, uint32_t *pk_next, uint32_t lane) {
-    if (!nx.have1) return;
+__device__ __forceinline__ void fine_step1(const PmFrameArgs &A, FineWarpSmem *w, uint32_t p, uint32_t lane) {
+    if (!(w->st & FINE_ST_VALID(p ^ 1u))) return;
     cp_async_wait_all();
     __syncwarp();
-    *pk_next = w->pkq[p ^ 1u];
-    fine_prefetch(A, w, p ^ 1u, *pk_next, lane);
+    fine_prefetch(A, w, p ^ 1u, w->pkq[p ^ 1u], lane);
 }
 // Pipeline step, parts 2 and 3: claim the position after the next tile; look its list entry up.
-__device__ __forceinline__ void fine_step3(const PmFrameArgs &A, FineNext &nx, uint32_t claim, FineWarpSmem *w, uint32_t p, uint32_t n_heavy, uint32_t n_total) {
-    if (nx.have1) nx.have2 = fine_entry(A, nx, claim, w, p, n_heavy, n_total, &nx.full2);
+__device__ __forceinline__ uint32_t fine_step2(const PmFrameArgs &A, const FineWarpSmem *w, uint32_t p, uint32_t lane) {
+    return (w->st & FINE_ST_VALID(p ^ 1u)) ? fine_claim(A, w, lane) : 0u;
+}
+__device__ __forceinline__ void fine_step3(const PmFrameArgs &A, uint32_t claim, FineWarpSmem *w, uint32_t p, uint32_t n_heavy, uint32_t n_total) {
+    if (w->st & FINE_ST_VALID(p ^ 1u)) {
+        fine_entry(A, claim, w, p, n_heavy, n_total);
+    } else {
+        __syncwarp();
+        w->st &= ~(FINE_ST_VALID(p) | FINE_ST_FULL(p));
+    }
 }
 
 // One tile that owns records; its header and inline records are in buffer `p` of w.  All 32 lanes
 // execute this together.  Records are handled in chunks of 32, one per lane; chunk 0 is the inline
 // slots.  Pixel layout: lane l owns pixel row (l >> 1), pixels 8*(l & 1) .. +7.
 template <bool F32, bool EXACT>
-__device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t packed_tile, bool skip_heavy, FineWarpSmem *w, uint32_t p, uint32_t lane,
-                                                  FineNext &nx, uint32_t *pk_next, uint32_t n_heavy, uint32_t n_total) {
-    const uint32_t trow = packed_tile >> 16, tx = packed_tile & 0xffffu;
+__device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarpSmem *w, uint32_t p, uint32_t lane, uint32_t n_heavy, uint32_t n_total) {
     cp_async_wait_all();
     __syncwarp();
-    // first half of the pipeline step: next tile's data on its way, the position after it claimed
-    nx.have2 = false;
+    const uint32_t packed_tile = w->pkq[p];
+    const bool skip_heavy = (w->st & FINE_ST_FULL(p)) != 0;
+    const uint32_t trow = packed_tile >> 16, tx = packed_tile & 0xffffu;
+#if PM_FINE_EARLY_CLAIM
+    const uint32_t claim = fine_step2(A, w, p, lane);
+#endif
     const uint4 *rec = w->rec[p];
     const u64 cw = w->hdr[p][0], ow = w->hdr[p][1];
     const uint32_t n = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
     const uint32_t occ_item1 = (uint32_t)(ow >> 32) == A.stamp ? (uint32_t)ow : 0u;
     const bool heavy = n > PM_TILE_SLOTS;
     if (heavy && skip_heavy) {  // pass 1 rendered it
-        fine_step1(A, nx, w, p, pk_next, lane);
-        fine_step3(A, nx, nx.have1 ? fine_claim(A, nx, lane) : 0u, w, p, n_heavy, n_total);
+        fine_step1(A, w, p, lane);
+#if PM_FINE_EARLY_CLAIM
+        fine_step3(A, claim, w, p, n_heavy, n_total);
+#else
+        fine_step3(A, fine_step2(A, w, p, lane), w, p, n_heavy, n_total);
+#endif
         return;
     }
     uint32_t occ_rgba = 0xffffffffu;  // solidColor starts as opaque white (metal:74)
@@ -352,7 +403,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
     // index the overflow chain.  n_over counts what was actually found (a frame whose overflow
     // pool ran out has fewer links than cnt says; the host re-renders such a frame, it only must
     // not fault).
-    const uint32_t n_inline = heavy ? PM_TILE_SLOTS : n;
+    const uint32_t n_inline = n < PM_TILE_SLOTS ? n : PM_TILE_SLOTS;
     uint32_t n_over = 0;
     uint32_t tail = 0;  // 1 + pool index of the first record that did not fit the shared-memory index
     if (heavy) {
@@ -406,8 +457,12 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
                                          (float)((c >> 16) & 0xff) / 255.0f, (float)(c >> 24) / 255.0f);
             for (int j = 0; j < 8; j++) dst32[j] = f;
         }
-        fine_step1(A, nx, w, p, pk_next, lane);
-        fine_step3(A, nx, nx.have1 ? fine_claim(A, nx, lane) : 0u, w, p, n_heavy, n_total);
+        fine_step1(A, w, p, lane);
+#if PM_FINE_EARLY_CLAIM
+        fine_step3(A, claim, w, p, n_heavy, n_total);
+#else
+        fine_step3(A, fine_step2(A, w, p, lane), w, p, n_heavy, n_total);
+#endif
         return;
     }
 
@@ -426,7 +481,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
             w->rgb[2][g][lane] = make_float4(b2, b2, b2, b2);
         }
     }
-    fine_step1(A, nx, w, p, pk_next, lane);
+    fine_step1(A, w, p, lane);
     const float tile_x0 = (float)(tx * PM_TILE_W), tile_y0 = (float)((A.tile_y0 + trow) * PM_TILE_H);  // scene coordinates
     // this lane's two 4-pixel groups of the coverage arrays (word offsets; cov = acc + 256)
     const int my_off0 = fine_swz((int)prow, (int)half * 8), my_off1 = fine_swz((int)prow, (int)half * 8 + 4);
@@ -568,7 +623,11 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
     // the position after the next tile is claimed here and looked up after the encode: the claim's result
     // must stay in its register until then (anything that touches it -- a spill included -- waits for the
     // atomic), and this is the stretch of the tile with the fewest live values
-    const uint32_t claim = nx.have1 ? fine_claim(A, nx, lane) : 0u;
+#if PM_FINE_EARLY_CLAIM
+    fine_step3(A, claim, w, p, n_heavy, n_total);
+#else
+    const uint32_t claim = fine_step2(A, w, p, lane);
+#endif
 
     #pragma unroll 1
     for (int g = 0; g < 2; g++) {
@@ -583,13 +642,38 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, uint32_t
             dst32[4 * g + 3] = make_float4(linear_to_srgb<EXACT>(r.w), linear_to_srgb<EXACT>(gg.w), linear_to_srgb<EXACT>(b.w), 1.0f);
         }
     }
-    fine_step3(A, nx, claim, w, p, n_heavy, n_total);
+#if !PM_FINE_EARLY_CLAIM
+    fine_step3(A, claim, w, p, n_heavy, n_total);
+#endif
 }
+
+__device__ __forceinline__ uint32_t fine_batch_claim(const PmFrameArgs &A, uint32_t lane) {
+    uint32_t k = 0;  // (atom.inc: see fine_claim)
+    if (lane == 0) asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(k) : "l"(&A.queue->batch_next) : "memory");
+    return k;
+}
+#if PM_FINE_BATCH_PIPELINE
+// The solid batches are pipelined like the tiles with records: while batch i is stored, the cnt / occ
+// words of batch i+1 are in flight into the other prefetch buffer and the position of batch i+2 is claimed.
+__device__ __forceinline__ void fine_batch_prefetch(const PmFrameArgs &A, FineWarpSmem *w, uint32_t b, uint32_t batch, uint32_t batches_per_row,
+                                                    uint32_t n_batches, uint32_t lane) {
+    if (batch < n_batches) {
+        const uint32_t row = batch / batches_per_row;
+        const uint32_t t = (batch - row * batches_per_row) * 32u + lane;
+        if (t < A.n_tx) {
+            const size_t tile = (size_t)row * A.n_tx + t;
+            cp_async8(&w->rec[b][lane], &A.cnt[tile]);
+            cp_async8(reinterpret_cast<unsigned char *>(&w->rec[b][lane]) + 8, &A.occ[tile]);
+        }
+    }
+    cp_async_commit();  // (an empty group when there is nothing to fetch: the group count stays in step)
+}
+#endif
 
 // 32 consecutive tiles of one tile row; the solid ones are written row-wise: each store
 // instruction covers 512 contiguous bytes (128 pixels) of one pixel row.
 template <bool F32>
-__device__ __forceinline__ void fine_solid_batch(const PmFrameArgs &A, uint32_t batch, uint32_t batches_per_row, uint32_t lane) {
+__device__ __forceinline__ void fine_solid_batch(const PmFrameArgs &A, uint32_t batch, uint32_t batches_per_row, const uint4 *words, uint32_t lane) {
     const uint32_t row = batch / batches_per_row;
     const uint32_t t0 = (batch - row * batches_per_row) * 32u;
     const uint32_t t = t0 + lane;
@@ -597,8 +681,14 @@ __device__ __forceinline__ void fine_solid_batch(const PmFrameArgs &A, uint32_t 
     bool solid = false;
     uint32_t colour = 0xffffffffu;  // solidColor starts as opaque white (metal:74)
     if (valid) {
+#if PM_FINE_BATCH_PIPELINE
+        const uint4 ww = words[lane];  // this lane's tile: cnt word, occ word (fine_batch_prefetch)
+        const u64 cw = ((u64)ww.y << 32) | ww.x, ow = ((u64)ww.w << 32) | ww.z;
+#else
+        (void)words;
         const size_t tile = (size_t)row * A.n_tx + t;
         const u64 cw = A.cnt[tile], ow = A.occ[tile];
+#endif
         solid = !((uint32_t)(cw >> 32) == A.stamp && (uint32_t)cw != 0u);
         if (solid && (uint32_t)(ow >> 32) == A.stamp && (uint32_t)ow != 0u)
             colour = ld_u32(A.scene + A.items_ix + (size_t)((uint32_t)ow - 1u) * PM_ITEM_SIZE + PM_FILL_RGBA);
@@ -649,37 +739,59 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArg
     bool complex_left = true, batches_left = true;
     // warps 3 and 7 (one of the SM's four schedulers) prefer the solid batches, the rest the tiles with records
     const bool prefer_complex = (warp & 3u) != 3u;
-    FineNext nx;
-    nx.have1 = nx.have2 = nx.full1 = nx.full2 = false;
-    nx.home = blockIdx.x & (PM_FINE_SUBQ - 1u); nx.dry = 0;
-    uint32_t pk_cur = 0, pk_next = 0, p = 0;
-    bool started = false, full_cur = false;
+    uint32_t p = 0;
+    bool started = false;
+#if PM_FINE_BATCH_PIPELINE
+    uint32_t b_cur = 0, b_next = 0, bp = 0;
+    bool b_started = false;
+#endif
+    if (lane == 0) w->st = (blockIdx.x & (PM_FINE_SUBQ - 1u)) << 4;
+    __syncwarp();
     while (complex_left || batches_left) {
         const bool take_complex = complex_left && (prefer_complex || !batches_left);
         if (take_complex) {
             // (one call site for the tile code: the kernel is sensitive to its instruction footprint)
             if (!started) {  // fill the pipeline: this tile's data, the next tile's list entry
                 started = true;
-                if (!fine_entry(A, nx, fine_claim(A, nx, lane), w, 2, n_heavy, n_total, &full_cur)) { complex_left = false; continue; }
+                fine_entry(A, fine_claim(A, w, lane), w, p, n_heavy, n_total);
+                if (!(w->st & FINE_ST_VALID(p))) { complex_left = false; continue; }
                 cp_async_wait_all();
                 __syncwarp();
-                pk_cur = w->pkq[2];
-                fine_prefetch(A, w, p, pk_cur, lane);
-                nx.have1 = fine_entry(A, nx, fine_claim(A, nx, lane), w, p ^ 1u, n_heavy, n_total, &nx.full1);
+                fine_prefetch(A, w, p, w->pkq[p], lane);
+                fine_entry(A, fine_claim(A, w, lane), w, p ^ 1u, n_heavy, n_total);
             }
-            fine_complex_tile<F32, EXACT>(A, pk_cur, full_cur, w, p, lane, nx, &pk_next, n_heavy, n_total);
+            fine_complex_tile<F32, EXACT>(A, w, p, lane, n_heavy, n_total);
             p ^= 1u;
-            pk_cur = pk_next;
-            full_cur = nx.full1;
-            if (!nx.have1) complex_left = false;
-            nx.have1 = nx.have2;
-            nx.full1 = nx.full2;
+            if (!(w->st & FINE_ST_VALID(p))) complex_left = false;
         } else {
-            uint32_t q = 0;
-            if (lane == 0) q = atomicAdd(&A.queue->batch_next, 1u);
+#if PM_FINE_BATCH_PIPELINE
+            if (!b_started) {  // fill the pipeline: two batches claimed, their words on the way
+                b_started = true;
+                cp_async_wait_all();
+                __syncwarp();
+                b_cur = __shfl_sync(PM_FULL_MASK, fine_batch_claim(A, lane), 0);
+                fine_batch_prefetch(A, w, 0, b_cur, batches_per_row, n_batches, lane);
+                b_next = __shfl_sync(PM_FULL_MASK, fine_batch_claim(A, lane), 0);
+                fine_batch_prefetch(A, w, 1, b_next, batches_per_row, n_batches, lane);
+                bp = 0;
+            }
+            if (b_cur >= n_batches) { batches_left = false; cp_async_wait_all(); __syncwarp(); continue; }
+            uint32_t claim = fine_batch_claim(A, lane);  // the batch after the next one
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();
+            fine_solid_batch<F32>(A, b_cur, batches_per_row, w->rec[bp], lane);
+            __syncwarp();
+            asm volatile("" : "+r"(claim) : : "memory");
+            b_cur = b_next;
+            b_next = __shfl_sync(PM_FULL_MASK, claim, 0);
+            fine_batch_prefetch(A, w, bp, b_next, batches_per_row, n_batches, lane);
+            bp ^= 1u;
+#else
+            uint32_t q = fine_batch_claim(A, lane);
             q = __shfl_sync(PM_FULL_MASK, q, 0);
             if (q >= n_batches) { batches_left = false; continue; }
-            fine_solid_batch<F32>(A, q, batches_per_row, lane);
+            fine_solid_batch<F32>(A, q, batches_per_row, nullptr, lane);
+#endif
         }
     }
 }
