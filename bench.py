@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-rows", type=int, default=0, help="tile rows in the CPU sample (0 = auto, ~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--equal-strips", action="store_true", help="equal-height row strips instead of cost-balanced ones")
     return ap.parse_args()
 
 
@@ -218,7 +219,10 @@ def main():
 
     r = pm.PietRenderer(device=local_rank)
     r.drawable_size_will_change(size, size)
-    bounds = pm.strip_bounds(nty, world)
+    # row-strip shard: every rank derives the same cost-balanced bounds from the broadcast scene (no collective)
+    scene_host = scene_dev.cpu().numpy()
+    bounds = pm.balanced_strip_bounds(pm.row_costs(scene_host, size, size), world) if (world > 1 and not args.equal_strips) \
+        else pm.strip_bounds(nty, world)
     if world > 1:
         r.set_strip(bounds[rank], bounds[rank + 1])
     r.set_scene_device(scene_dev.data_ptr(), scene_bytes)
@@ -314,7 +318,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": "Ghostscript_Tiger %dx%d" % (size, size) if args.scene == "tiger" else "%s %dx%d" % (args.scene, size, size),
-                "scene_bytes": scene_bytes, "tile": "16x16", "parallelism": "row-strips x%d" % world,
+                "scene_bytes": scene_bytes, "tile": "16x16", "parallelism": "row-strips x%d (%s)" % (world, "equal height" if args.equal_strips or world == 1 else "cost-balanced"),
                 "strip_tile_rows": [bounds[g + 1] - bounds[g] for g in range(world)],
                 "l2": ("flushed between timed frames (strip %.0f MiB <= L2)" % (fb_bytes / 2**20)) if flush
                       else "framebuffer strip %.0f MiB > 126 MB L2: every frame streams to HBM" % (fb_bytes / 2**20),
@@ -331,8 +335,6 @@ def main():
             "frame_stats": {"overflow_records": st.n_overflow_records, "complex_tiles": st.n_complex_tiles, "tiles": st.n_tiles},
         }
         if not args.no_cpu_baseline:
-            import oracle_api
-            scene_host = scene_dev.cpu().numpy()
             v, desc, threads = cpu_sample(scene_host, size, args.cpu_rows)
             out["cpu_baseline"] = {"value": v, "unit": "Mpixel/s", "cores": threads, "kind": "port", "sample": desc}
     r.close()

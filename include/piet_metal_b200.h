@@ -121,6 +121,17 @@ int64_t pm_scene_from_pathlist(const char *text, size_t len, double scale, uint8
 /* Bounds-checks every ref/count of an encoded scene (the reference never does). */
 int pm_scene_validate(const uint8_t *scene, size_t len);
 
+/* Multi-GPU row-strip shard (host only).  The reference is single-device; tiles are independent
+ * given the scene (TestApp/PietRender.metal:167-170, :463-466), so N GPUs take N contiguous strips
+ * of tile rows.  pm_scene_row_costs estimates the relative cost of every tile row of the frame
+ * (n_rows >= ceil(height / 16) entries); pm_balance_strips cuts the rows into n_parts contiguous,
+ * non-empty strips whose largest cost is minimal: strip g = rows [bounds[g], bounds[g+1]),
+ * bounds has n_parts + 1 entries.  Both are deterministic, so every rank can compute its own strip
+ * from the broadcast scene without a further collective. */
+int pm_scene_row_costs(const uint8_t *scene, size_t len, uint32_t width, uint32_t height,
+                       float *cost, size_t n_rows);
+int pm_balance_strips(const float *cost, uint32_t n_rows, uint32_t n_parts, uint32_t *bounds);
+
 /* ------------------------------------------------------------------------------------------- */
 /* Renderer (CUDA, sm_100a)                                                                     */
 /* ------------------------------------------------------------------------------------------- */

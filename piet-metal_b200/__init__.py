@@ -65,6 +65,8 @@ EXPORTS = [
     "pm_encoder_new", "pm_encoder_begin_group", "pm_encoder_end_group", "pm_encoder_circle",
     "pm_encoder_stroke_line", "pm_encoder_fill", "pm_encoder_polyline", "pm_encoder_bytes", "pm_encoder_free",
     "pm_flatten_svg_path", "pm_parse_color", "pm_scene_build", "pm_scene_from_pathlist", "pm_scene_validate",
+    "pm_scene_row_costs", "pm_balance_strips",
+    "pm_scene_row_costs", "pm_balance_strips",
     "pm_renderer_create", "pm_renderer_destroy", "pm_renderer_resize", "pm_renderer_set_strip",
     "pm_renderer_set_scene", "pm_renderer_set_scene_device", "pm_renderer_render", "pm_renderer_sync",
     "pm_renderer_read_rgba8", "pm_renderer_render_host", "pm_renderer_framebuffer", "pm_renderer_stream",
@@ -103,6 +105,8 @@ def _lib():
         "pm_scene_build": (i64, [ctypes.POINTER(SceneDesc), vp, sz]),
         "pm_scene_from_pathlist": (i64, [ctypes.c_char_p, sz, dbl, vp, sz]),
         "pm_scene_validate": (cint, [vp, sz]),
+        "pm_scene_row_costs": (cint, [vp, sz, u32, u32, vp, sz]),
+        "pm_balance_strips": (cint, [vp, u32, u32, vp]),
         "pm_renderer_create": (cint, [ctypes.POINTER(vp), ctypes.POINTER(Config)]),
         "pm_renderer_destroy": (None, [vp]),
         "pm_renderer_resize": (cint, [vp, u32, u32]),
@@ -350,6 +354,23 @@ class PietRenderer:
         s = ctypes.c_void_p()
         _check(_lib().pm_renderer_stream(self._h, ctypes.byref(s)), "pm_renderer_stream")
         return s.value or 0
+
+
+def row_costs(scene, width, height):
+    """pm_scene_row_costs: relative cost of every tile row of the frame (float32 array)."""
+    scene = np.ascontiguousarray(scene, np.uint8)
+    n = (height + 15) // 16
+    cost = np.zeros(n, np.float32)
+    _check(_lib().pm_scene_row_costs(_ptr(scene), scene.size, width, height, _ptr(cost), n), "pm_scene_row_costs")
+    return cost
+
+
+def balanced_strip_bounds(cost, world_size):
+    """pm_balance_strips: contiguous non-empty strips of tile rows with the smallest possible maximum cost."""
+    cost = np.ascontiguousarray(cost, np.float32)
+    bounds = np.zeros(world_size + 1, np.uint32)
+    _check(_lib().pm_balance_strips(_ptr(cost), cost.size, world_size, _ptr(bounds)), "pm_balance_strips")
+    return [int(b) for b in bounds]
 
 
 def strip_bounds(n_tile_rows, world_size):

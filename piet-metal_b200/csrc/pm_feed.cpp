@@ -847,4 +847,118 @@ int pm_scene_validate(const uint8_t *scene, size_t len) {
     return PM_OK;
 }
 
+// ---- row-strip shard: cost estimate per tile row and balanced contiguous partition --------------
+// The frame's tile rows are independent given the scene (TestApp/PietRender.metal:167-170, :463-466),
+// so the multi-GPU shard is a partition of the rows; equal-height strips leave the GPUs that own
+// the middle of a centred drawing with most of the work.  cost[r] models one GPU's time for tile
+// row r: a term per tile (the framebuffer store) and a term per (segment, tile) crossing (binning
+// and coverage work), in the ratio measured on the 8192^2 and 16384^2 tiger.
+#define PM_COST_PER_TILE 0.25f
+#define PM_COST_PER_CROSSING 0.32f
+
+int pm_scene_row_costs(const uint8_t *scene, size_t len, uint32_t width, uint32_t height, float *cost, size_t n_rows) {
+    if (!scene || !cost || width == 0 || height == 0) return PM_ERR_INVALID_ARG;
+    const int st = pm_scene_validate(scene, len);
+    if (st != PM_OK) return st;
+    const uint32_t n_tx = (width + PM_TILE_W - 1) / PM_TILE_W, n_ty = (height + PM_TILE_H - 1) / PM_TILE_H;
+    if (n_rows < n_ty) return PM_ERR_BUFFER_TOO_SMALL;
+    std::vector<double> acc(n_ty, 0.0);
+    pm_group_header g;
+    memcpy(&g, scene, sizeof g);
+    auto add_segment = [&](double sx, double sy, double ex, double ey, double hw) {
+        if (!(std::isfinite(sx) && std::isfinite(sy) && std::isfinite(ex) && std::isfinite(ey))) return;
+        const double y_lo = std::min(sy, ey) - hw, y_hi = std::max(sy, ey) + hw;
+        long r0 = (long)std::floor(y_lo / PM_TILE_H), r1 = (long)std::floor(y_hi / PM_TILE_H);
+        if (r1 < 0 || r0 >= (long)n_ty) return;
+        r0 = std::max(r0, 0L);
+        r1 = std::min(r1, (long)n_ty - 1);
+        const double dy = ey - sy;
+        for (long r = r0; r <= r1; r++) {
+            // x extent of the segment inside the band of this tile row
+            double xa = sx, xb = ex;
+            if (dy != 0.0) {
+                const double ya = std::max((double)r * PM_TILE_H - hw, std::min(sy, ey)), yb = std::min((double)(r + 1) * PM_TILE_H + hw, std::max(sy, ey));
+                xa = sx + (ya - sy) * (ex - sx) / dy;
+                xb = sx + (yb - sy) * (ex - sx) / dy;
+            }
+            double x_lo = std::max(std::min(xa, xb) - hw, 0.0), x_hi = std::min(std::max(xa, xb) + hw, (double)n_tx * PM_TILE_W);
+            if (x_hi < x_lo) continue;
+            acc[(size_t)r] += std::floor(x_hi / PM_TILE_W) - std::floor(x_lo / PM_TILE_W) + 1.0;
+        }
+    };
+    for (uint64_t i = 0; i < g.n_items; i++) {
+        pm_item_any it;
+        memcpy(&it, scene + g.items_ix + i * PM_ITEM_SIZE, sizeof it);
+        if (it.tag == PM_ITEM_FILL || it.tag == PM_ITEM_POLY) {
+            const uint32_t np = it.body[2], pix = it.body[3];
+            const float *pts = reinterpret_cast<const float *>(scene + pix);
+            float w = 0.0f;
+            if (it.tag == PM_ITEM_POLY) memcpy(&w, &it.body[1], 4);
+            const double hw = it.tag == PM_ITEM_POLY ? 0.5 * w + 0.5 : 0.0;
+            const uint32_t n_seg = it.tag == PM_ITEM_FILL ? np : np - 1;
+            for (uint32_t k = 0; k < n_seg; k++) {
+                const uint32_t k1 = k + 1 == np ? 0 : k + 1;
+                add_segment(pts[2 * k], pts[2 * k + 1], pts[2 * k1], pts[2 * k1 + 1], hw);
+            }
+        } else if (it.tag == PM_ITEM_LINE) {
+            pm_item_line ln;
+            memcpy(&ln, &it, sizeof ln);
+            add_segment(ln.sx, ln.sy, ln.ex, ln.ey, 0.5 * ln.width + 0.5);
+        } else if (it.tag == PM_ITEM_CIRCLE) {
+            pm_bbox bb;
+            memcpy(&bb, scene + PM_GROUP_HEADER_SIZE + i * PM_BBOX_SIZE, sizeof bb);
+            for (uint32_t r = bb.y0 / PM_TILE_H; r <= bb.y1 / PM_TILE_H && r < n_ty; r++) acc[r] += (double)(bb.x1 / PM_TILE_W - bb.x0 / PM_TILE_W + 1);
+        }
+    }
+    for (uint32_t r = 0; r < n_ty; r++) cost[r] = PM_COST_PER_TILE * (float)n_tx + PM_COST_PER_CROSSING * (float)acc[r];
+    return PM_OK;
+}
+
+int pm_balance_strips(const float *cost, uint32_t n_rows, uint32_t n_parts, uint32_t *bounds) {
+    if (!cost || !bounds || n_parts == 0 || n_rows == 0) return PM_ERR_INVALID_ARG;
+    if (n_parts > n_rows) return PM_ERR_INVALID_ARG;  // every strip owns at least one tile row
+    std::vector<double> pre(n_rows + 1, 0.0);
+    double mx = 0.0;
+    for (uint32_t r = 0; r < n_rows; r++) {
+        const double c = cost[r] > 0.0f && std::isfinite(cost[r]) ? cost[r] : 0.0;
+        pre[r + 1] = pre[r] + c;
+        mx = std::max(mx, c);
+    }
+    // smallest capacity for which a greedy left-to-right packing needs at most n_parts strips
+    auto parts_needed = [&](double cap, std::vector<uint32_t> *cuts) {
+        uint32_t parts = 0, r = 0;
+        while (r < n_rows) {
+            // furthest end such that the strip [r, end) fits, leaving at least one row for each remaining strip
+            uint32_t end = (uint32_t)(std::upper_bound(pre.begin() + r + 1, pre.end(), pre[r] + cap) - pre.begin()) - 1;
+            if (end <= r) end = r + 1;
+            if (cuts) {
+                const uint32_t remaining = n_parts - 1 - std::min(parts, n_parts - 1);
+                if (end > n_rows - remaining) end = n_rows - remaining;
+                if (end <= r) end = r + 1;
+                cuts->push_back(end);
+            }
+            r = end;
+            parts++;
+        }
+        return parts;
+    };
+    double lo = mx, hi = pre[n_rows];
+    for (int it = 0; it < 60 && hi - lo > 1e-9 * std::max(1.0, hi); it++) {
+        const double mid = 0.5 * (lo + hi);
+        if (parts_needed(mid, nullptr) <= n_parts) hi = mid; else lo = mid;
+    }
+    std::vector<uint32_t> cuts;
+    parts_needed(hi * (1.0 + 1e-9), &cuts);
+    bounds[0] = 0;
+    for (uint32_t g = 1; g <= n_parts; g++) {
+        uint32_t b = g - 1 < cuts.size() ? cuts[g - 1] : n_rows;
+        if (b < bounds[g - 1] + 1) b = bounds[g - 1] + 1;       // non-empty
+        const uint32_t max_b = n_rows - (n_parts - g);              // room for the strips that follow
+        if (b > max_b) b = max_b;
+        bounds[g] = b;
+    }
+    bounds[n_parts] = n_rows;
+    return PM_OK;
+}
+
 }  // extern "C"

@@ -33,7 +33,8 @@ def _worker(rank, world, port, out_dir, size):
     if rank != 0:
         scene = torch.empty(int(n[0]), dtype=torch.uint8)
     dist.broadcast(scene, 0)                       # the one collective: scene bytes, once
-    bounds = pm.strip_bounds((size + 15) // 16, world)
+    # every rank derives the same cost-balanced strips from the broadcast scene
+    bounds = pm.balanced_strip_bounds(pm.row_costs(scene.numpy(), size, size), world)
     strip = oracle_api.harness_render(scene.numpy(), size, size, tile_y0=bounds[rank], tile_y1=bounds[rank + 1])["rgba8"]
     rows = [(bounds[g + 1] - bounds[g]) * 16 for g in range(world)]
     if rank == 0:
@@ -63,3 +64,41 @@ def test_strip_bounds_partition(pm):
             b = pm.strip_bounds(rows, world)
             assert b[0] == 0 and b[-1] == rows and all(b[i] <= b[i + 1] for i in range(world))
             assert max(b[i + 1] - b[i] for i in range(world)) - min(b[i + 1] - b[i] for i in range(world)) <= 1
+
+
+def test_balanced_strips_properties(pm):
+    """pm_balance_strips: contiguous, non-empty, covering; never worse than equal-height strips; optimal on
+    small cases (brute force)."""
+    import itertools
+    rng = np.random.default_rng(7)
+    for rows, world in ((1, 1), (5, 5), (9, 3), (12, 4), (64, 8), (512, 8)):
+        for trial in range(4):
+            cost = rng.random(rows).astype(np.float32) * (10.0 if trial % 2 else 1.0) + (0.0 if trial < 2 else 5.0)
+            b = pm.balanced_strip_bounds(cost, world)
+            assert b[0] == 0 and b[-1] == rows and all(b[i] < b[i + 1] for i in range(world))
+            worst = max(cost[b[i]:b[i + 1]].sum() for i in range(world))
+            eq = pm.strip_bounds(rows, world)
+            if all(eq[i] < eq[i + 1] for i in range(world)):
+                assert worst <= max(cost[eq[i]:eq[i + 1]].sum() for i in range(world)) * (1 + 1e-5)
+            if rows <= 12:
+                best = min(max(cost[c0:c1].sum() for c0, c1 in zip((0,) + cuts, cuts + (rows,)))
+                           for cuts in itertools.combinations(range(1, rows), world - 1))
+                assert worst <= best * (1 + 1e-5)
+    with pytest.raises(pm.PietMetalError):
+        pm.balanced_strip_bounds(np.ones(3, np.float32), 4)
+
+
+def test_row_costs_follow_the_drawing(pm):
+    """pm_scene_row_costs: every row costs at least the per-tile term; the tiger's middle rows cost several times
+    the cheapest row; the balanced 8-way split of the 8192^2 tiger is within 2 % of even."""
+    size = 2048
+    scene = pm.build_scene(pm.SCENE_TIGER, size, size)
+    cost = pm.row_costs(scene, size, size)
+    assert cost.shape == (size // 16,) and (cost > 0).all()
+    assert cost.min() >= 0.25 * (size // 16) and cost[len(cost) // 2] > 3 * cost.min()
+    b = pm.balanced_strip_bounds(cost, 8)
+    parts = np.array([cost[b[i]:b[i + 1]].sum() for i in range(8)])
+    assert parts.max() / parts.mean() < 1.06
+    rect = pm.build_scene(pm.SCENE_RECT1, 64, 64, rect=(3, 2, 13, 14))
+    c = pm.row_costs(rect, 64, 64)
+    assert c[0] > c[1] == c[2] == c[3]
