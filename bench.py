@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=0, help="tile rows in the CPU sample (0 = auto, ~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--equal-strips", action="store_true", help="equal-height row strips instead of cost-balanced ones")
+    ap.add_argument("--emulate-world", default="", help="experiments on 1 GPU: 'N:g' renders the strip rank g of N would own")
     return ap.parse_args()
 
 
@@ -225,6 +226,11 @@ def main():
         else pm.strip_bounds(nty, world)
     if world > 1:
         r.set_strip(bounds[rank], bounds[rank + 1])
+    if args.emulate_world and world == 1:
+        ew, eg = [int(x) for x in args.emulate_world.split(":")]
+        eb = pm.strip_bounds(nty, ew) if args.equal_strips else pm.balanced_strip_bounds(pm.row_costs(scene_host, size, size), ew)
+        r.set_strip(eb[eg], eb[eg + 1])
+        bounds = [eb[eg], eb[eg + 1]]
     r.set_scene_device(scene_dev.data_ptr(), scene_bytes)
     strip_rows = r.strip_rows
     fb_bytes = strip_rows * size * 4

@@ -160,7 +160,7 @@ typedef struct pm_frame_stats {
     float ms_bin_sum;
     float ms_fine_sum;
     uint32_t n_tiles;        /* tiles in the strip */
-    uint32_t n_overflow_records; /* records that did not fit their tile's 8 inline slots (last frame) */
+    uint32_t n_overflow_records; /* pool records used beyond the 16 inline slots per tile (last frame) */
     uint32_t n_complex_tiles;/* tiles that own at least one record (last frame) */
     uint32_t n_launches;     /* kernels launched per frame */
     uint32_t retries;        /* re-renders after growing the record pool */

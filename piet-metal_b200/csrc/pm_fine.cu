@@ -49,7 +49,7 @@ typedef unsigned long long u64;
 #ifndef PM_FINE_EARLY_CLAIM
 #define PM_FINE_EARLY_CLAIM 0    // 1: the next-but-one tile is claimed at the start of a tile; 0: before the encode
 #endif
-#define PM_FINE_LIST_CAP 96      // overflow records per tile indexed in shared memory; the rest is re-walked
+#define PM_FINE_LIST_CAP 112     // overflow records per tile indexed in shared memory (extension block + 64 of the chain); the rest is re-walked      
 
 __device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
 
@@ -66,7 +66,8 @@ struct FineWarpSmem {
     float4 rgb[3][2][32];
     uint4 rec[2][2 * PM_TILE_SLOTS];
     u64 hdr[2][4];
-    uint32_t idx[PM_FINE_LIST_CAP];
+    uint32_t idx[PM_FINE_LIST_CAP];  // heavy tiles: pool indices of the overflow records ...
+    uint2 ovk[PM_FINE_LIST_CAP];     // ... and their (item, key), so that only the geometry is read from global memory
     uint32_t pkq[2];  // pipeline state of the walk over the tile list (see fine_entry)
     uint32_t st;
     uint32_t pad;
@@ -400,21 +401,35 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
     uint32_t occ_rgba = 0xffffffffu;  // solidColor starts as opaque white (metal:74)
     if (occ_item1) occ_rgba = __ldg(reinterpret_cast<const uint32_t *>(A.scene + A.items_ix + (size_t)(occ_item1 - 1u) * PM_ITEM_SIZE + PM_FILL_RGBA));
 
-    // index the overflow chain.  n_over counts what was actually found (a frame whose overflow
-    // pool ran out has fewer links than cnt says; the host re-renders such a frame, it only must
-    // not fault).
+    // index the overflow records: the extension block (positions 16..63, contiguous) and the chain behind
+    // it.  n_over counts what was actually found (a frame whose overflow pool ran out has fewer records
+    // than cnt says; the host re-renders such a frame, it only must not fault).
     const uint32_t n_inline = n < PM_TILE_SLOTS ? n : PM_TILE_SLOTS;
     uint32_t n_over = 0;
     uint32_t tail = 0;  // 1 + pool index of the first record that did not fit the shared-memory index
     if (heavy) {
         const u64 vw = w->hdr[p][2];
-        uint32_t cur = (uint32_t)(vw >> 32) == A.stamp ? (uint32_t)vw : 0u;
-        while (cur != 0 && n_over < PM_FINE_LIST_CAP) {
-            if (lane == 0) w->idx[n_over] = cur - 1u;
-            cur = A.pool[cur - 1u].next;
-            n_over++;
+        uint32_t base1 = (uint32_t)(vw >> 32) == A.stamp ? (uint32_t)vw : 0u;
+        if (base1 == PM_EXT_FAILED) base1 = 0;
+        if (base1) {
+            n_over = (n < PM_TILE_SLOTS + PM_EXT_SLOTS ? n : PM_TILE_SLOTS + PM_EXT_SLOTS) - PM_TILE_SLOTS;
+            for (uint32_t i = lane; i < n_over; i += 32) {
+                w->idx[i] = base1 + i;
+                w->ovk[i] = *reinterpret_cast<const uint2 *>(&A.pool[base1 + i]);
+            }
+            if (n > PM_TILE_SLOTS + PM_EXT_SLOTS) {
+                const uint32_t n_ext = n_over;
+                uint32_t cur = A.pool[base1 - 1u].next;
+                while (cur != 0 && n_over < PM_FINE_LIST_CAP) {
+                    if (lane == 0) w->idx[n_over] = cur - 1u;
+                    cur = A.pool[cur - 1u].next;
+                    n_over++;
+                }
+                tail = cur;
+                __syncwarp();
+                for (uint32_t i = n_ext + lane; i < n_over; i += 32) w->ovk[i] = *reinterpret_cast<const uint2 *>(&A.pool[w->idx[i]]);
+            }
         }
-        tail = cur;
         __syncwarp();
     }
     const uint32_t n_chunks = 1u + ((n_over + 31u) >> 5);  // chunk 0: inline slots; chunk c >= 1: idx[32 (c - 1) ..]
@@ -430,7 +445,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
     bool has_draw = my_item != 0xffffffffu && (my_key & 15u) != PM_REC_SOLID;
     if (heavy) {
         for (uint32_t i = lane; i < n_over; i += 32) {
-            const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[w->idx[i]]);
+            const uint2 ik = w->ovk[i];
             if (ik.x >= occ_item1 && (ik.y & 15u) != PM_REC_SOLID) has_draw = true;
         }
         for (uint32_t cur = tail; cur != 0; cur = A.pool[cur - 1u].next) {
@@ -493,7 +508,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
         uint32_t cur_item = (first || my_item > last_item) ? my_item : 0xffffffffu;
         if (heavy) {
             for (uint32_t i = lane; i < n_over; i += 32) {
-                const uint32_t it = A.pool[w->idx[i]].item;
+                const uint32_t it = w->ovk[i].x;
                 if (it >= occ_item1 && (first || it > last_item) && it < cur_item) cur_item = it;
             }
             for (uint32_t cur = tail; cur != 0; cur = A.pool[cur - 1u].next) {
@@ -515,8 +530,11 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
                 t_kind = a.y & 15u; t_w0 = a.z; t_w1 = a.w;
             } else if (heavy) {
                 for (uint32_t i = lane; i < n_over; i += 32) {
-                    const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[w->idx[i]]);
-                    if (a.x == cur_item && (a.y & 15u) >= PM_REC_CIRCLE) { t_kind = a.y & 15u; t_w0 = a.z; t_w1 = a.w; }
+                    const uint2 ik = w->ovk[i];
+                    if (ik.x == cur_item && (ik.y & 15u) >= PM_REC_CIRCLE) {
+                        const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[w->idx[i]]);
+                        t_kind = a.y & 15u; t_w0 = a.z; t_w1 = a.w;
+                    }
                 }
                 for (uint32_t cur = tail; cur != 0; cur = A.pool[cur - 1u].next) {
                     const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[cur - 1u]);
@@ -553,7 +571,10 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
                     const uint32_t i = (c - 1u) * 32u + lane;
                     PmRecord rc;
                     rc.item = 0xffffffffu; rc.key = 0; rc.p[0] = rc.p[1] = rc.p[2] = rc.p[3] = 0.0f; rc.edge_y = 0.0f; rc.next = 0;
-                    if (i < n_over) rc = load_record(A.pool, w->idx[i]);
+                    if (i < n_over) {
+                        const uint2 ik = w->ovk[i];
+                        if (ik.x == cur_item && (ik.y & 15u) <= PM_REC_LINE) rc = load_record(A.pool, w->idx[i]);
+                    }
                     const bool mine = rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE;
                     if (__any_sync(PM_FULL_MASK, mine))
                         fine_pairs_cold(w, mine, rc.key & 15u, rc.p[0], rc.p[1], rc.p[2], rc.p[3], rc.edge_y, stroke, reach, tile_x0, tile_y0, lane);

@@ -309,15 +309,37 @@ struct BinSink {
         if (pos < PM_TILE_SLOTS) {
             idx = tile * PM_TILE_SLOTS + pos;
         } else {
-            // one counter serves every overflow record of the frame: aggregate the lanes that are here together
-            cg::coalesced_group og = cg::coalesced_threads();
-            uint32_t o = 0;
-            if (og.thread_rank() == 0) o = atomicAdd(&A.counters->n_overflow, og.size());
-            o = og.shfl(o, 0) + og.thread_rank();
-            if (o >= A.overflow_cap) return;  // the host sees n_overflow > overflow_cap, grows the pool and re-renders
-            idx = A.n_rows * A.n_tx * PM_TILE_SLOTS + o;
-            u64 prev = atomicExch(&A.ovf[tile], ((u64)A.stamp << 32) | (u64)(idx + 1u));
-            if ((uint32_t)(prev >> 32) == A.stamp) r.next = (uint32_t)prev;
+            // Records 16..63 of a tile go into its extension block: PM_EXT_BLOCK contiguous pool records,
+            // allocated by whoever claims position 16 and published in ovf[tile]; everybody else with a
+            // position beyond 15 waits for that word (the publisher is running: it cannot depend on a
+            // waiter).  The block's first record is a header whose `next` heads the chain of records 64...
+            const uint32_t ovf_region = A.n_rows * A.n_tx * PM_TILE_SLOTS;
+            uint32_t base1;  // 1 + pool index of the block header, or PM_EXT_FAILED
+            if (pos == PM_TILE_SLOTS) {
+                const uint32_t o = atomicAdd(&A.counters->n_overflow, (uint32_t)PM_EXT_BLOCK);
+                if (o + PM_EXT_BLOCK <= A.overflow_cap) {
+                    base1 = ovf_region + o + 1u;
+                    A.pool[base1 - 1u].next = 0;
+                    __threadfence();
+                } else {
+                    base1 = PM_EXT_FAILED;  // the host sees n_overflow > overflow_cap, grows the pool and re-renders
+                }
+                atomicExch(&A.ovf[tile], ((u64)A.stamp << 32) | (u64)base1);
+            } else {
+                volatile u64 *vw = &A.ovf[tile];
+                u64 v = *vw;
+                while ((uint32_t)(v >> 32) != A.stamp) { __nanosleep(40); v = *vw; }
+                base1 = (uint32_t)v;
+            }
+            if (base1 == PM_EXT_FAILED) return;
+            if (pos < PM_TILE_SLOTS + PM_EXT_SLOTS) {
+                idx = base1 + (pos - PM_TILE_SLOTS);
+            } else {
+                const uint32_t o = atomicAdd(&A.counters->n_overflow, 1u);
+                if (o >= A.overflow_cap) return;
+                idx = ovf_region + o;
+                r.next = atomicExch(&A.pool[base1 - 1u].next, idx + 1u);
+            }
         }
         uint4 *dst = reinterpret_cast<uint4 *>(&A.pool[idx]);
         const uint4 *src = reinterpret_cast<const uint4 *>(&r);

@@ -598,8 +598,13 @@ int pm_renderer_read_tile_items(pm_renderer *r, uint32_t *offsets, pm_tile_item 
             keyed.push_back({((uint64_t)q.item << 32) | q.key, idx});
         };
         for (uint32_t k = 0; k < std::min<uint32_t>(n, PM_TILE_SLOTS); k++) visit((uint32_t)(t * PM_TILE_SLOTS + k));
-        if (n > PM_TILE_SLOTS && (uint32_t)(ovf[t] >> 32) == stamp)
-            for (uint32_t cur = (uint32_t)ovf[t]; cur != 0; cur = rec[cur - 1].next) visit(cur - 1);
+        if (n > PM_TILE_SLOTS && (uint32_t)(ovf[t] >> 32) == stamp && (uint32_t)ovf[t] != PM_EXT_FAILED && (uint32_t)ovf[t] != 0) {
+            const uint32_t base1 = (uint32_t)ovf[t];  // 1 + index of the extension block's header
+            const uint32_t n_ext = std::min<uint32_t>(n, PM_TILE_SLOTS + PM_EXT_SLOTS) - PM_TILE_SLOTS;
+            for (uint32_t k = 0; k < n_ext && base1 + k < n_rec; k++) visit(base1 + k);
+            if (base1 - 1 < n_rec)
+                for (uint32_t cur = rec[base1 - 1].next; cur != 0 && cur - 1 < n_rec; cur = rec[cur - 1].next) visit(cur - 1);
+        }
         std::sort(keyed.begin(), keyed.end());
         auto push = [&](uint32_t item, int32_t backdrop, uint32_t effect) {
             if (items && total < cap_items) { items[total].item = item; items[total].backdrop = backdrop; items[total].effect = effect; }
