@@ -199,7 +199,7 @@ int run_plan(pm_renderer *r) {
         }
     }
     r->n_pieces = res.n_pieces;
-    if (getenv("PM_DEBUG_SEG")) {
+    if (getenv("PM_DEBUG_SEG") || getenv("PM_DEBUG_FINE")) {
         if (r->debug) cudaFree(r->debug);
         PM_CUDA(cudaMalloc(&r->debug, (size_t)(1u << 20) * 8));
         {
@@ -445,7 +445,7 @@ int pm_renderer_sync(pm_renderer *r, pm_frame_stats *stats) {
     const uint32_t retries_before = r->retries;
     st = finish_frames(r, false);
     if (st != PM_OK) return st;
-    if (r->debug) {
+    if (r->debug && getenv("PM_DEBUG_SEG")) {
         size_t nb = std::min<size_t>((size_t)r->n_pieces / 256 + 1, 1u << 19);
         std::vector<unsigned long long> d(2 * nb);
         cudaMemcpy(d.data(), r->debug, 2 * nb * 8, cudaMemcpyDeviceToHost);
@@ -625,6 +625,15 @@ int pm_renderer_read_tile_items(pm_renderer *r, uint32_t *offsets, pm_tile_item 
     offsets[n_tiles] = (uint32_t)total;
     if (n_items_out) *n_items_out = total;
     return (items && total > cap_items) ? PM_ERR_BUFFER_TOO_SMALL : PM_OK;
+}
+
+/* Debug builds only (PM_DEBUG_FINE=1 and a library built with -DPM_FINE_TIMELINE=1): copies the first
+ * n_words 64-bit words of the kernels' debug buffer.  Not declared in the public header. */
+int pm_debug_read(pm_renderer *r, unsigned long long *dst, size_t n_words) {
+    if (!r || !dst || !r->debug || n_words > (1u << 20)) return PM_ERR_STATE;
+    PM_CUDA(cudaStreamSynchronize(r->stream));
+    PM_CUDA(cudaMemcpy(dst, r->debug, n_words * 8, cudaMemcpyDeviceToHost));
+    return PM_OK;
 }
 
 int pm_host_alloc(void **out, size_t bytes) {
