@@ -21,7 +21,11 @@
 // extra warps give).  Measured and rejected on the 8192^2 tiger: 64 registers / 4 CTAs per SM (+15 %
 // time), an out-of-line copy of the tile code for heavy tiles (+10 %: they are the long pole, and the
 // call boundary spills), prefetching the solid batches' words as well (+3 %: code size), one work
-// counter instead of eight (the L2 atomic unit saturates: claims take microseconds).
+// counter instead of eight (the L2 atomic unit saturates: claims take microseconds), and for strokes a
+// first pass that finds, per (segment, pixel row), the pixels certainly inside the stroke analytically
+// so that the per-pixel distance work can skip them (+20 %: the sqrt and eight divisions of that test per
+// pair cost more than the pixels they save; a single warp runs ~0.1 instructions per cycle, so anything
+// that adds serial work to a tile with many segments lengthens the critical path).
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -46,9 +50,6 @@ typedef unsigned long long u64;
 #ifndef PM_FINE_BATCH_PIPELINE
 #define PM_FINE_BATCH_PIPELINE 0 // 1: cnt / occ words of the solid batches prefetched too (measured: the extra code costs more
 #endif                           //    in instruction-cache misses than the hidden latency gains; the solid warps are not critical)
-#ifndef PM_FINE_TIMELINE
-#define PM_FINE_TIMELINE 0       // 1 (debug builds, tools/fine_timeline.py): per-warp timestamps into PmFrameArgs::debug
-#endif
 #ifndef PM_FINE_EARLY_CLAIM
 #define PM_FINE_EARLY_CLAIM 0    // 1: the next-but-one tile is claimed at the start of a tile; 0: before the encode
 #endif
@@ -76,9 +77,6 @@ struct FineWarpSmem {
     uint32_t pad;
 };
 
-#if PM_FINE_TIMELINE
-__device__ __forceinline__ unsigned long long fine_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#endif
 __device__ __forceinline__ int fine_swz(int row, int j) { return row * 16 + (j ^ (((row >> 1) & 3) << 2)); }
 
 struct FineAcc {
@@ -167,31 +165,14 @@ __device__ __forceinline__ PmRecord load_record(const PmRecord *pool, uint32_t i
     return record_from(src[0], src[1]);
 }
 
-// position of the k-th (0-based) set bit of a 16-bit mask that has more than k bits set
-__device__ __forceinline__ int fine_nth_bit(uint32_t m, int k) {
-    int pos = 0;
-    int c = __popc(m & 0xffu);
-    if (k >= c) { k -= c; pos = 8; m >>= 8; }
-    c = __popc(m & 0xfu);
-    if (k >= c) { k -= c; pos += 4; m >>= 4; }
-    c = __popc(m & 0x3u);
-    if (k >= c) { k -= c; pos += 2; m >>= 2; }
-    return pos + ((k >= (int)(m & 1u)) ? 1 : 0);
-}
-
 // Phase A for up to 32 records held one per lane (`mine` = this lane holds a FILL*/LINE record of
 // the current item).  Two levels of work distribution, because both the rows a segment crosses and
 // the pixels of a row that need arithmetic vary from 0 to 16:
 //   level 1: the (record, pixel row) pairs are enumerated across the lanes; a lane computes the
-//            row-dependent part of its pair and the 16-bit mask of the pixels that need per-pixel
-//            work (fill: the pixels near the segment, after adding the row's cover delta; stroke:
-//            the pixels within reach of the segment that are not known to be fully inside);
+//            row-dependent part of its pair, adds the row's cover delta, and finds the pixel span
+//            that needs per-pixel work (fill: the pixels near the segment; stroke: the pixels
+//            within reach of it);
 //   level 2: those (pair, pixel) units are enumerated across the lanes again, one pixel per lane.
-// A stroke runs level 1 twice: the first pass only ORs, per pixel row, the pixels that are certainly
-// inside the stroke (pm_line_pair_inside: alpha exactly 1 whatever the other segments do) into the
-// row's word of the otherwise unused cover array, so that the second pass can drop them for every
-// segment -- with strokes ~40 px wide, a tile under a curve sees two dozen segments that all reach
-// all of its pixels, and almost all of those pixels are inside.
 // Owner lookup at both levels: exclusive prefix and payload packed into one word that is
 // monotone in the lane, binary search with shuffles.
 __device__ __forceinline__ void fine_pairs(FineWarpSmem *w, bool mine, uint32_t kind, float r_p0, float r_p1, float r_p2, float r_p3,
@@ -212,90 +193,86 @@ __device__ __forceinline__ void fine_pairs(FineWarpSmem *w, bool mine, uint32_t 
     const int key = ((incl - cnt) << 5) | ra;  // (pairs before this lane, first row)
     const int total = __shfl_sync(PM_FULL_MASK, incl, 31);
     #pragma unroll 1
-    for (int pass = stroke ? 0 : 1; pass < 2; pass++) {
-        #pragma unroll 1
-        for (int q = (int)lane; q - (int)lane < total; q += 32) {
-            // level 1: owner = last lane whose exclusive prefix is <= q
-            const int qk = (q << 5) | 31;
-            int lo = 0;
-            #pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-                const int v = __shfl_sync(PM_FULL_MASK, key, lo + step);
-                if (v <= qk) lo += step;
-            }
-            const int o_key = __shfl_sync(PM_FULL_MASK, key, lo);
-            float p[4];
-            p[0] = __shfl_sync(PM_FULL_MASK, r_p0, lo);
-            p[1] = __shfl_sync(PM_FULL_MASK, r_p1, lo);
-            p[2] = __shfl_sync(PM_FULL_MASK, r_p2, lo);
-            p[3] = __shfl_sync(PM_FULL_MASK, r_p3, lo);
-            const int row = (q < total) ? (o_key & 31) + (q - (o_key >> 5)) : 0;
-            if (pass == 0) {  // stroke, first pass: the pixels certainly inside
-                if (q < total) {
-                    int ia, ib;
-                    pm_line_pair_inside(p, reach - 0.5f, row, tile_x0, tile_y0, &ia, &ib);
-                    if (ia <= ib) atomicOr(reinterpret_cast<unsigned int *>(&w->cov[fine_swz(row, 0)]), (0xffffu >> (15 - ib)) & (0xffffu << ia));
-                }
-                continue;
-            }
-            // this lane's pair: m = pixels that need per-pixel work; d0..d5 = what a pixel of it needs
-            // (stroke: the segment; fill: sx, ex and the row's window / t)
-            uint32_t m = 0;
-            float d0 = p[0], d1 = p[1], d2 = p[2], d3 = p[3], d4 = 0.0f, d5 = 0.0f;
-            if (q < total) {
-                if (stroke) {
-                    int ja, jb;
-                    pm_line_pair_span(p, reach, row, tile_x0, tile_y0, &ja, &jb);
-                    if (ja <= jb) m = (0xffffu >> (15 - jb)) & (0xffffu << ja) & ~(uint32_t)w->cov[fine_swz(row, 0)];
-                } else {
-                    PmFillRow fr;
-                    int j_near, j_cover;
-                    if (pm_fill_pair_row(p, row, tile_x0, tile_y0, &fr, &j_near, &j_cover)) {
-                        if (j_cover < 16) acc.cover(row, j_cover, pm_to_fx(fr.wx - fr.wy));
-                        if (j_near < j_cover) m = (0xffffu >> (16 - j_cover)) & (0xffffu << j_near);
-                        d1 = p[2]; d2 = fr.wx; d3 = fr.wy; d4 = fr.tx; d5 = fr.ty;
-                    }
-                }
-            }
-            // level 2
-            const int npx = __popc(m);
-            int incl2 = npx;
-            #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int v = __shfl_up_sync(PM_FULL_MASK, incl2, o);
-                if (lane >= (uint32_t)o) incl2 += v;
-            }
-            const int key2 = ((incl2 - npx) << 20) | (row << 16) | (int)m;  // (pixels before this lane, row, pixel mask)
-            const int total2 = __shfl_sync(PM_FULL_MASK, incl2, 31);
-            #pragma unroll 1
-            for (int u = (int)lane; u - (int)lane < total2; u += 32) {
-                const int uk = (u << 20) | 0xfffff;
-                int lo2 = 0;
-                #pragma unroll
-                for (int step = 16; step > 0; step >>= 1) {
-                    const int v = __shfl_sync(PM_FULL_MASK, key2, lo2 + step);
-                    if (v <= uk) lo2 += step;
-                }
-                const int k2 = __shfl_sync(PM_FULL_MASK, key2, lo2);
-                const float e0 = __shfl_sync(PM_FULL_MASK, d0, lo2);
-                const float e1 = __shfl_sync(PM_FULL_MASK, d1, lo2);
-                const float e2 = __shfl_sync(PM_FULL_MASK, d2, lo2);
-                const float e3 = __shfl_sync(PM_FULL_MASK, d3, lo2);
-                const int prow = (k2 >> 16) & 15;
-                const int j = (u < total2) ? fine_nth_bit((uint32_t)k2 & 0xffffu, u - (k2 >> 20)) : 0;
-                if (stroke) {
-                    if (u < total2) acc.dist(prow, j, pm_px_line_dist(e0, e1, e2, e3, tile_x0 + (float)j, tile_y0 + (float)prow));
-                } else {
-                    PmFillRow fr;
-                    fr.wx = e2; fr.wy = e3;
-                    fr.tx = __shfl_sync(PM_FULL_MASK, d4, lo2);
-                    fr.ty = __shfl_sync(PM_FULL_MASK, d5, lo2);
-                    fr.active = true;
-                    if (u < total2) acc.near(prow, j, pm_fill_pair_px(e0, e1, tile_x0, j, fr));
+    for (int q = (int)lane; q - (int)lane < total; q += 32) {
+        // level 1: owner = last lane whose exclusive prefix is <= q
+        const int qk = (q << 5) | 31;
+        int lo = 0;
+        #pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int v = __shfl_sync(PM_FULL_MASK, key, lo + step);
+            if (v <= qk) lo += step;
+        }
+        const int o_key = __shfl_sync(PM_FULL_MASK, key, lo);
+        float p[4];
+        p[0] = __shfl_sync(PM_FULL_MASK, r_p0, lo);
+        p[1] = __shfl_sync(PM_FULL_MASK, r_p1, lo);
+        p[2] = __shfl_sync(PM_FULL_MASK, r_p2, lo);
+        p[3] = __shfl_sync(PM_FULL_MASK, r_p3, lo);
+#if PM_FINE_TWO_LEVEL
+        // this lane's pair: d0..d5 is what a pixel of it needs (stroke: the segment; fill: sx, ex and the row's window / t)
+        int row = 0, j0 = 0, npx = 0;
+        float d0 = p[0], d1 = p[1], d2 = p[2], d3 = p[3], d4 = 0.0f, d5 = 0.0f;
+        if (q < total) {
+            row = (o_key & 31) + (q - (o_key >> 5));
+            if (stroke) {
+                int ja, jb;
+                pm_line_pair_span(p, reach, row, tile_x0, tile_y0, &ja, &jb);
+                j0 = ja;
+                npx = jb >= ja ? jb - ja + 1 : 0;
+            } else {
+                PmFillRow fr;
+                int j_near, j_cover;
+                if (pm_fill_pair_row(p, row, tile_x0, tile_y0, &fr, &j_near, &j_cover)) {
+                    if (j_cover < 16) acc.cover(row, j_cover, pm_to_fx(fr.wx - fr.wy));
+                    j0 = j_near;
+                    npx = j_cover - j_near;
+                    d1 = p[2]; d2 = fr.wx; d3 = fr.wy; d4 = fr.tx; d5 = fr.ty;
                 }
             }
         }
-        __syncwarp();  // (stroke: the inside masks of the first pass are complete before the second reads them)
+        // level 2
+        int incl2 = npx;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(PM_FULL_MASK, incl2, o);
+            if (lane >= (uint32_t)o) incl2 += v;
+        }
+        const int key2 = ((incl2 - npx) << 9) | (row << 5) | j0;  // (pixels before this lane, row, first pixel)
+        const int total2 = __shfl_sync(PM_FULL_MASK, incl2, 31);
+        #pragma unroll 1
+        for (int u = (int)lane; u - (int)lane < total2; u += 32) {
+            const int uk = (u << 9) | 511;
+            int lo2 = 0;
+            #pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int v = __shfl_sync(PM_FULL_MASK, key2, lo2 + step);
+                if (v <= uk) lo2 += step;
+            }
+            const int k2 = __shfl_sync(PM_FULL_MASK, key2, lo2);
+            const float e0 = __shfl_sync(PM_FULL_MASK, d0, lo2);
+            const float e1 = __shfl_sync(PM_FULL_MASK, d1, lo2);
+            const float e2 = __shfl_sync(PM_FULL_MASK, d2, lo2);
+            const float e3 = __shfl_sync(PM_FULL_MASK, d3, lo2);
+            const int prow = (k2 >> 5) & 15;
+            const int j = (k2 & 31) + (u - (k2 >> 9));
+            if (stroke) {
+                if (u < total2) acc.dist(prow, j, pm_px_line_dist(e0, e1, e2, e3, tile_x0 + (float)j, tile_y0 + (float)prow));
+            } else {
+                PmFillRow fr;
+                fr.wx = e2; fr.wy = e3;
+                fr.tx = __shfl_sync(PM_FULL_MASK, d4, lo2);
+                fr.ty = __shfl_sync(PM_FULL_MASK, d5, lo2);
+                fr.active = true;
+                if (u < total2) acc.near(prow, j, pm_fill_pair_px(e0, e1, tile_x0, j, fr));
+            }
+        }
+#else
+        if (q < total) {
+            const int row = (o_key & 31) + (q - (o_key >> 5));
+            if (stroke) pm_line_pair(acc, p, reach, row, tile_x0, tile_y0);
+            else pm_fill_pair(acc, p, row, tile_x0, tile_y0);
+        }
+#endif
     }
     // FillEdge commands: one record at a time, lanes 0..15 take the 16 pixel rows
     if (!stroke) {
@@ -580,7 +557,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
         float fg[4] = {0.0f, 0.0f, 0.0f, 1.0f};  // Cmd_Circle paints black (metal:491)
         const bool stroke = t_kind == PM_REC_STROKE, fill = t_kind == PM_REC_DRAWFILL;
         const float half_width = pm_u2f(t_w0);
-        int run = 0;  // fill: cover entering this lane's pixels from the left; stroke: this lane's 8 "inside" bits
+        int run = 0;  // fill: cover entering this lane's pixels from the left
         if (t_kind != PM_REC_CIRCLE) unpack_fg(lut, t_w1, fg);
         if (fill || stroke) {
             const float reach = half_width + 0.5f;
@@ -614,12 +591,6 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
                 }
             }
             __syncwarp();
-            if (stroke) {  // the row's "certainly inside" pixels (fine_pairs), cleared for the next item
-                const uint32_t msk = (uint32_t)w->cov[fine_swz((int)prow, 0)];
-                __syncwarp();
-                if (half == 0) w->cov[fine_swz((int)prow, 0)] = 0;
-                run = (int)((msk >> (8u * half)) & 0xffu);
-            }
             if (fill) {  // covers of the left half of the pixel row carry into the right half
                 const int4 c0 = *reinterpret_cast<const int4 *>(&w->cov[my_off0]), c1 = *reinterpret_cast<const int4 *>(&w->cov[my_off1]);
                 const int sum = ((c0.x + c0.y) + (c0.z + c0.w)) + ((c1.x + c1.y) + (c1.z + c1.w));
@@ -647,11 +618,10 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
                     run += c.w; al[3] = pm_resolve_fill_alpha(a.w + run, backdrop);
                 } else {  // renderDf, metal:58-60
                     const float lim = half_width + 0.5f;
-                    const int in4 = run >> (4 * g);
-                    al[0] = (in4 & 1) ? 1.0f : (a.x ? pm_saturate(lim - __uint_as_float(~(uint32_t)a.x)) : 0.0f);
-                    al[1] = (in4 & 2) ? 1.0f : (a.y ? pm_saturate(lim - __uint_as_float(~(uint32_t)a.y)) : 0.0f);
-                    al[2] = (in4 & 4) ? 1.0f : (a.z ? pm_saturate(lim - __uint_as_float(~(uint32_t)a.z)) : 0.0f);
-                    al[3] = (in4 & 8) ? 1.0f : (a.w ? pm_saturate(lim - __uint_as_float(~(uint32_t)a.w)) : 0.0f);
+                    al[0] = a.x ? pm_saturate(lim - __uint_as_float(~(uint32_t)a.x)) : 0.0f;
+                    al[1] = a.y ? pm_saturate(lim - __uint_as_float(~(uint32_t)a.y)) : 0.0f;
+                    al[2] = a.z ? pm_saturate(lim - __uint_as_float(~(uint32_t)a.z)) : 0.0f;
+                    al[3] = a.w ? pm_saturate(lim - __uint_as_float(~(uint32_t)a.w)) : 0.0f;
                 }
             } else if (t_kind == PM_REC_CIRCLE) {
                 const float px0 = tile_x0 + (float)(half * 8u + 4u * (uint32_t)g), py = tile_y0 + (float)prow;
@@ -796,11 +766,6 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArg
     const bool prefer_complex = (warp & 3u) != 3u;
     uint32_t p = 0;
     bool started = false;
-#if PM_FINE_TIMELINE
-    const unsigned long long tl_begin = fine_now();
-    unsigned long long tl_last = tl_begin, tl_long = 0;
-    uint32_t tl_tiles = 0, tl_long_pk = 0;
-#endif
 #if PM_FINE_BATCH_PIPELINE
     uint32_t b_cur = 0, b_next = 0, bp = 0;
     bool b_started = false;
@@ -820,19 +785,7 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArg
                 fine_prefetch(A, w, p, w->pkq[p], lane);
                 fine_entry(A, fine_claim(A, w, lane), w, p ^ 1u, n_heavy, n_total);
             }
-#if PM_FINE_TIMELINE
-            const unsigned long long tl0 = fine_now();
-            const uint32_t tl_pk = w->pkq[p];
-#endif
             fine_complex_tile<F32, EXACT>(A, w, p, lane, n_heavy, n_total);
-#if PM_FINE_TIMELINE
-            {
-                const unsigned long long tl1 = fine_now();
-                tl_tiles++;
-                tl_last = tl1;
-                if (tl1 - tl0 > tl_long) { tl_long = tl1 - tl0; tl_long_pk = tl_pk; }
-            }
-#endif
             p ^= 1u;
             if (!(w->st & FINE_ST_VALID(p))) complex_left = false;
         } else {
@@ -866,12 +819,6 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArg
 #endif
         }
     }
-#if PM_FINE_TIMELINE
-    if (A.debug && lane == 0) {  // per warp: begin, end of its last tile with records, end, tiles | longest tile (ns << 32 | packed tile)
-        unsigned long long *d = A.debug + (size_t)(blockIdx.x * PM_FINE_WARPS + warp) * 5;
-        d[0] = tl_begin; d[1] = tl_last; d[2] = fine_now(); d[3] = tl_tiles; d[4] = (tl_long << 32) | tl_long_pk;
-    }
-#endif
 }
 
 }  // namespace

@@ -52,7 +52,6 @@ struct TileAcc {
     void near(int row, int j, int fx) { acc[row][j] += fx; }
     void cover(int row, int j, int fx) { cov[row][j] += fx; }
     void dist(int row, int j, float d) { dmin[row][j] = fminf(dmin[row][j], d); }
-    void inside(int row, int ia, int ib) { for (int j = ia; j <= ib; j++) dmin[row][j] = 0.0f; }
     void clear_fill() { memset(acc, 0, sizeof acc); memset(cov, 0, sizeof cov); }
     void clear_dist() { for (auto &r : dmin) for (float &v : r) v = 1e9f; }
 };
@@ -312,7 +311,6 @@ extern "C" int pmh_stats(const uint8_t *scene, uint32_t width, uint32_t height, 
         void near(int, int, int) { n_near++; }
         void cover(int, int, int) { n_cover++; }
         void dist(int, int, float) { n_dist++; }
-        void inside(int, int, int) {}
     };
     for (uint32_t r = 0; r < tile_y1 - tile_y0; r++)
         for (uint32_t tx = 0; tx < n_tx; tx++) {
