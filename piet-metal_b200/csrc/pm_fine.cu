@@ -50,6 +50,9 @@ typedef unsigned long long u64;
 #ifndef PM_FINE_BATCH_PIPELINE
 #define PM_FINE_BATCH_PIPELINE 0 // 1: cnt / occ words of the solid batches prefetched too (measured: the extra code costs more
 #endif                           //    in instruction-cache misses than the hidden latency gains; the solid warps are not critical)
+#ifndef PM_FINE_TIMELINE
+#define PM_FINE_TIMELINE 0       // 1 (debug builds, tools/fine_timeline.py): per-warp timestamps into PmFrameArgs::debug
+#endif
 #ifndef PM_FINE_EARLY_CLAIM
 #define PM_FINE_EARLY_CLAIM 0    // 1: the next-but-one tile is claimed at the start of a tile; 0: before the encode
 #endif
@@ -77,6 +80,9 @@ struct FineWarpSmem {
     uint32_t pad;
 };
 
+#if PM_FINE_TIMELINE
+__device__ __forceinline__ unsigned long long fine_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 __device__ __forceinline__ int fine_swz(int row, int j) { return row * 16 + (j ^ (((row >> 1) & 3) << 2)); }
 
 struct FineAcc {
@@ -766,6 +772,11 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArg
     const bool prefer_complex = (warp & 3u) != 3u;
     uint32_t p = 0;
     bool started = false;
+#if PM_FINE_TIMELINE
+    const unsigned long long tl_begin = fine_now();
+    unsigned long long tl_last = tl_begin, tl_long = 0;
+    uint32_t tl_tiles = 0, tl_long_pk = 0;
+#endif
 #if PM_FINE_BATCH_PIPELINE
     uint32_t b_cur = 0, b_next = 0, bp = 0;
     bool b_started = false;
@@ -785,7 +796,19 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArg
                 fine_prefetch(A, w, p, w->pkq[p], lane);
                 fine_entry(A, fine_claim(A, w, lane), w, p ^ 1u, n_heavy, n_total);
             }
+#if PM_FINE_TIMELINE
+            const unsigned long long tl0 = fine_now();
+            const uint32_t tl_pk = w->pkq[p];
+#endif
             fine_complex_tile<F32, EXACT>(A, w, p, lane, n_heavy, n_total);
+#if PM_FINE_TIMELINE
+            {
+                const unsigned long long tl1 = fine_now();
+                tl_tiles++;
+                tl_last = tl1;
+                if (tl1 - tl0 > tl_long) { tl_long = tl1 - tl0; tl_long_pk = tl_pk; }
+            }
+#endif
             p ^= 1u;
             if (!(w->st & FINE_ST_VALID(p))) complex_left = false;
         } else {
@@ -819,6 +842,12 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArg
 #endif
         }
     }
+#if PM_FINE_TIMELINE
+    if (A.debug && lane == 0) {  // per warp: begin, end of its last tile with records, end, tiles | longest tile (ns << 32 | packed tile)
+        unsigned long long *d = A.debug + (size_t)(blockIdx.x * PM_FINE_WARPS + warp) * 5;
+        d[0] = tl_begin; d[1] = tl_last; d[2] = fine_now(); d[3] = tl_tiles; d[4] = (tl_long << 32) | tl_long_pk;
+    }
+#endif
 }
 
 }  // namespace
