@@ -81,6 +81,11 @@ struct FineWarpSmem {
 };
 
 #if PM_FINE_TIMELINE
+#define TL_MARK(k) do { const unsigned long long tl_t = fine_now(); tl_acc[(heavy ? 8 : 0) + (k)] += tl_t - tl_prev; tl_prev = tl_t; } while (0)
+#else
+#define TL_MARK(k) do { } while (0)
+#endif
+#if PM_FINE_TIMELINE
 __device__ __forceinline__ unsigned long long fine_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
 __device__ __forceinline__ int fine_swz(int row, int j) { return row * 16 + (j ^ (((row >> 1) & 3) << 2)); }
@@ -385,7 +390,14 @@ __device__ __forceinline__ void fine_step3(const PmFrameArgs &A, uint32_t claim,
 // execute this together.  Records are handled in chunks of 32, one per lane; chunk 0 is the inline
 // slots.  Pixel layout: lane l owns pixel row (l >> 1), pixels 8*(l & 1) .. +7.
 template <bool F32, bool EXACT>
-__device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarpSmem *w, uint32_t p, uint32_t lane, uint32_t n_heavy, uint32_t n_total) {
+__device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarpSmem *w, uint32_t p, uint32_t lane, uint32_t n_heavy, uint32_t n_total
+#if PM_FINE_TIMELINE
+                                                  , unsigned long long *tl_acc
+#endif
+                                                  ) {
+#if PM_FINE_TIMELINE
+    unsigned long long tl_prev = fine_now();
+#endif
     cp_async_wait_all();
     __syncwarp();
     const uint32_t packed_tile = w->pkq[p];
@@ -400,6 +412,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
     const uint32_t occ_item1 = (uint32_t)(ow >> 32) == A.stamp ? (uint32_t)ow : 0u;
     const bool heavy = n > PM_TILE_SLOTS;
     if (heavy && skip_heavy) {  // pass 1 rendered it
+        TL_MARK(6);
         fine_step1(A, w, p, lane);
 #if PM_FINE_EARLY_CLAIM
         fine_step3(A, claim, w, p, n_heavy, n_total);
@@ -472,6 +485,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
                      (tx * PM_TILE_W + half * 8u);
 
     if (!has_draw) {
+        TL_MARK(6);
         // Only Solid commands after the last rewind: the tile Bails and shows solidColor (metal:145-147, :34-44)
         const uint32_t c = occ_rgba;
         const uint4 v = make_uint4(c, c, c, c);
@@ -511,6 +525,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
     // this lane's two 4-pixel groups of the coverage arrays (word offsets; cov = acc + 256)
     const int my_off0 = fine_swz((int)prow, (int)half * 8), my_off1 = fine_swz((int)prow, (int)half * 8 + 4);
 
+    TL_MARK(0);
     // items in painter's order: repeatedly take the smallest item id above the last one done
     uint32_t last_item = 0;
     bool first = true;
@@ -560,6 +575,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
             }
         }
 
+        TL_MARK(1);
         float fg[4] = {0.0f, 0.0f, 0.0f, 1.0f};  // Cmd_Circle paints black (metal:491)
         const bool stroke = t_kind == PM_REC_STROKE, fill = t_kind == PM_REC_DRAWFILL;
         const float half_width = pm_u2f(t_w0);
@@ -576,6 +592,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
                                tile_x0, tile_y0, lane);
                 }
             }
+            TL_MARK(stroke ? 2 : 7);
             if (heavy) {
                 for (uint32_t c = 1; c < n_chunks; c++) {
                     const uint32_t i = (c - 1u) * 32u + lane;
@@ -597,6 +614,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
                 }
             }
             __syncwarp();
+            TL_MARK(3);
             if (fill) {  // covers of the left half of the pixel row carry into the right half
                 const int4 c0 = *reinterpret_cast<const int4 *>(&w->cov[my_off0]), c1 = *reinterpret_cast<const int4 *>(&w->cov[my_off1]);
                 const int sum = ((c0.x + c0.y) + (c0.z + c0.w)) + ((c1.x + c1.y) + (c1.z + c1.w));
@@ -649,6 +667,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
             }
         }
         __syncwarp();
+        TL_MARK(4);
     }
 
     // the position after the next tile is claimed here and looked up after the encode: the claim's result
@@ -676,6 +695,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
 #if !PM_FINE_EARLY_CLAIM
     fine_step3(A, claim, w, p, n_heavy, n_total);
 #endif
+    TL_MARK(5);
 }
 
 __device__ __forceinline__ uint32_t fine_batch_claim(const PmFrameArgs &A, uint32_t lane) {
@@ -776,6 +796,8 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArg
     const unsigned long long tl_begin = fine_now();
     unsigned long long tl_last = tl_begin, tl_long = 0;
     uint32_t tl_tiles = 0, tl_long_pk = 0;
+    unsigned long long tl_acc[16];
+    for (int k = 0; k < 16; k++) tl_acc[k] = 0;
 #endif
 #if PM_FINE_BATCH_PIPELINE
     uint32_t b_cur = 0, b_next = 0, bp = 0;
@@ -800,7 +822,11 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArg
             const unsigned long long tl0 = fine_now();
             const uint32_t tl_pk = w->pkq[p];
 #endif
+#if PM_FINE_TIMELINE
+            fine_complex_tile<F32, EXACT>(A, w, p, lane, n_heavy, n_total, tl_acc);
+#else
             fine_complex_tile<F32, EXACT>(A, w, p, lane, n_heavy, n_total);
+#endif
 #if PM_FINE_TIMELINE
             {
                 const unsigned long long tl1 = fine_now();
@@ -844,8 +870,9 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArg
     }
 #if PM_FINE_TIMELINE
     if (A.debug && lane == 0) {  // per warp: begin, end of its last tile with records, end, tiles | longest tile (ns << 32 | packed tile)
-        unsigned long long *d = A.debug + (size_t)(blockIdx.x * PM_FINE_WARPS + warp) * 5;
+        unsigned long long *d = A.debug + (size_t)(blockIdx.x * PM_FINE_WARPS + warp) * 24;
         d[0] = tl_begin; d[1] = tl_last; d[2] = fine_now(); d[3] = tl_tiles; d[4] = (tl_long << 32) | tl_long_pk;
+        for (int k = 0; k < 16; k++) d[8 + k] = tl_acc[k];
     }
 #endif
 }

@@ -21,10 +21,10 @@ for _ in range(5):
 st = r.sync()
 lib = pm._lib()
 n_warps = 148 * 4 * 8
-buf = np.zeros(n_warps * 5, np.uint64)
+buf = np.zeros(n_warps * 24, np.uint64)
 lib.pm_debug_read.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
 assert lib.pm_debug_read(r._h, buf.ctypes.data_as(ctypes.c_void_p), buf.size) == 0
-d = buf.reshape(n_warps, 5).astype(np.int64)
+d = buf.reshape(n_warps, 24).astype(np.int64)
 t0 = d[:, 0].min()
 beg, lastc, end, tiles = (d[:, 0] - t0) / 1e3, (d[:, 1] - t0) / 1e3, (d[:, 2] - t0) / 1e3, d[:, 3]
 longest, lpk = (d[:, 4] >> 32) / 1e3, d[:, 4] & 0xffffffff
@@ -37,3 +37,11 @@ order = np.argsort(-longest)[:8]
 for k in order:
     print("  longest tile of warp %5d: %.1f us  tile row %d col %d (ended at %.1f us, %d tiles)" % (k, longest[k], (lpk[k] >> 16), lpk[k] & 0xffff, lastc[k], tiles[k]))
 print("sum of per-warp busy-with-complex estimates: longest-tile median %.2f us" % np.median(longest[tiles > 0]))
+names = ["set-up", "item select", "phase A stroke (inline chunk)", "phase A overflow chunks", "resolve+blend", "encode+store", "no-draw/skipped", "phase A fill (inline chunk)"]
+acc = d[:, 8:24].sum(axis=0) / 1e3
+tot = acc.sum()
+print("time by phase, summed over warps (us, %% of %.0f):" % tot)
+for h in (0, 1):
+    for k, nme in enumerate(names):
+        v = acc[8 * h + k]
+        if v > 0: print("  %-6s %-32s %9.0f  %5.1f%%" % ("heavy" if h else "light", nme, v, 100 * v / tot))
