@@ -364,3 +364,51 @@ extern "C" int pmh_stats(const uint8_t *scene, uint32_t width, uint32_t height, 
         }
     return 0;
 }
+
+// Per-tile workload of one tile row (tools): for each tile of row `ty`: records, items, fill pairs, fill near
+// pixels, line pairs, line pixels, LINE records, FILL records.  out has 8 * n_tx entries.
+extern "C" int pmh_row_stats(const uint8_t *scene, uint32_t width, uint32_t height, uint32_t ty, uint64_t *out) {
+    const uint32_t n_tx = (width + 15) / 16;
+    (void)height;
+    auto tiles = bin_scene(scene, n_tx, ty, ty + 1, false);
+    struct AccCount {
+        uint64_t n_near = 0, n_cover = 0, n_dist = 0;
+        void near(int, int, int) { n_near++; }
+        void cover(int, int, int) { n_cover++; }
+        void dist(int, int, float) { n_dist++; }
+    };
+    for (uint32_t tx = 0; tx < n_tx; tx++) {
+        TileBin &tb = tiles[0][tx];
+        uint64_t *o = out + 8 * (size_t)tx;
+        const uint32_t occ_item1 = (uint32_t)(tb.occ_color >> 32);
+        std::vector<PmRecord> recs;
+        for (const PmRecord &q : tb.recs) if (q.item >= occ_item1) recs.push_back(q);
+        std::sort(recs.begin(), recs.end(), [](const PmRecord &a, const PmRecord &b) {
+            return (((uint64_t)a.item << 32) | a.key) < (((uint64_t)b.item << 32) | b.key);
+        });
+        o[0] = tb.recs.size();
+        const float tile_x0 = (float)(tx * 16), ty0 = (float)(ty * 16);
+        for (size_t j0 = 0; j0 < recs.size();) {
+            size_t j1 = j0 + 1;
+            while (j1 < recs.size() && recs[j1].item == recs[j0].item) j1++;
+            o[1]++;
+            const PmRecord &last = recs[j1 - 1];
+            const uint32_t kind = last.key & 15u;
+            for (size_t j = j0; j + 1 < j1; j++) {
+                const PmRecord &q = recs[j];
+                int ra, rb;
+                if (kind == PM_REC_DRAWFILL) {
+                    o[7]++;
+                    pm_fill_rows(q.p[1], q.p[3], ty0, &ra, &rb);
+                    for (int row = ra; row <= rb; row++) { AccCount c; pm_fill_pair(c, q.p, row, tile_x0, ty0); o[2]++; o[3] += c.n_near; }
+                } else if (kind == PM_REC_STROKE) {
+                    o[6]++;
+                    pm_line_rows(q.p[1], q.p[3], last.p[0] + 0.5f, ty0, &ra, &rb);
+                    for (int row = ra; row <= rb; row++) { AccCount c; pm_line_pair(c, q.p, last.p[0] + 0.5f, row, tile_x0, ty0); o[4]++; o[5] += c.n_dist; }
+                }
+            }
+            j0 = j1;
+        }
+    }
+    return 0;
+}
