@@ -183,6 +183,11 @@ int pm_renderer_set_scene_device(pm_renderer *r, const void *scene_dev, size_t l
 
 /* Enqueue one frame on the renderer's stream (asynchronous, like drawInMTKView's commit). */
 int pm_renderer_render(pm_renderer *r);
+/* Per-frame CUDA events (the ms_* fields of pm_frame_stats) are recorded by default.  With them disabled the
+ * three kernels of a frame, and consecutive frames, are chained by programmatic dependent launch: each kernel's
+ * launch and prologue overlap the tail of the one before it, like the reference's back-to-back command buffers
+ * (TestApp/PietRenderer.m:59-103 commits and never waits).  pm_frame_stats then reports frames = 0 and no times. */
+int pm_renderer_set_frame_events(pm_renderer *r, int enabled);
 /* Wait for the stream; report the last frame's statistics (stats may be NULL). */
 int pm_renderer_sync(pm_renderer *r, pm_frame_stats *stats);
 /* Copy the strip's pixels to host memory: rows [16*tile_y0, min(16*tile_y1, height)),

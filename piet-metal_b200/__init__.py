@@ -68,7 +68,7 @@ EXPORTS = [
     "pm_scene_row_costs", "pm_balance_strips",
     "pm_scene_row_costs", "pm_balance_strips",
     "pm_renderer_create", "pm_renderer_destroy", "pm_renderer_resize", "pm_renderer_set_strip",
-    "pm_renderer_set_scene", "pm_renderer_set_scene_device", "pm_renderer_render", "pm_renderer_sync",
+    "pm_renderer_set_scene", "pm_renderer_set_scene_device", "pm_renderer_render", "pm_renderer_set_frame_events", "pm_renderer_sync",
     "pm_renderer_read_rgba8", "pm_renderer_render_host", "pm_renderer_framebuffer", "pm_renderer_stream",
     "pm_renderer_read_rgba32f", "pm_renderer_read_tile_items", "pm_host_alloc", "pm_host_free",
 ]
@@ -114,6 +114,7 @@ def _lib():
         "pm_renderer_set_scene": (cint, [vp, vp, sz]),
         "pm_renderer_set_scene_device": (cint, [vp, vp, sz]),
         "pm_renderer_render": (cint, [vp]),
+        "pm_renderer_set_frame_events": (cint, [vp, cint]),
         "pm_renderer_sync": (cint, [vp, ctypes.POINTER(FrameStats)]),
         "pm_renderer_read_rgba8": (cint, [vp, vp, sz]),
         "pm_renderer_render_host": (cint, [vp, vp, sz, vp, sz, ctypes.POINTER(FrameStats)]),
@@ -297,6 +298,10 @@ class PietRenderer:
         _check(_lib().pm_renderer_render(self._h), "pm_renderer_render")
 
     render = draw
+
+    def set_frame_events(self, enabled):
+        """Per-frame CUDA events on/off (off: the frame's kernels overlap their launches; no per-frame times)."""
+        _check(_lib().pm_renderer_set_frame_events(self._h, 1 if enabled else 0), "pm_renderer_set_frame_events")
 
     def sync(self):
         st = FrameStats()

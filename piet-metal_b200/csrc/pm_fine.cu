@@ -774,6 +774,8 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArg
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FineWarpSmem *w = reinterpret_cast<FineWarpSmem *>(s_raw) + warp;
     for (uint32_t i = lane; i < 256; i += 32) { w->acc[i] = 0; w->cov[i] = 0; }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // (programmatic dependent launch, see pm_kernels.cu)
+    asm volatile("griddepcontrol.wait;" ::: "memory");               // binning has finished
     const uint32_t n_complex = A.counters->n_complex, n_heavy = A.counters->n_heavy;
     const uint32_t n_total = n_complex + n_heavy;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -898,16 +900,26 @@ int pm_fine_setup(void) {
     return 0;
 }
 
-void pm_launch_fine(const PmFrameArgs &a, int sm_count, cudaStream_t s) {
+template <bool F32, bool EXACT>
+static void fine_launch(const PmFrameArgs &a, int grid, bool overlap, cudaStream_t s) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PM_FINE_WARPS * 32); cfg.dynamicSmemBytes = PM_FINE_SMEM; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = overlap ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k_fine<F32, EXACT>, a);
+}
+
+void pm_launch_fine(const PmFrameArgs &a, int sm_count, bool overlap, cudaStream_t s) {
     // persistent: enough CTAs to fill every SM, work pulled from two queues
     const int grid = sm_count * 4;
-    const size_t smem = PM_FINE_SMEM;
     const bool exact = (a.flags & PM_FLAG_EXACT_SRGB) != 0;
     if (a.fb32) {  // debug render with the fp32 parity buffer
-        if (exact) k_fine<true, true><<<grid, PM_FINE_WARPS * 32, smem, s>>>(a);
-        else       k_fine<true, false><<<grid, PM_FINE_WARPS * 32, smem, s>>>(a);
+        if (exact) fine_launch<true, true>(a, grid, overlap, s);
+        else       fine_launch<true, false>(a, grid, overlap, s);
     } else {
-        if (exact) k_fine<false, true><<<grid, PM_FINE_WARPS * 32, smem, s>>>(a);
-        else       k_fine<false, false><<<grid, PM_FINE_WARPS * 32, smem, s>>>(a);
+        if (exact) fine_launch<false, true>(a, grid, overlap, s);
+        else       fine_launch<false, false>(a, grid, overlap, s);
     }
 }

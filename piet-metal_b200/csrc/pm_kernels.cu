@@ -20,6 +20,13 @@
 
 namespace cg = cooperative_groups;
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the attribute may start while its
+// predecessor in the stream is still draining; pm_grid_wait() blocks until the predecessor has completed
+// and its writes are visible, pm_grid_launch_dependents() lets the successor's CTAs be scheduled as this
+// grid's CTAs retire.  Both are no-ops for a normal launch.
+__device__ __forceinline__ void pm_grid_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pm_grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 namespace {
 
 __device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
@@ -385,6 +392,13 @@ __global__ void __launch_bounds__(256) k_seg(const PmFrameArgs A) {
         __device__ Timer(const PmFrameArgs &a) : A(a) { if (A.debug) atomicMin(&A.debug[2 * blockIdx.x], now()); }
         __device__ ~Timer() { if (A.debug) atomicMax(&A.debug[2 * blockIdx.x + 1], now()); }
     } timer(A);
+    pm_grid_launch_dependents();
+    pm_grid_wait();  // the previous frame's fill kernel is done with the queues, the lists and the scratch
+    {   // the backdrop scratch the NEXT frame will use (last touched by the frame before this one): no memset in the frame
+        uint4 *z = reinterpret_cast<uint4 *>(A.bd_next);
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < A.bd_quads; i += (unsigned long long)gridDim.x * blockDim.x)
+            z[i] = make_uint4(0, 0, 0, 0);
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         A.queue->batch_next = 0;
         for (int s = 0; s < PM_FINE_SUBQ; s++) A.queue->sub[s][0] = 0;
@@ -413,11 +427,13 @@ __global__ void __launch_bounds__(256) k_seg(const PmFrameArgs A) {
 // One warp per (item, tile row, chunk of 32 tiles): closes what k_seg accumulated -- DrawFill /
 // Solid / opaque cover per tile of a Fill item (metal:359-363), Stroke per tile of a Poly item
 // (metal:441-443).  Line and Circle items have no segments and are binned here directly
-// (metal:218-247).  The scratch is cleared by a memset at the start of the next frame.
+// (metal:218-247).  The scratch alternates between two buffers; k_seg clears the one the next frame will use.
 #define PM_ROW_WARPS 8
 __global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t unit = blockIdx.x * PM_ROW_WARPS + warp;
+    pm_grid_launch_dependents();
+    pm_grid_wait();  // k_seg has finished
     if (unit >= A.n_row_units) return;
     const uint2 ri = A.row_info[unit];  // (item, tile row << 16 | chunk), tabulated by k_plan
     const uint32_t item = ri.x;
@@ -501,11 +517,24 @@ void pm_launch_plan_pieces(const uint8_t *scene, uint32_t n_items, uint32_t item
     k_plan_pieces<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, n_segments, seg_info, piece_info, piece_cap, result);
 }
 
-void pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, cudaStream_t s) {
+template <class K>
+static void launch_overlapped(K kernel, dim3 grid, dim3 block, bool overlap, cudaStream_t s, const PmFrameArgs &a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = overlap ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
+void pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, bool overlap, cudaStream_t s) {
     uint32_t grid_seg = (a.n_pieces + 255u) / 256u;
     if (grid_seg == 0) grid_seg = 1;  // still clears the fill kernel's queues
-    k_seg<<<grid_seg, 256, 0, s>>>(a);
-    if (a.n_row_units) k_row<<<(a.n_row_units + PM_ROW_WARPS - 1) / PM_ROW_WARPS, PM_ROW_WARPS * 32, 0, s>>>(a);
+    launch_overlapped(k_seg, dim3(grid_seg), dim3(256), overlap, s, a);
+    // (k_row runs even without units when the launches overlap: the chain of grid dependencies must not skip a kernel)
+    if (a.n_row_units || overlap)
+        launch_overlapped(k_row, dim3((a.n_row_units + PM_ROW_WARPS - 1) / PM_ROW_WARPS > 0 ? (a.n_row_units + PM_ROW_WARPS - 1) / PM_ROW_WARPS : 1), dim3(PM_ROW_WARPS * 32), overlap, s, a);
     if (mid) cudaEventRecord(mid, s);
-    pm_launch_fine(a, sm_count, s);
+    pm_launch_fine(a, sm_count, overlap, s);
 }

@@ -50,7 +50,9 @@ struct PmFrameArgs {
     uint32_t n_segments;        // segments of the Fill / Poly items that touch the strip
     uint32_t n_pieces;          // k_seg threads
     uint32_t n_row_units;       // k_row warps: (item, tile row) pairs inside the strip
-    uint32_t *bd;               // backdrop scratch, all zero between frames
+    uint32_t *bd;               // backdrop scratch of this frame, all zero when the frame starts
+    uint32_t *bd_next;          // the next frame's (the two alternate); k_seg clears it
+    unsigned long long bd_quads; // size of each in 16-byte units
     uint32_t tile_y0;           // first tile row of the strip
     uint32_t n_rows;            // tile rows in the strip
     uint32_t n_tx;              // tiles per row
@@ -87,8 +89,10 @@ void pm_launch_plan_pieces(const uint8_t *scene, uint32_t n_items, uint32_t item
                            const unsigned long long *plan_a, uint32_t n_segments, PmSegInfo *seg_info, uint2 *piece_info,
                            uint32_t piece_cap, PmPlanResult *result, cudaStream_t s);
 // One frame: binning (k_seg, k_row) then fill/blend (k_fine).  `mid` (optional) is recorded before k_fine.
-void pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, cudaStream_t s);
+// `overlap`: programmatic dependent launch between the frame's kernels and from one frame to the next (no event
+// may sit between them, so `mid` must be null).
+void pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, bool overlap, cudaStream_t s);
 // The fill/blend kernel alone (pm_fine.cu), and its one-time set-up on the current device
 // (shared-memory attributes of the kernel).
-void pm_launch_fine(const PmFrameArgs &a, int sm_count, cudaStream_t s);
+void pm_launch_fine(const PmFrameArgs &a, int sm_count, bool overlap, cudaStream_t s);
 int pm_fine_setup(void);

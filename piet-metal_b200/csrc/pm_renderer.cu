@@ -64,6 +64,7 @@ struct pm_renderer {
     unsigned long long *debug = nullptr;
     size_t bd_cap = 0, bd_words = 0;
     bool have_scene = false, plan_dirty = true;
+    bool frame_events = true;   // per-frame CUDA events (pm_frame_stats); off: the frame's kernels overlap their launches
     uint32_t *dev_err = nullptr;
     PmPlanResult *dev_plan = nullptr;
 
@@ -209,14 +210,15 @@ int run_plan(pm_renderer *r) {
         }
     }
     r->n_row_units = res.n_rows;
-    const size_t want = (size_t)res.bd_words + 1;
+    const size_t want = (((size_t)res.bd_words + 1) + 3) & ~(size_t)3;  // whole 16-byte units (k_seg clears with 128-bit stores)
     if (want > r->bd_cap) {
         if (r->bd) PM_CUDA(cudaFree(r->bd));
         r->bd = nullptr;
-        PM_CUDA(cudaMalloc(&r->bd, want * sizeof(uint32_t)));
+        PM_CUDA(cudaMalloc(&r->bd, 2 * want * sizeof(uint32_t)));  // two buffers: frames alternate, each clears the other's
         r->bd_cap = want;
     }
     r->bd_words = want;
+    PM_CUDA(cudaMemsetAsync(r->bd, 0, 2 * want * sizeof(uint32_t), r->stream));
     r->plan_dirty = false;
     return PM_OK;
 }
@@ -236,7 +238,7 @@ int enqueue_frame(pm_renderer *r, bool debug_f32) {
     PmFrameArgs a;
     memset(&a, 0, sizeof a);
     a.scene = r->scene; a.scene_len = r->scene_len; a.n_items = r->n_items; a.items_ix = r->items_ix;
-    a.plan_a = r->plan_a; a.plan_b = r->plan_b; a.n_segments = r->n_segments; a.n_row_units = r->n_row_units; a.bd = r->bd;
+    a.plan_a = r->plan_a; a.plan_b = r->plan_b; a.n_segments = r->n_segments; a.n_row_units = r->n_row_units; a.bd = r->bd + (size_t)(r->frame & 1) * r->bd_words; a.bd_next = r->bd + (size_t)((r->frame + 1) & 1) * r->bd_words; a.bd_quads = r->bd_words / 4;
     a.piece_info = r->piece_info; a.seg_info = r->seg_info; a.item_info = r->item_info; a.n_pieces = r->n_pieces; a.row_info = r->row_info;
     a.tile_y0 = r->tile_y0; a.n_rows = r->tile_y1 - r->tile_y0; a.n_tx = r->n_tx;
     a.occ = r->occ; a.cnt = r->cnt; a.ovf = r->ovf;
@@ -248,13 +250,13 @@ int enqueue_frame(pm_renderer *r, bool debug_f32) {
     a.srgb_lut = r->lut;
     a.debug = r->debug;
     const uint32_t slot = r->frame % EVENT_RING;
-    PM_CUDA(cudaEventRecord(r->ev_start[slot], r->stream));
-    PM_CUDA(cudaMemsetAsync(r->bd, 0, r->bd_words * sizeof(uint32_t), r->stream));  // backdrop scratch of this frame
-    pm_launch_frame(a, r->sm_count, r->ev_mid[slot], r->stream);
-    PM_CUDA(cudaEventRecord(r->ev_end[slot], r->stream));
+    const bool events = r->frame_events || debug_f32;
+    if (events) PM_CUDA(cudaEventRecord(r->ev_start[slot], r->stream));
+    pm_launch_frame(a, r->sm_count, events ? r->ev_mid[slot] : nullptr, !events, r->stream);
+    if (events) PM_CUDA(cudaEventRecord(r->ev_end[slot], r->stream));
     PM_CUDA(cudaGetLastError());
     r->frame++;
-    r->frames_unsynced++;
+    if (events) r->frames_unsynced++;
     return PM_OK;
 }
 
@@ -438,6 +440,16 @@ int pm_renderer_render(pm_renderer *r) {
     return enqueue_frame(r, false);
 }
 
+int pm_renderer_set_frame_events(pm_renderer *r, int enabled) {
+    if (!r) return PM_ERR_INVALID_ARG;
+    int st = use_device(r);
+    if (st != PM_OK) return st;
+    PM_CUDA(cudaStreamSynchronize(r->stream));
+    r->frame_events = enabled != 0;
+    r->frames_unsynced = 0;
+    return PM_OK;
+}
+
 int pm_renderer_sync(pm_renderer *r, pm_frame_stats *stats) {
     if (!r) return PM_ERR_INVALID_ARG;
     int st = use_device(r);
@@ -463,7 +475,7 @@ int pm_renderer_sync(pm_renderer *r, pm_frame_stats *stats) {
     }
     if (stats) {
         memset(stats, 0, sizeof *stats);
-        uint32_t n = std::min<uint32_t>(r->frames_unsynced, EVENT_RING);
+        uint32_t n = r->frame_events ? std::min<uint32_t>(r->frames_unsynced, EVENT_RING) : 0;
         double sum_total = 0, sum_bin = 0, sum_fine = 0;
         for (uint32_t k = 0; k < n; k++) {
             uint32_t slot = (r->frame - 1 - k) % EVENT_RING;
