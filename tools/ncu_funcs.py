@@ -2,8 +2,25 @@
 """Per-function attribution (innermost inlined function by line) of an ncu source-page CSV.
     tools/ncu_funcs.py <source.csv> <cubin> <kernel-substring> <src-root>"""
 import csv, re, subprocess, sys, os, collections, bisect
+
+def _section(rows, kern):
+    """rows of the source-page CSV that belong to the kernel whose name contains `kern` (a file may hold several)."""
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    if not starts:
+        return rows
+    pick = None
+    for k, i in enumerate(starts):
+        name = rows[i][1] if len(rows[i]) > 1 else ""
+        short = kern.split("E")[0].split("IL")[0]
+        if short in name.replace("::", ""):
+            pick = k
+            break
+    if pick is None:
+        pick = 0
+    end = starts[pick + 1] if pick + 1 < len(starts) else len(rows)
+    return rows[starts[pick]:end]
 src_csv, cubin, kern, root = sys.argv[1:5]
-rows = list(csv.reader(open(src_csv)))
+rows = _section(list(csv.reader(open(src_csv))), kern)
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 col = {n: i for i, n in enumerate(rows[hi])}
 prof = [r for r in rows[hi + 1:] if len(r) > col["Instructions Executed"]]

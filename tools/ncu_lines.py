@@ -7,9 +7,26 @@ Joins the two instruction streams by order (opcodes are checked) and sums execut
 instructions and stall samples per file:line."""
 import csv, re, subprocess, sys, collections, os
 
+def _section(rows, kern):
+    """rows of the source-page CSV that belong to the kernel whose name contains `kern` (a file may hold several)."""
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    if not starts:
+        return rows
+    pick = None
+    for k, i in enumerate(starts):
+        name = rows[i][1] if len(rows[i]) > 1 else ""
+        short = kern.split("E")[0].split("IL")[0]
+        if short in name.replace("::", ""):
+            pick = k
+            break
+    if pick is None:
+        pick = 0
+    end = starts[pick + 1] if pick + 1 < len(starts) else len(rows)
+    return rows[starts[pick]:end]
+
 src_csv, cubin, kern = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-rows = list(csv.reader(open(src_csv)))
+rows = _section(list(csv.reader(open(src_csv))), kern)
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]
 col = {n: i for i, n in enumerate(hdr)}

@@ -2,9 +2,26 @@
 """Top SASS instructions of an ncu source-page CSV by a stall column, with nvdisasm line info.
     tools/ncu_stalls.py <source.csv> <cubin> <kernel-substring> <column> [top]"""
 import csv, re, subprocess, sys, os
+
+def _section(rows, kern):
+    """rows of the source-page CSV that belong to the kernel whose name contains `kern` (a file may hold several)."""
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    if not starts:
+        return rows
+    pick = None
+    for k, i in enumerate(starts):
+        name = rows[i][1] if len(rows[i]) > 1 else ""
+        short = kern.split("E")[0].split("IL")[0]
+        if short in name.replace("::", ""):
+            pick = k
+            break
+    if pick is None:
+        pick = 0
+    end = starts[pick + 1] if pick + 1 < len(starts) else len(rows)
+    return rows[starts[pick]:end]
 src_csv, cubin, kern, column = sys.argv[1:5]
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 30
-rows = list(csv.reader(open(src_csv)))
+rows = _section(list(csv.reader(open(src_csv))), kern)
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 col = {n: i for i, n in enumerate(rows[hdr_i])}
 prof = [r for r in rows[hdr_i + 1:] if len(r) > col["Instructions Executed"]]

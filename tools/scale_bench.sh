@@ -4,8 +4,8 @@ N=${1:-2}
 OUT=gpurun_out
 mkdir -p $OUT
 for size in 8192 16384; do
-  for mode in "" "--equal-strips"; do
-    tag=$(echo "$mode" | tr -d '-' ); tag=${tag:-balanced}
+  for tag in ${MODES:-balanced equal}; do
+    mode=""; [ "$tag" = "equal" ] && mode="--equal-strips"
     if [ "$N" = "1" ]; then
       python bench.py --gpus 1 --size $size --steps 100 --no-cpu-baseline --e2e-steps 2 $mode > $OUT/scale_n${N}_${size}_${tag}.json 2>$OUT/scale_err.log
     else
