@@ -77,7 +77,8 @@ struct FineWarpSmem {
     uint2 ovk[PM_FINE_LIST_CAP];     // ... and their (item, key), so that only the geometry is read from global memory
     uint32_t pkq[2];  // pipeline state of the walk over the tile list (see fine_entry)
     uint32_t st;
-    uint32_t pad;
+    uint32_t n_over, tail;  // heavy tiles: overflow records indexed in idx / ovk; 1 + pool index of the first one that did not fit
+    uint32_t pad[3];
 };
 
 #if PM_FINE_TIMELINE
@@ -296,14 +297,6 @@ __device__ __forceinline__ void fine_pairs(FineWarpSmem *w, bool mine, uint32_t 
     }
 }
 
-// Out-of-line copy for the overflow records of heavy tiles (rare): the hot call site is inlined so that
-// nothing has to survive a call boundary -- in particular the pending queue claim, which would be
-// spilled, i.e. waited for, right after its atomic.
-__device__ __noinline__ void fine_pairs_cold(FineWarpSmem *w, bool mine, uint32_t kind, float r_p0, float r_p1, float r_p2, float r_p3,
-                                             float r_edge_y, bool stroke, float reach, float tile_x0, float tile_y0, uint32_t lane) {
-    fine_pairs(w, mine, kind, r_p0, r_p1, r_p2, r_p3, r_edge_y, stroke, reach, tile_x0, tile_y0, lane);
-}
-
 // Pipeline state of a warp that walks the list of tiles with records.  While tile i is rendered, the
 // header and inline records of tile i+1 are in flight into the other half of the shared-memory
 // buffer; the queue position of tile i+2 is claimed when the coverage of tile i is done and its
@@ -386,6 +379,106 @@ __device__ __forceinline__ void fine_step3(const PmFrameArgs &A, uint32_t claim,
     }
 }
 
+// ---- heavy tiles (more records than inline slots, ~1 % of the tiles): out-of-line helpers, so that their
+// loops stay out of the instruction footprint of the common path ----
+
+// Indexes the overflow records: the extension block (positions 16..63, contiguous) and the chain behind it.
+// w->n_over counts what was actually found (a frame whose overflow pool ran out has fewer records than cnt
+// says; the host re-renders such a frame, it only must not fault).
+__device__ __noinline__ void fine_heavy_index(const PmFrameArgs &A, FineWarpSmem *w, uint32_t p, uint32_t n, uint32_t lane) {
+    uint32_t n_over = 0, tail = 0;
+    const u64 vw = w->hdr[p][2];
+    uint32_t base1 = (uint32_t)(vw >> 32) == A.stamp ? (uint32_t)vw : 0u;
+    if (base1 == PM_EXT_FAILED) base1 = 0;
+    if (base1) {
+        n_over = (n < PM_TILE_SLOTS + PM_EXT_SLOTS ? n : PM_TILE_SLOTS + PM_EXT_SLOTS) - PM_TILE_SLOTS;
+        for (uint32_t i = lane; i < n_over; i += 32) {
+            w->idx[i] = base1 + i;
+            w->ovk[i] = *reinterpret_cast<const uint2 *>(&A.pool[base1 + i]);
+        }
+        if (n > PM_TILE_SLOTS + PM_EXT_SLOTS) {
+            const uint32_t n_ext = n_over;
+            uint32_t cur = A.pool[base1 - 1u].next;
+            while (cur != 0 && n_over < PM_FINE_LIST_CAP) {
+                if (lane == 0) w->idx[n_over] = cur - 1u;
+                cur = A.pool[cur - 1u].next;
+                n_over++;
+            }
+            tail = cur;
+            __syncwarp();
+            for (uint32_t i = n_ext + lane; i < n_over; i += 32) w->ovk[i] = *reinterpret_cast<const uint2 *>(&A.pool[w->idx[i]]);
+        }
+    }
+    if (lane == 0) { w->n_over = n_over; w->tail = tail; }
+    __syncwarp();
+}
+__device__ __noinline__ bool fine_heavy_has_draw(const PmFrameArgs &A, const FineWarpSmem *w, uint32_t occ_item1, uint32_t lane) {
+    bool has_draw = false;
+    for (uint32_t i = lane; i < w->n_over; i += 32) {
+        const uint2 ik = w->ovk[i];
+        if (ik.x >= occ_item1 && (ik.y & 15u) != PM_REC_SOLID) has_draw = true;
+    }
+    for (uint32_t cur = w->tail; cur != 0; cur = A.pool[cur - 1u].next) {
+        const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[cur - 1u]);
+        if (ik.x >= occ_item1 && (ik.y & 15u) != PM_REC_SOLID) has_draw = true;
+    }
+    return has_draw;
+}
+// this lane's candidate for the next item in painter's order among the overflow records
+__device__ __noinline__ uint32_t fine_heavy_min_item(const PmFrameArgs &A, const FineWarpSmem *w, uint32_t occ_item1, bool first, uint32_t last_item,
+                                                     uint32_t cur_item, uint32_t lane) {
+    for (uint32_t i = lane; i < w->n_over; i += 32) {
+        const uint32_t it = w->ovk[i].x;
+        if (it >= occ_item1 && (first || it > last_item) && it < cur_item) cur_item = it;
+    }
+    for (uint32_t cur = w->tail; cur != 0; cur = A.pool[cur - 1u].next) {
+        const uint32_t it = A.pool[cur - 1u].item;
+        if (it >= occ_item1 && (first || it > last_item) && it < cur_item) cur_item = it;
+    }
+    return cur_item;
+}
+// the item's closing record among the overflow records: (kind, w0, w1), kind 0 if there is none
+__device__ __noinline__ uint3 fine_heavy_trailer(const PmFrameArgs &A, const FineWarpSmem *w, uint32_t cur_item, uint32_t lane) {
+    uint32_t t_kind = 0, t_w0 = 0, t_w1 = 0;
+    for (uint32_t i = lane; i < w->n_over; i += 32) {
+        const uint2 ik = w->ovk[i];
+        if (ik.x == cur_item && (ik.y & 15u) >= PM_REC_CIRCLE) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[w->idx[i]]);
+            t_kind = a.y & 15u; t_w0 = a.z; t_w1 = a.w;
+        }
+    }
+    for (uint32_t cur = w->tail; cur != 0; cur = A.pool[cur - 1u].next) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[cur - 1u]);
+        if (a.x == cur_item && (a.y & 15u) >= PM_REC_CIRCLE) { t_kind = a.y & 15u; t_w0 = a.z; t_w1 = a.w; }
+    }
+    const uint32_t src = __ffs(__ballot_sync(PM_FULL_MASK, t_kind != 0));
+    if (src == 0) return make_uint3(0, 0, 0);
+    return make_uint3(__shfl_sync(PM_FULL_MASK, t_kind, src - 1), __shfl_sync(PM_FULL_MASK, t_w0, src - 1), __shfl_sync(PM_FULL_MASK, t_w1, src - 1));
+}
+// phase A over the overflow records of the item, 32 at a time; those beyond the shared-memory index one at a time
+__device__ __noinline__ void fine_heavy_pairs(const PmFrameArgs &A, FineWarpSmem *w, uint32_t cur_item, bool stroke, float reach, float tile_x0, float tile_y0,
+                                              uint32_t lane) {
+    const uint32_t n_over = w->n_over;
+    for (uint32_t i0 = 0; i0 < n_over; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        PmRecord rc;
+        rc.item = 0xffffffffu; rc.key = 0; rc.p[0] = rc.p[1] = rc.p[2] = rc.p[3] = 0.0f; rc.edge_y = 0.0f; rc.next = 0;
+        if (i < n_over) {
+            const uint2 ik = w->ovk[i];
+            if (ik.x == cur_item && (ik.y & 15u) <= PM_REC_LINE) rc = load_record(A.pool, w->idx[i]);
+        }
+        const bool mine = rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE;
+        if (__any_sync(PM_FULL_MASK, mine))
+            fine_pairs(w, mine, rc.key & 15u, rc.p[0], rc.p[1], rc.p[2], rc.p[3], rc.edge_y, stroke, reach, tile_x0, tile_y0, lane);
+    }
+    for (uint32_t cur = w->tail; cur != 0;) {
+        PmRecord rc = load_record(A.pool, cur - 1u);
+        cur = rc.next;
+        if (rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE)
+            fine_pairs(w, lane == 0, rc.key & 15u, rc.p[0], rc.p[1], rc.p[2], rc.p[3], rc.edge_y, stroke, reach, tile_x0, tile_y0, lane);
+    }
+}
+
 // One tile that owns records; its header and inline records are in buffer `p` of w.  All 32 lanes
 // execute this together.  Records are handled in chunks of 32, one per lane; chunk 0 is the inline
 // slots.  Pixel layout: lane l owns pixel row (l >> 1), pixels 8*(l & 1) .. +7.
@@ -424,38 +517,8 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
     uint32_t occ_rgba = 0xffffffffu;  // solidColor starts as opaque white (metal:74)
     if (occ_item1) occ_rgba = __ldg(reinterpret_cast<const uint32_t *>(A.scene + A.items_ix + (size_t)(occ_item1 - 1u) * PM_ITEM_SIZE + PM_FILL_RGBA));
 
-    // index the overflow records: the extension block (positions 16..63, contiguous) and the chain behind
-    // it.  n_over counts what was actually found (a frame whose overflow pool ran out has fewer records
-    // than cnt says; the host re-renders such a frame, it only must not fault).
     const uint32_t n_inline = n < PM_TILE_SLOTS ? n : PM_TILE_SLOTS;
-    uint32_t n_over = 0;
-    uint32_t tail = 0;  // 1 + pool index of the first record that did not fit the shared-memory index
-    if (heavy) {
-        const u64 vw = w->hdr[p][2];
-        uint32_t base1 = (uint32_t)(vw >> 32) == A.stamp ? (uint32_t)vw : 0u;
-        if (base1 == PM_EXT_FAILED) base1 = 0;
-        if (base1) {
-            n_over = (n < PM_TILE_SLOTS + PM_EXT_SLOTS ? n : PM_TILE_SLOTS + PM_EXT_SLOTS) - PM_TILE_SLOTS;
-            for (uint32_t i = lane; i < n_over; i += 32) {
-                w->idx[i] = base1 + i;
-                w->ovk[i] = *reinterpret_cast<const uint2 *>(&A.pool[base1 + i]);
-            }
-            if (n > PM_TILE_SLOTS + PM_EXT_SLOTS) {
-                const uint32_t n_ext = n_over;
-                uint32_t cur = A.pool[base1 - 1u].next;
-                while (cur != 0 && n_over < PM_FINE_LIST_CAP) {
-                    if (lane == 0) w->idx[n_over] = cur - 1u;
-                    cur = A.pool[cur - 1u].next;
-                    n_over++;
-                }
-                tail = cur;
-                __syncwarp();
-                for (uint32_t i = n_ext + lane; i < n_over; i += 32) w->ovk[i] = *reinterpret_cast<const uint2 *>(&A.pool[w->idx[i]]);
-            }
-        }
-        __syncwarp();
-    }
-    const uint32_t n_chunks = 1u + ((n_over + 31u) >> 5);  // chunk 0: inline slots; chunk c >= 1: idx[32 (c - 1) ..]
+    if (heavy) fine_heavy_index(A, w, p, n, lane);
 
     // this lane's inline record: item and key stay in registers, the geometry is re-read when needed
     uint32_t my_item = 0xffffffffu, my_key = 0;
@@ -466,16 +529,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
     if (my_item < occ_item1) my_item = 0xffffffffu;  // below the topmost opaque cover: rewound away (metal:132-135)
 
     bool has_draw = my_item != 0xffffffffu && (my_key & 15u) != PM_REC_SOLID;
-    if (heavy) {
-        for (uint32_t i = lane; i < n_over; i += 32) {
-            const uint2 ik = w->ovk[i];
-            if (ik.x >= occ_item1 && (ik.y & 15u) != PM_REC_SOLID) has_draw = true;
-        }
-        for (uint32_t cur = tail; cur != 0; cur = A.pool[cur - 1u].next) {
-            const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[cur - 1u]);
-            if (ik.x >= occ_item1 && (ik.y & 15u) != PM_REC_SOLID) has_draw = true;
-        }
-    }
+    if (heavy && fine_heavy_has_draw(A, w, occ_item1, lane)) has_draw = true;
     has_draw = __any_sync(PM_FULL_MASK, has_draw);
 
     const uint32_t prow = lane >> 1, half = lane & 1u;
@@ -531,16 +585,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
     bool first = true;
     for (;;) {
         uint32_t cur_item = (first || my_item > last_item) ? my_item : 0xffffffffu;
-        if (heavy) {
-            for (uint32_t i = lane; i < n_over; i += 32) {
-                const uint32_t it = w->ovk[i].x;
-                if (it >= occ_item1 && (first || it > last_item) && it < cur_item) cur_item = it;
-            }
-            for (uint32_t cur = tail; cur != 0; cur = A.pool[cur - 1u].next) {
-                const uint32_t it = A.pool[cur - 1u].item;
-                if (it >= occ_item1 && (first || it > last_item) && it < cur_item) cur_item = it;
-            }
-        }
+        if (heavy) cur_item = fine_heavy_min_item(A, w, occ_item1, first, last_item, cur_item, lane);
         cur_item = __reduce_min_sync(PM_FULL_MASK, cur_item);
         if (cur_item == 0xffffffffu) break;
         first = false;
@@ -554,22 +599,9 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
                 const uint4 a = rec[2 * (__ffs(m) - 1)];
                 t_kind = a.y & 15u; t_w0 = a.z; t_w1 = a.w;
             } else if (heavy) {
-                for (uint32_t i = lane; i < n_over; i += 32) {
-                    const uint2 ik = w->ovk[i];
-                    if (ik.x == cur_item && (ik.y & 15u) >= PM_REC_CIRCLE) {
-                        const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[w->idx[i]]);
-                        t_kind = a.y & 15u; t_w0 = a.z; t_w1 = a.w;
-                    }
-                }
-                for (uint32_t cur = tail; cur != 0; cur = A.pool[cur - 1u].next) {
-                    const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[cur - 1u]);
-                    if (a.x == cur_item && (a.y & 15u) >= PM_REC_CIRCLE) { t_kind = a.y & 15u; t_w0 = a.z; t_w1 = a.w; }
-                }
-                const uint32_t src = __ffs(__ballot_sync(PM_FULL_MASK, t_kind != 0));
-                if (src == 0) continue;  // cannot happen for a well-formed list
-                t_kind = __shfl_sync(PM_FULL_MASK, t_kind, src - 1);
-                t_w0 = __shfl_sync(PM_FULL_MASK, t_w0, src - 1);
-                t_w1 = __shfl_sync(PM_FULL_MASK, t_w1, src - 1);
+                const uint3 tr = fine_heavy_trailer(A, w, cur_item, lane);
+                if (tr.x == 0) continue;  // cannot happen for a well-formed list
+                t_kind = tr.x; t_w0 = tr.y; t_w1 = tr.z;
             } else {
                 continue;  // cannot happen for a well-formed list
             }
@@ -593,26 +625,7 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
                 }
             }
             TL_MARK(stroke ? 2 : 7);
-            if (heavy) {
-                for (uint32_t c = 1; c < n_chunks; c++) {
-                    const uint32_t i = (c - 1u) * 32u + lane;
-                    PmRecord rc;
-                    rc.item = 0xffffffffu; rc.key = 0; rc.p[0] = rc.p[1] = rc.p[2] = rc.p[3] = 0.0f; rc.edge_y = 0.0f; rc.next = 0;
-                    if (i < n_over) {
-                        const uint2 ik = w->ovk[i];
-                        if (ik.x == cur_item && (ik.y & 15u) <= PM_REC_LINE) rc = load_record(A.pool, w->idx[i]);
-                    }
-                    const bool mine = rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE;
-                    if (__any_sync(PM_FULL_MASK, mine))
-                        fine_pairs_cold(w, mine, rc.key & 15u, rc.p[0], rc.p[1], rc.p[2], rc.p[3], rc.edge_y, stroke, reach, tile_x0, tile_y0, lane);
-                }
-                for (uint32_t cur = tail; cur != 0;) {  // records beyond the shared-memory index, one at a time
-                    PmRecord rc = load_record(A.pool, cur - 1u);
-                    cur = rc.next;
-                    if (rc.item == cur_item && (rc.key & 15u) <= PM_REC_LINE)
-                        fine_pairs_cold(w, lane == 0, rc.key & 15u, rc.p[0], rc.p[1], rc.p[2], rc.p[3], rc.edge_y, stroke, reach, tile_x0, tile_y0, lane);
-                }
-            }
+            if (heavy) fine_heavy_pairs(A, w, cur_item, stroke, reach, tile_x0, tile_y0, lane);
             __syncwarp();
             TL_MARK(3);
             if (fill) {  // covers of the left half of the pixel row carry into the right half
