@@ -56,7 +56,12 @@ typedef unsigned long long u64;
 #ifndef PM_FINE_EARLY_CLAIM
 #define PM_FINE_EARLY_CLAIM 0    // 1: the next-but-one tile is claimed at the start of a tile; 0: before the encode
 #endif
+#ifndef PM_FINE_CTAS
+#define PM_FINE_CTAS 3           // CTAs per SM the kernel is compiled for (3: 80 registers; 4: 64 registers and PM_FINE_LIST_CAP <= 64)
+#endif
+#ifndef PM_FINE_LIST_CAP
 #define PM_FINE_LIST_CAP 112     // overflow records per tile indexed in shared memory (extension block + 64 of the chain); the rest is re-walked      
+#endif
 
 __device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
 
@@ -326,6 +331,22 @@ __device__ __forceinline__ uint32_t fine_claim(const PmFrameArgs &A, const FineW
     if (lane == 0) asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(k) : "l"(&A.queue->sub[FINE_ST_HOME(w->st)][0]) : "memory");
     return k;
 }
+// The warp's sub-queue has run dry: move on to the next ones until a position is found or all are dry
+// (out of line: only the end of the frame comes here).
+__device__ __noinline__ uint32_t fine_next_subqueue(const PmFrameArgs &A, uint32_t n_total, uint32_t *home_io, uint32_t *dry_io) {
+    uint32_t home = *home_io, dry = *dry_io, q = 0xffffffffu;
+    while (dry < PM_FINE_SUBQ) {
+        if (++dry >= PM_FINE_SUBQ) break;
+        home = (home + 1u) & (PM_FINE_SUBQ - 1u);
+        uint32_t k = 0;
+        if ((threadIdx.x & 31u) == 0) k = atomicAdd(&A.queue->sub[home][0], 1u);
+        q = home + PM_FINE_SUBQ * __shfl_sync(PM_FULL_MASK, k, 0);
+        if (q < n_total) break;
+    }
+    *home_io = home;
+    *dry_io = dry;
+    return q;
+}
 // Turns the claim (lane 0's `claim` = k in the warp's current sub-queue) into a list entry on its way into
 // w->pkq[b] (no register waits for it).  The empty asm keeps the compiler from hoisting the shuffle up
 // to the atomic.  A sub-queue that has run dry sends the warp on to the next one, until all are dry.
@@ -334,13 +355,7 @@ __device__ __forceinline__ void fine_entry(const PmFrameArgs &A, uint32_t claim,
     uint32_t st = w->st & ~(FINE_ST_VALID(b) | FINE_ST_FULL(b));
     uint32_t home = FINE_ST_HOME(st), dry = FINE_ST_DRY(st);
     uint32_t q = home + PM_FINE_SUBQ * __shfl_sync(PM_FULL_MASK, claim, 0);
-    while (q >= n_total && dry < PM_FINE_SUBQ) {
-        if (++dry >= PM_FINE_SUBQ) break;
-        home = (home + 1u) & (PM_FINE_SUBQ - 1u);
-        uint32_t k = 0;
-        if ((threadIdx.x & 31u) == 0) k = atomicAdd(&A.queue->sub[home][0], 1u);
-        q = home + PM_FINE_SUBQ * __shfl_sync(PM_FULL_MASK, k, 0);
-    }
+    if (q >= n_total) q = fine_next_subqueue(A, n_total, &home, &dry);
     st = (st & ~0xff0u) | (home << 4) | (dry << 8);
     if (q < n_total) {
         const bool full = q >= n_heavy;
@@ -377,6 +392,12 @@ __device__ __forceinline__ void fine_step3(const PmFrameArgs &A, uint32_t claim,
         __syncwarp();
         w->st &= ~(FINE_ST_VALID(p) | FINE_ST_FULL(p));
     }
+}
+
+// Cmd_Circle coverage of four consecutive pixels (out of line: rare, and the kernel is sensitive to the size of its hot path)
+__device__ __noinline__ float4 fine_circle_alpha4(uint32_t bbox_lo, uint32_t bbox_hi, float px0, float py) {
+    return make_float4(pm_px_circle_alpha(bbox_lo, bbox_hi, px0, py), pm_px_circle_alpha(bbox_lo, bbox_hi, px0 + 1.0f, py),
+                       pm_px_circle_alpha(bbox_lo, bbox_hi, px0 + 2.0f, py), pm_px_circle_alpha(bbox_lo, bbox_hi, px0 + 3.0f, py));
 }
 
 // ---- heavy tiles (more records than inline slots, ~1 % of the tiles): out-of-line helpers, so that their
@@ -661,9 +682,8 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
                     al[3] = a.w ? pm_saturate(lim - __uint_as_float(~(uint32_t)a.w)) : 0.0f;
                 }
             } else if (t_kind == PM_REC_CIRCLE) {
-                const float px0 = tile_x0 + (float)(half * 8u + 4u * (uint32_t)g), py = tile_y0 + (float)prow;
-                #pragma unroll
-                for (int j = 0; j < 4; j++) al[j] = pm_px_circle_alpha(t_w0, t_w1, px0 + (float)j, py);
+                const float4 ca = fine_circle_alpha4(t_w0, t_w1, tile_x0 + (float)(half * 8u + 4u * (uint32_t)g), tile_y0 + (float)prow);
+                al[0] = ca.x; al[1] = ca.y; al[2] = ca.z; al[3] = ca.w;
             } else {  // PM_REC_SOLID: a translucent full cover
                 al[0] = al[1] = al[2] = al[3] = 1.0f;
             }
@@ -782,7 +802,7 @@ __device__ __forceinline__ void fine_solid_batch(const PmFrameArgs &A, uint32_t 
 }
 
 template <bool F32, bool EXACT>
-__global__ void __launch_bounds__(PM_FINE_WARPS * 32, 3) k_fine(const PmFrameArgs A) {
+__global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const PmFrameArgs A) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FineWarpSmem *w = reinterpret_cast<FineWarpSmem *>(s_raw) + warp;
