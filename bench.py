@@ -4,16 +4,18 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step is one frame: the encoded scene (resident in HBM) -> binning kernel -> fill/blend kernel ->
-RGBA8 framebuffer in HBM.  With N GPUs the frame's tile rows are sharded into N contiguous
+A step is one frame: the encoded scene (resident in HBM) -> binning kernels (k_seg, k_row) -> fill/blend
+kernel (k_fine) -> RGBA8 framebuffer in HBM.  With N GPUs the frame's tile rows are sharded into N contiguous
 row-strips (strong scaling: the frame is fixed); the scene is broadcast once over NCCL before the
 timed region and there is no collective per frame.  Rank 0 prints ONE JSON line.
 
-  value      whole-frame Mpixel/s, K frames back to back, device-timed, max over ranks
+  value      whole-frame Mpixel/s, K frames back to back (launches overlapped, no per-frame events),
+             device-timed with CUDA events around the K frames, max over ranks
   e2e        the same metric through the C-ABI call pm_renderer_render_host: scene bytes in pinned
              host memory -> H2D -> frame -> D2H of the strip's pixels into pinned host memory
-  roofline   fill/blend kernel: algorithmic bytes (4*W*H_strip + scene) / its CUDA-event duration,
-             against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  roofline   fill/blend kernel: algorithmic bytes (4*W*H_strip + scene) / its CUDA-event duration (a second
+             pass of K frames with per-frame events on the render stream), against the measured HBM copy
+             bandwidth in MEASURED_PEAKS.json
   cpu_baseline   the oracle (scalar port of the reference's tile loop) on the host cores, on a
              bounded band of tile rows of the same frame
 
@@ -300,12 +302,14 @@ def main():
     fine_ms = ms_fine_total / args.steps
     algo_bytes = fb_bytes + scene_bytes
     achieved = algo_bytes / (fine_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_fine_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    except Exception:
-        pass
+    traffic = None  # DRAM bytes per launch of the fill kernel from the committed ncu capture of this very workload
+    if world == 1 and size == 8192 and args.scene == "tiger":
+        try:
+            import glob
+            with open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_fine_traffic.json")))[-1]) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
 
     # ---- e2e: host scene bytes -> H2D -> frame -> D2H pixels, through pm_renderer_render_host ----
     host_scene = torch.empty(scene_bytes, dtype=torch.uint8).pin_memory()

@@ -222,3 +222,87 @@ def test_config5_band_matches_oracle(pm, oracle, renderer):
     gpu = gpu_render(renderer, scene, w, h, strip=(y0, y1))
     ref = oracle.render(scene, w, h, tile_y0=y0, tile_y1=y1, f32=True, items=True)
     check(gpu, ref, "glyphs 4096 rows %d..%d" % (y0, y1))
+
+
+def test_empty_and_tiny_surfaces(pm, oracle, renderer):
+    """Edge cases: a scene without items (every tile is background white), a 1x1 and a 17x33 surface (ragged
+    right and bottom tiles)."""
+    empty = np.zeros(8, np.uint8)
+    empty[4:8].view(np.uint32)[0] = 8  # n_items = 0, items_ix = 8
+    for w, h in ((16, 16), (1, 1), (17, 33)):
+        gpu = gpu_render(renderer, empty, w, h)
+        assert gpu["rgba8"].shape == (h, w, 4) and (gpu["rgba8"] == 255).all()
+        assert len(gpu["items"]) == 0 and (gpu["solid"] == 0xffffffff).all()
+    for w, h in ((1, 1), (17, 33), (33, 17)):
+        scene = pm.build_scene(pm.SCENE_RECT1, w, h, rect=(0.5, 0.25, w - 0.25, h - 0.5))
+        gpu = gpu_render(renderer, scene, w, h)
+        ref = oracle.render(scene, w, h, f32=True, items=True)
+        check(gpu, ref, "rect on %dx%d" % (w, h))
+
+
+def test_frames_without_events_are_identical(pm, renderer):
+    """pm_renderer_set_frame_events(0): the frame's kernels are chained by programmatic dependent launch and
+    consecutive frames overlap their launches; the pixels must not change, frame after frame."""
+    w = h = 1024
+    scene = pm.build_scene(pm.SCENE_TIGER, w, h)
+    renderer.drawable_size_will_change(w, h)
+    renderer.init_scene(scene)
+    renderer.draw()
+    want = renderer.read_rgba8()
+    renderer.set_frame_events(False)
+    try:
+        for _ in range(25):
+            renderer.draw()
+        st = renderer.sync()
+        assert st.frames == 0 and st.n_complex_tiles > 0
+        assert np.array_equal(renderer.read_rgba8(), want)
+        # a debug read-back in between (it renders a frame of its own) and more overlapped frames
+        f32 = renderer.read_rgba32f()
+        assert f32.shape == (h, w, 4)
+        for _ in range(3):
+            renderer.draw()
+        assert np.array_equal(renderer.read_rgba8(), want)
+    finally:
+        renderer.set_frame_events(True)
+    renderer.draw()
+    st = renderer.sync()
+    assert st.frames == 1 and st.ms_total > 0
+    assert np.array_equal(renderer.read_rgba8(), want)
+
+
+def test_balanced_strips_equal_full_frame(pm, renderer):
+    """Cost-balanced (unequal) row strips of the tiger and of the glyph scene reproduce the full frame byte for byte."""
+    for kind, size, count in ((pm.SCENE_TIGER, 2048, 0), (pm.SCENE_GLYPHS, 1024, 6000)):
+        scene = pm.build_scene(kind, size, size, count=count)
+        full = gpu_render(renderer, scene, size, size)["rgba8"]
+        b = pm.balanced_strip_bounds(pm.row_costs(scene, size, size), 8)
+        assert len(set(b[i + 1] - b[i] for i in range(8))) > 1  # really unequal
+        parts = []
+        for g in range(8):
+            renderer.drawable_size_will_change(size, size)
+            renderer.set_strip(b[g], b[g + 1])
+            renderer.init_scene(scene)
+            renderer.draw()
+            parts.append(renderer.read_rgba8())
+        assert np.array_equal(np.concatenate(parts, axis=0), full)
+
+
+def test_many_records_per_tile_extension_and_chain(pm, oracle, renderer):
+    """Tiles with 17..63 records (extension block) and beyond 64 (chain): a fan of thin polygons through one
+    point, drawn with translucent colours so that nothing is rewound away."""
+    w, h = 64, 48
+    for n_blades in (20, 70, 150):
+        enc = pm.Encoder(1 << 20)
+        enc.begin_group(n_blades)
+        for k in range(n_blades):
+            a = np.pi * k / n_blades
+            dx, dy = np.cos(a), np.sin(a)
+            cx, cy = 24.3, 20.7
+            pts = [(cx - 40 * dx - 0.6 * dy, cy - 40 * dy + 0.6 * dx), (cx + 40 * dx - 0.6 * dy, cy + 40 * dy + 0.6 * dx),
+                   (cx + 40 * dx + 0.6 * dy, cy + 40 * dy - 0.6 * dx), (cx - 40 * dx + 0.6 * dy, cy - 40 * dy - 0.6 * dx)]
+            enc.fill(np.array(pts), 0x20406080 + (k << 8))
+        enc.end_group()
+        scene = enc.bytes()
+        gpu = gpu_render(renderer, scene, w, h)
+        ref = oracle.render(scene, w, h, f32=True, items=True)
+        check(gpu, ref, "fan of %d" % n_blades)
