@@ -147,7 +147,7 @@ enum {
 typedef struct pm_config {
     int32_t device;          /* CUDA device ordinal */
     uint32_t flags;
-    uint64_t scratch_bytes;  /* overflow part of the record pool (beyond the 8 inline slots per
+    uint64_t scratch_bytes;  /* overflow part of the record pool (beyond the 16 inline slots per
                                 tile); 0 = sized automatically; it grows on demand either way */
 } pm_config;
 

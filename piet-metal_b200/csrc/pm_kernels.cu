@@ -1,11 +1,15 @@
 // CUDA kernels of the render path (sm_100a).  Compiled with -fmad=false: see pm_tile_logic.h.
 //
-//   k_validate   bounds/finite check of an uploaded scene            (the reference has none)
-//   k_plan       per-item tile-row counts -> work-unit prefix        (once per scene/size/strip)
-//   k_bin        one warp per (item, tile row): exact tile tests of TestApp/PietRender.metal:160-454
-//                evaluated per segment and row; appends per-tile records, accumulates backdrops,
-//                resolves opaque full covers with a 64-bit atomic max   (per frame)
-//   k_fine       fill/blend: see pm_fine.cu
+//   k_validate     bounds/finite check of an uploaded scene                      (the reference has none)
+//   k_plan         per-item prefixes: segments, (tile row, 32-tile chunk) units of k_row, backdrop-scratch
+//                  words; item table                                              (once per scene/size/strip)
+//   k_plan_pieces  per segment: the conservative list of (tile row, candidate tile) "pieces" = k_seg threads
+//   k_seg          one thread per piece: the exact tile tests of TestApp/PietRender.metal:248-445 for one
+//                  segment and one tile; appends per-tile records, accumulates the row's backdrop deltas
+//   k_row          one warp per (item, tile row, 32-tile chunk): prefix-sums the backdrop deltas and closes
+//                  the item per tile -- DrawFill / Solid / opaque cover (64-bit atomic max), Stroke; Line and
+//                  Circle items are binned here directly                          (k_seg, k_row: per frame)
+//   k_fine         fill/blend: see pm_fine.cu
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -227,62 +231,87 @@ __device__ __forceinline__ uint32_t item_of_segment(const u64 *plan_a, uint32_t 
 // (segment, tile row) that has no candidate tile but may still carry backdrop.  The candidate tiles
 // are the conservative span of pm_*_candidate_span; the exact tests run in k_seg every frame.
 // piece_info[q] = (segment, first << 31 | has_tile << 30 | tile row << 15 | tile column).
-// Pass 1 (piece_info == nullptr) only counts; pass 2 tabulates.  A long flat segment simply becomes
-// many pieces, a tall one too: no thread of k_seg does more than one tile's worth of work.
+// A long flat segment simply becomes many pieces, a tall one too: no thread of k_seg does more than one
+// tile's worth of work.
 #define PM_PIECE_FIRST 0x80000000u
 #define PM_PIECE_TILE 0x40000000u
 
-__global__ void __launch_bounds__(1024) k_plan_pieces(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0,
+// Three kernels (the plan is redone for every scene that is uploaded, i.e. inside every end-to-end frame):
+//   k_pieces_count  one thread per segment: its PmSegInfo and the number of its pieces
+//   k_pieces_scan   one CTA: exclusive prefix of the counts (each thread sums a contiguous chunk)
+//   k_pieces_fill   one thread per segment: writes its pieces at its offset
+__device__ __forceinline__ SegCtx segment_of(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1,
+                                             uint32_t n_tx, const u64 *plan_a, uint32_t g, uint32_t *item_out) {
+    const uint32_t item = item_of_segment(plan_a, n_items, g);
+    *item_out = item;
+    return load_segment(scene, items_ix, item, g - (uint32_t)plan_a[item], tile_y0, tile_y1, n_tx);
+}
+
+__global__ void __launch_bounds__(256) k_pieces_count(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0,
                                                       uint32_t tile_y1, uint32_t n_tx, const u64 *plan_a, uint32_t n_segments,
-                                                      PmSegInfo *seg_info, uint2 *piece_info, uint32_t piece_cap, PmPlanResult *result) {
-    __shared__ u64 warp_excl[32];
-    __shared__ u64 total, carry;
-    const uint32_t tid = threadIdx.x;
-    if (tid == 0) carry = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n_segments; base += blockDim.x) {
-        const uint32_t g = base + tid;
-        u64 cnt = 0;
-        SegCtx c;
-        c.ra = 1; c.rb = 0;
-        if (g < n_segments) {
-            const uint32_t item = item_of_segment(plan_a, n_items, g);
-            c = load_segment(scene, items_ix, item, g - (uint32_t)plan_a[item], tile_y0, tile_y1, n_tx);
-            PmSegInfo si;
-            si.sx = c.sg.sx; si.sy = c.sg.sy; si.ex = c.sg.ex; si.ey = c.sg.ey;
-            si.item = item; si.k = g - (uint32_t)plan_a[item]; si.hw = c.hw; si.tag = c.sp.tag;
-            seg_info[g] = si;
-            for (int r = c.ra; r <= c.rb; r++) {
-                uint32_t ta = 1, tb = 0;
-                const float y0 = (float)(r * PM_TILE_H);
-                const bool has = c.sp.tag == PM_ITEM_FILL ? pm_fill_candidate_span(c.sg, y0, c.sp.t_lo, c.sp.t_hi, &ta, &tb)
-                                                           : pm_poly_candidate_span(c.sg, y0, c.hw, c.sp.t_lo, c.sp.t_hi, &ta, &tb);
-                cnt += has ? (u64)(tb - ta + 1) : 1ull;
-            }
-        }
-        const u64 e = carry + block_scan_excl(cnt, warp_excl, &total);
-        if (g < n_segments && piece_info) {
-            u64 q = e;
-            for (int r = c.ra; r <= c.rb; r++) {
-                uint32_t ta = 1, tb = 0;
-                const float y0 = (float)(r * PM_TILE_H);
-                const bool has = c.sp.tag == PM_ITEM_FILL ? pm_fill_candidate_span(c.sg, y0, c.sp.t_lo, c.sp.t_hi, &ta, &tb)
-                                                           : pm_poly_candidate_span(c.sg, y0, c.hw, c.sp.t_lo, c.sp.t_hi, &ta, &tb);
-                if (!has) {
-                    if (q < piece_cap) piece_info[q] = make_uint2(g, PM_PIECE_FIRST | ((uint32_t)r << 15));
-                    q++;
-                } else {
-                    for (uint32_t t = ta; t <= tb; t++, q++)
-                        if (q < piece_cap) piece_info[q] = make_uint2(g, (t == ta ? PM_PIECE_FIRST : 0u) | PM_PIECE_TILE | ((uint32_t)r << 15) | t);
-                }
-            }
-        }
-        if (e + cnt >= 0x80000000ull) result->error = 1;
-        __syncthreads();
-        if (tid == 0) carry += total;
-        __syncthreads();
+                                                      PmSegInfo *seg_info, uint32_t *piece_cnt) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_segments) return;
+    uint32_t item;
+    const SegCtx c = segment_of(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, g, &item);
+    PmSegInfo si;
+    si.sx = c.sg.sx; si.sy = c.sg.sy; si.ex = c.sg.ex; si.ey = c.sg.ey;
+    si.item = item; si.k = g - (uint32_t)plan_a[item]; si.hw = c.hw; si.tag = c.sp.tag;
+    seg_info[g] = si;
+    u64 cnt = 0;
+    for (int r = c.ra; r <= c.rb; r++) {
+        uint32_t ta = 1, tb = 0;
+        const float y0 = (float)(r * PM_TILE_H);
+        const bool has = c.sp.tag == PM_ITEM_FILL ? pm_fill_candidate_span(c.sg, y0, c.sp.t_lo, c.sp.t_hi, &ta, &tb)
+                                                   : pm_poly_candidate_span(c.sg, y0, c.hw, c.sp.t_lo, c.sp.t_hi, &ta, &tb);
+        cnt += has ? (u64)(tb - ta + 1) : 1ull;
     }
-    if (tid == 0) result->n_pieces = (uint32_t)carry;
+    piece_cnt[g] = cnt > 0xffffffffull ? 0xffffffffu : (uint32_t)cnt;  // (saturated: the scan reports the overflow)
+}
+
+// piece_cnt[g] -> exclusive prefix, in place; result->n_pieces = total; result->error if it does not fit 31 bits
+__global__ void __launch_bounds__(1024) k_pieces_scan(uint32_t *piece_cnt, uint32_t n_segments, PmPlanResult *result) {
+    __shared__ u64 warp_excl[32];
+    __shared__ u64 total;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t chunk = (n_segments + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = tid * chunk < n_segments ? tid * chunk : n_segments;
+    const uint32_t hi = lo + chunk < n_segments ? lo + chunk : n_segments;
+    u64 sum = 0;
+    for (uint32_t g = lo; g < hi; g++) sum += piece_cnt[g];
+    u64 run = block_scan_excl(sum, warp_excl, &total);
+    for (uint32_t g = lo; g < hi; g++) {
+        const uint32_t c = piece_cnt[g];
+        piece_cnt[g] = (uint32_t)run;
+        run += c;
+    }
+    if (tid == 0) {
+        if (total >= 0x80000000ull) result->error = 1;
+        result->n_pieces = (uint32_t)total;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pieces_fill(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0,
+                                                     uint32_t tile_y1, uint32_t n_tx, const u64 *plan_a, uint32_t n_segments,
+                                                     const uint32_t *piece_off, uint2 *piece_info, uint32_t piece_cap) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_segments) return;
+    uint32_t item;
+    const SegCtx c = segment_of(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, g, &item);
+    u64 q = piece_off[g];
+    for (int r = c.ra; r <= c.rb; r++) {
+        uint32_t ta = 1, tb = 0;
+        const float y0 = (float)(r * PM_TILE_H);
+        const bool has = c.sp.tag == PM_ITEM_FILL ? pm_fill_candidate_span(c.sg, y0, c.sp.t_lo, c.sp.t_hi, &ta, &tb)
+                                                   : pm_poly_candidate_span(c.sg, y0, c.hw, c.sp.t_lo, c.sp.t_hi, &ta, &tb);
+        if (!has) {
+            if (q < piece_cap) piece_info[q] = make_uint2(g, PM_PIECE_FIRST | ((uint32_t)r << 15));
+            q++;
+        } else {
+            for (uint32_t t = ta; t <= tb; t++, q++)
+                if (q < piece_cap) piece_info[q] = make_uint2(g, (t == ta ? PM_PIECE_FIRST : 0u) | PM_PIECE_TILE | ((uint32_t)r << 15) | t);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -384,7 +413,10 @@ struct BinSink {
 // One thread per piece (see k_plan_pieces): the exact tile tests of TestApp/PietRender.metal:248-445
 // of one segment for one candidate tile; the first piece of a (segment, tile row) also adds the
 // row's backdrop intervals.
-__global__ void __launch_bounds__(256) k_seg(const PmFrameArgs A) {
+#ifndef PM_SEG_CTAS
+#define PM_SEG_CTAS 5  // resident CTAs per SM k_seg is compiled for (5: 43 registers as the compiler likes it)
+#endif
+__global__ void __launch_bounds__(256, PM_SEG_CTAS) k_seg(const PmFrameArgs A) {
     // PM_DEBUG_SEG=1: per-CTA [start, end] in globaltimer ns, two words per CTA
     struct Timer {
         const PmFrameArgs &A;
@@ -511,10 +543,17 @@ void pm_launch_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, u
     k_plan<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, plan_b, item_info, row_info, row_info_cap, result);
 }
 
-void pm_launch_plan_pieces(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
-                           const unsigned long long *plan_a, uint32_t n_segments, PmSegInfo *seg_info, uint2 *piece_info,
-                           uint32_t piece_cap, PmPlanResult *result, cudaStream_t s) {
-    k_plan_pieces<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, n_segments, seg_info, piece_info, piece_cap, result);
+void pm_launch_pieces_count(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
+                            const unsigned long long *plan_a, uint32_t n_segments, PmSegInfo *seg_info, uint32_t *piece_cnt,
+                            PmPlanResult *result, cudaStream_t s) {
+    if (n_segments) k_pieces_count<<<(n_segments + 255) / 256, 256, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, n_segments, seg_info, piece_cnt);
+    k_pieces_scan<<<1, 1024, 0, s>>>(piece_cnt, n_segments, result);
+}
+
+void pm_launch_pieces_fill(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
+                           const unsigned long long *plan_a, uint32_t n_segments, const uint32_t *piece_off, uint2 *piece_info,
+                           uint32_t piece_cap, cudaStream_t s) {
+    if (n_segments) k_pieces_fill<<<(n_segments + 255) / 256, 256, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, n_segments, piece_off, piece_info, piece_cap);
 }
 
 template <class K>

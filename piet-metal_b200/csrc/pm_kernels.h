@@ -85,9 +85,13 @@ void pm_launch_validate(const uint8_t *scene, uint32_t scene_len, uint32_t *err,
 void pm_launch_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1,
                     uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, PmItemInfo *item_info, uint2 *row_info,
                     uint32_t row_info_cap, PmPlanResult *result, cudaStream_t s);
-void pm_launch_plan_pieces(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
-                           const unsigned long long *plan_a, uint32_t n_segments, PmSegInfo *seg_info, uint2 *piece_info,
-                           uint32_t piece_cap, PmPlanResult *result, cudaStream_t s);
+// The k_seg work list: count + prefix (result->n_pieces, piece_cnt becomes the per-segment offset), then fill.
+void pm_launch_pieces_count(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
+                            const unsigned long long *plan_a, uint32_t n_segments, PmSegInfo *seg_info, uint32_t *piece_cnt,
+                            PmPlanResult *result, cudaStream_t s);
+void pm_launch_pieces_fill(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
+                           const unsigned long long *plan_a, uint32_t n_segments, const uint32_t *piece_off, uint2 *piece_info,
+                           uint32_t piece_cap, cudaStream_t s);
 // One frame: binning (k_seg, k_row) then fill/blend (k_fine).  `mid` (optional) is recorded before k_fine.
 // `overlap`: programmatic dependent launch between the frame's kernels and from one frame to the next (no event
 // may sit between them, so `mid` must be null).

@@ -56,6 +56,7 @@ struct pm_renderer {
     size_t plan_cap = 0;
     uint32_t n_segments = 0, n_row_units = 0, n_pieces = 0;
     PmSegInfo *seg_info = nullptr;
+    uint32_t *piece_off = nullptr;  // per segment: offset of its pieces in piece_info
     size_t seg_cap = 0;
     PmItemInfo *item_info = nullptr;
     uint2 *piece_info = nullptr, *row_info = nullptr;
@@ -159,46 +160,48 @@ int alloc_surface(pm_renderer *r) {
 
 int run_plan(pm_renderer *r) {
     PmPlanResult res;
-    // pass 1 sizes the k_row unit table, pass 2 fills it
+    // the k_row unit table is filled in the same pass that sizes it; a second pass only if it was too small
     for (int pass = 0; pass < 2; pass++) {
         PM_CUDA(cudaMemsetAsync(r->dev_plan, 0, sizeof(PmPlanResult), r->stream));
         pm_launch_plan(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, r->plan_b, r->item_info,
-                       pass ? r->row_info : nullptr, (uint32_t)r->row_info_cap, r->dev_plan, r->stream);
+                       r->row_info, (uint32_t)r->row_info_cap, r->dev_plan, r->stream);
         PM_CUDA(cudaGetLastError());
         PM_CUDA(cudaMemcpyAsync(&res, r->dev_plan, sizeof res, cudaMemcpyDeviceToHost, r->stream));
         PM_CUDA(cudaStreamSynchronize(r->stream));
-        if (res.error) break;
-        if (pass == 0 && (size_t)res.n_rows + 1 > r->row_info_cap) {
-            if (r->row_info) PM_CUDA(cudaFree(r->row_info));
-            r->row_info = nullptr;
-            PM_CUDA(cudaMalloc(&r->row_info, ((size_t)res.n_rows + 1) * sizeof(uint2)));
-            r->row_info_cap = (size_t)res.n_rows + 1;
-        }
+        if (res.error || (size_t)res.n_rows <= r->row_info_cap) break;
+        if (r->row_info) PM_CUDA(cudaFree(r->row_info));
+        r->row_info = nullptr;
+        r->row_info_cap = 0;
+        PM_CUDA(cudaMalloc(&r->row_info, ((size_t)res.n_rows + res.n_rows / 8 + 1) * sizeof(uint2)));
+        r->row_info_cap = (size_t)res.n_rows + res.n_rows / 8 + 1;
     }
     if (res.error) { g_last_error = "scene has more than 2^31 segments or (item, tile row) pairs"; return PM_ERR_INVALID_ARG; }
     if (res.bd_words > (1ull << 31)) { g_last_error = "item bounding boxes cover more than 2^31 tiles in total"; return PM_ERR_NOMEM; }
     r->n_segments = res.n_segments;
     if ((size_t)res.n_segments + 1 > r->seg_cap) {
         if (r->seg_info) PM_CUDA(cudaFree(r->seg_info));
-        r->seg_info = nullptr;
+        if (r->piece_off) PM_CUDA(cudaFree(r->piece_off));
+        r->seg_info = nullptr; r->piece_off = nullptr;
         PM_CUDA(cudaMalloc(&r->seg_info, ((size_t)res.n_segments + 1) * sizeof(PmSegInfo)));
+        PM_CUDA(cudaMalloc(&r->piece_off, ((size_t)res.n_segments + 1) * sizeof(uint32_t)));
         r->seg_cap = (size_t)res.n_segments + 1;
     }
-    // pass 1 counts the k_seg pieces; pass 2 tabulates them
-    for (int pass = 0; pass < 2; pass++) {
-        pm_launch_plan_pieces(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, res.n_segments,
-                              r->seg_info, pass ? r->piece_info : nullptr, (uint32_t)r->piece_cap, r->dev_plan, r->stream);
-        PM_CUDA(cudaGetLastError());
-        PM_CUDA(cudaMemcpyAsync(&res, r->dev_plan, sizeof res, cudaMemcpyDeviceToHost, r->stream));
-        PM_CUDA(cudaStreamSynchronize(r->stream));
-        if (res.error) { g_last_error = "scene has more than 2^31 (segment, tile row, tile) pieces"; return PM_ERR_INVALID_ARG; }
-        if (pass == 0 && (size_t)res.n_pieces + 1 > r->piece_cap) {
-            if (r->piece_info) PM_CUDA(cudaFree(r->piece_info));
-            r->piece_info = nullptr;
-            PM_CUDA(cudaMalloc(&r->piece_info, ((size_t)res.n_pieces + 1) * sizeof(uint2)));
-            r->piece_cap = (size_t)res.n_pieces + 1;
-        }
+    // the k_seg pieces: count and prefix, then (once the table is large enough) fill
+    pm_launch_pieces_count(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, res.n_segments,
+                           r->seg_info, r->piece_off, r->dev_plan, r->stream);
+    PM_CUDA(cudaGetLastError());
+    PM_CUDA(cudaMemcpyAsync(&res, r->dev_plan, sizeof res, cudaMemcpyDeviceToHost, r->stream));
+    PM_CUDA(cudaStreamSynchronize(r->stream));
+    if (res.error) { g_last_error = "scene has more than 2^31 (segment, tile row, tile) pieces"; return PM_ERR_INVALID_ARG; }
+    if ((size_t)res.n_pieces + 1 > r->piece_cap) {
+        if (r->piece_info) PM_CUDA(cudaFree(r->piece_info));
+        r->piece_info = nullptr;
+        PM_CUDA(cudaMalloc(&r->piece_info, ((size_t)res.n_pieces + 1) * sizeof(uint2)));
+        r->piece_cap = (size_t)res.n_pieces + 1;
     }
+    pm_launch_pieces_fill(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, res.n_segments, r->piece_off,
+                          r->piece_info, (uint32_t)r->piece_cap, r->stream);
+    PM_CUDA(cudaGetLastError());
     r->n_pieces = res.n_pieces;
     if (getenv("PM_DEBUG_SEG") || getenv("PM_DEBUG_FINE")) {
         if (r->debug) cudaFree(r->debug);
@@ -382,7 +385,7 @@ void pm_renderer_destroy(pm_renderer *r) {
     if (!r) return;
     cudaSetDevice(r->device);
     if (r->stream) cudaStreamSynchronize(r->stream);
-    cudaFree(r->scene); cudaFree(r->plan_a); cudaFree(r->plan_b); cudaFree(r->bd); cudaFree(r->seg_info); cudaFree(r->item_info); cudaFree(r->piece_info); cudaFree(r->row_info); cudaFree(r->debug); cudaFree(r->dev_err); cudaFree(r->dev_plan);
+    cudaFree(r->scene); cudaFree(r->plan_a); cudaFree(r->plan_b); cudaFree(r->bd); cudaFree(r->seg_info); cudaFree(r->piece_off); cudaFree(r->item_info); cudaFree(r->piece_info); cudaFree(r->row_info); cudaFree(r->debug); cudaFree(r->dev_err); cudaFree(r->dev_plan);
     cudaFree(r->fb); cudaFree(r->fb32); cudaFree(r->occ); cudaFree(r->cnt); cudaFree(r->ovf); cudaFree(r->complex_list);
     cudaFree(r->pool); cudaFree(r->counters); cudaFree(r->queue); cudaFree(r->lut);
     if (r->report) cudaFreeHost(r->report);
@@ -493,7 +496,7 @@ int pm_renderer_sync(pm_renderer *r, pm_frame_stats *stats) {
         stats->n_tiles = (r->tile_y1 - r->tile_y0) * r->n_tx;
         stats->n_overflow_records = r->report->n_overflow;
         stats->n_complex_tiles = r->report->n_complex;
-        stats->n_launches = 3;  /* k_seg, k_row, k_fine (+ one memset node) */
+        stats->n_launches = 3;  /* k_seg, k_row, k_fine */
         stats->retries = r->retries - retries_before;
     }
     r->frames_unsynced = 0;
