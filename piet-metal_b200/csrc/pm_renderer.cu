@@ -512,7 +512,10 @@ int pm_renderer_read_rgba8(pm_renderer *r, uint8_t *dst, size_t stride) {
     st = finish_frames(r, false);
     if (st != PM_OK) return st;
     uint32_t y_begin = r->tile_y0 * PM_TILE_H, y_end = std::min(r->tile_y1 * PM_TILE_H, r->height);
-    PM_CUDA(cudaMemcpy2DAsync(dst, stride, r->fb, r->pitch, (size_t)r->width * 4, y_end - y_begin, cudaMemcpyDeviceToHost, r->stream));
+    if (stride == r->pitch && (size_t)r->width * 4 == r->pitch)  // contiguous on both sides: one linear copy
+        PM_CUDA(cudaMemcpyAsync(dst, r->fb, r->pitch * (y_end - y_begin), cudaMemcpyDeviceToHost, r->stream));
+    else
+        PM_CUDA(cudaMemcpy2DAsync(dst, stride, r->fb, r->pitch, (size_t)r->width * 4, y_end - y_begin, cudaMemcpyDeviceToHost, r->stream));
     PM_CUDA(cudaStreamSynchronize(r->stream));
     return PM_OK;
 }
