@@ -346,26 +346,26 @@ struct BinSink {
             idx = tile * PM_TILE_SLOTS + pos;
         } else {
             // Records 16..63 of a tile go into its extension block: PM_EXT_BLOCK contiguous pool records,
-            // allocated by whoever claims position 16 and published in ovf[tile]; everybody else with a
-            // position beyond 15 waits for that word (the publisher is running: it cannot depend on a
-            // waiter).  The block's first record is a header whose `next` heads the chain of records 64...
+            // published in ovf[tile] (stamped).  Lock-free and without waiting: whoever finds the word
+            // unpublished allocates a block and tries to install it with a compare-and-swap; a loser adopts
+            // the winner's block (its own stays unused -- bump allocation cannot give it back; the count
+            // the host sees includes it).  The block's first record is a header whose `next` heads the
+            // chain of records 64...
             const uint32_t ovf_region = A.n_rows * A.n_tx * PM_TILE_SLOTS;
             uint32_t base1;  // 1 + pool index of the block header, or PM_EXT_FAILED
-            if (pos == PM_TILE_SLOTS) {
-                const uint32_t o = atomicAdd(&A.counters->n_overflow, (uint32_t)PM_EXT_BLOCK);
-                if (o + PM_EXT_BLOCK <= A.overflow_cap) {
-                    base1 = ovf_region + o + 1u;
-                    A.pool[base1 - 1u].next = 0;
-                    __threadfence();
-                } else {
-                    base1 = PM_EXT_FAILED;  // the host sees n_overflow > overflow_cap, grows the pool and re-renders
-                }
-                atomicExch(&A.ovf[tile], ((u64)A.stamp << 32) | (u64)base1);
+            const u64 seen = *reinterpret_cast<volatile u64 *>(&A.ovf[tile]);
+            if ((uint32_t)(seen >> 32) == A.stamp) {
+                base1 = (uint32_t)seen;
             } else {
-                volatile u64 *vw = &A.ovf[tile];
-                u64 v = *vw;
-                while ((uint32_t)(v >> 32) != A.stamp) { __nanosleep(40); v = *vw; }
-                base1 = (uint32_t)v;
+                const uint32_t o = atomicAdd(&A.counters->n_overflow, (uint32_t)PM_EXT_BLOCK);
+                uint32_t mine = PM_EXT_FAILED;  // the host sees n_overflow > overflow_cap, grows the pool and re-renders
+                if (o + PM_EXT_BLOCK <= A.overflow_cap) {
+                    mine = ovf_region + o + 1u;
+                    A.pool[mine - 1u].next = 0;
+                    __threadfence();
+                }
+                const u64 prev = atomicCAS(&A.ovf[tile], seen, ((u64)A.stamp << 32) | (u64)mine);
+                base1 = prev == seen ? mine : (uint32_t)prev;  // (a word that changed was published by somebody else, this frame)
             }
             if (base1 == PM_EXT_FAILED) return;
             if (pos < PM_TILE_SLOTS + PM_EXT_SLOTS) {
