@@ -528,7 +528,13 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
     const uint32_t n = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
     const uint32_t occ_item1 = (uint32_t)(ow >> 32) == A.stamp ? (uint32_t)ow : 0u;
     const bool heavy = n > PM_TILE_SLOTS;
+#if PM_CTA_TILES
+    const bool by_cta = (w->st & 0x1000u) != 0 && n >= PM_CTA_MIN && n <= PM_CTA_CAP &&
+                        (uint32_t)(w->hdr[p][2] >> 32) == A.stamp && (uint32_t)w->hdr[p][2] != PM_EXT_FAILED;  // the test of fine_cta_tile
+    if ((heavy && skip_heavy) || by_cta) {
+#else
     if (heavy && skip_heavy) {  // pass 1 rendered it
+#endif
         TL_MARK(6);
         fine_step1(A, w, p, lane);
 #if PM_FINE_EARLY_CLAIM
@@ -734,6 +740,149 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
     TL_MARK(5);
 }
 
+#if PM_CTA_TILES
+// ---- costly tiles rendered by a whole CTA (see PM_CTA_TILES in pm_kernels.h; not yet validated on a GPU) ----
+// Thread t owns pixel (row t >> 4, column t & 15) and holds its linear colour in three registers.  The tile's
+// records (at most PM_CTA_CAP) are indexed in shared memory borrowed from the per-warp state of warps 1 and 2
+// (their colour planes, which a warp initialises before every use); thread t holds (item, key) of record t, so
+// warp w has records 32 w .. 32 w + 31, one per lane, and runs the same fine_pairs() as the per-warp path on them -- all eight warps accumulating into
+// warp 0's coverage arrays with shared-memory atomics.  Per item: block-wide minimum of the item ids, coverage,
+// barrier, resolve + blend one pixel per thread, barrier.  Same functions, same operand order, integer coverage
+// sums: the pixels are bit-identical to the per-warp path.
+struct FineCtaShared {      // lives in warp 2's colour planes
+    u64 cw, ow, vw;
+    uint32_t red[PM_FINE_WARPS];   // block reductions
+    uint32_t t_kind, t_w0, t_w1, pad;
+};
+
+__device__ __forceinline__ uint32_t fine_block_min(uint32_t v, volatile uint32_t *red, uint32_t lane, uint32_t warp) {
+    v = __reduce_min_sync(PM_FULL_MASK, v);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    uint32_t m = red[0];
+    #pragma unroll
+    for (int k = 1; k < PM_FINE_WARPS; k++) m = red[k] < m ? red[k] : m;
+    __syncthreads();
+    return m;
+}
+
+template <bool F32, bool EXACT>
+__device__ __noinline__ void fine_cta_tile(const PmFrameArgs &A, FineWarpSmem *ws, uint32_t packed_tile) {
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const uint32_t trow = packed_tile >> 16, tx = packed_tile & 0xffffu;
+    const size_t tile = (size_t)trow * A.n_tx + tx;
+    FineWarpSmem *acc_w = &ws[0];                                          // shared coverage accumulators
+    uint32_t *idx = reinterpret_cast<uint32_t *>(&ws[1].rgb[0][0][0]);     // [PM_CTA_CAP] pool indices
+    FineCtaShared *sh = reinterpret_cast<FineCtaShared *>(&ws[2].rgb[0][0][0]);
+    if (t == 0) { sh->cw = A.cnt[tile]; sh->ow = A.occ[tile]; sh->vw = A.ovf[tile]; }
+    __syncthreads();
+    const u64 cw = sh->cw, ow = sh->ow, vw = sh->vw;
+    const uint32_t n = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
+    const uint32_t occ_item1 = (uint32_t)(ow >> 32) == A.stamp ? (uint32_t)ow : 0u;
+    uint32_t base1 = (uint32_t)(vw >> 32) == A.stamp ? (uint32_t)vw : 0u;
+    if (base1 == PM_EXT_FAILED) base1 = 0;
+    if (n < PM_CTA_MIN || n > PM_CTA_CAP || base1 == 0) { __syncthreads(); return; }  // (left to the per-warp path, which applies the same test)
+    // record index: inline slots, extension block, chain
+    if (t < n) {
+        if (t < PM_TILE_SLOTS) idx[t] = (uint32_t)tile * PM_TILE_SLOTS + t;
+        else if (t < PM_TILE_SLOTS + PM_EXT_SLOTS) idx[t] = base1 + (t - PM_TILE_SLOTS);
+    }
+    if (t == 0 && n > PM_TILE_SLOTS + PM_EXT_SLOTS) {
+        uint32_t cur = A.pool[base1 - 1u].next, k = PM_TILE_SLOTS + PM_EXT_SLOTS;
+        for (; cur != 0 && k < n; k++) { idx[k] = cur - 1u; cur = A.pool[cur - 1u].next; }
+        for (; k < n; k++) idx[k] = 0xffffffffu;  // (a frame whose overflow pool ran out: fewer links than cnt says)
+    }
+    __syncthreads();
+    uint32_t my_item = 0xffffffffu, my_key = 0;
+    if (t < n && idx[t] != 0xffffffffu) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(&A.pool[idx[t]]);
+        my_item = v.x; my_key = v.y;
+    }
+    if (my_item < occ_item1) my_item = 0xffffffffu;  // below the topmost opaque cover: rewound away (metal:132-135)
+    const int has_draw = __syncthreads_or(my_item != 0xffffffffu && (my_key & 15u) != PM_REC_SOLID);
+
+    const uint32_t prow = t >> 4, px = t & 15u;
+    uint8_t *dst = A.fb + (size_t)(trow * PM_TILE_H + prow) * A.pitch + (size_t)(tx * PM_TILE_W + px) * 4u;
+    float4 *dst32 = nullptr;
+    if (F32) dst32 = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(A.fb32) + (size_t)(trow * PM_TILE_H + prow) * A.pitch32) + (tx * PM_TILE_W + px);
+    uint32_t occ_rgba = 0xffffffffu;  // solidColor starts as opaque white (metal:74)
+    if (occ_item1) occ_rgba = __ldg(reinterpret_cast<const uint32_t *>(A.scene + A.items_ix + (size_t)(occ_item1 - 1u) * PM_ITEM_SIZE + PM_FILL_RGBA));
+    if (!has_draw) {  // the tile Bails and shows solidColor (metal:145-147, :34-44)
+        *reinterpret_cast<uint32_t *>(dst) = occ_rgba;
+        if (F32) *dst32 = make_float4((float)(occ_rgba & 0xff) / 255.0f, (float)((occ_rgba >> 8) & 0xff) / 255.0f,
+                                      (float)((occ_rgba >> 16) & 0xff) / 255.0f, (float)(occ_rgba >> 24) / 255.0f);
+        __syncthreads();
+        return;
+    }
+    const float *lut = A.srgb_lut;
+    float c0 = 1.0f, c1 = 1.0f, c2 = 1.0f;  // metal:470; then the cover's Cmd_Solid (metal:136-142, :546-551)
+    if (occ_item1) {
+        float fg[4];
+        unpack_fg(lut, occ_rgba, fg);
+        c0 = mix_fma(1.0f, fg[0], fg[3]); c1 = mix_fma(1.0f, fg[1], fg[3]); c2 = mix_fma(1.0f, fg[2], fg[3]);
+    }
+    const float tile_x0 = (float)(tx * PM_TILE_W), tile_y0 = (float)((A.tile_y0 + trow) * PM_TILE_H);
+    const int my_cell = fine_swz((int)prow, (int)px);
+    uint32_t last_item = 0;
+    bool first = true;
+    for (;;) {
+        const uint32_t cand = (first || my_item > last_item) ? my_item : 0xffffffffu;
+        const uint32_t cur_item = fine_block_min(cand, sh->red, lane, warp);
+        if (cur_item == 0xffffffffu) break;
+        first = false;
+        last_item = cur_item;
+        // the item's closing record
+        if (t == 0) sh->t_kind = 0;
+        __syncthreads();
+        if (my_item == cur_item && (my_key & 15u) >= PM_REC_CIRCLE) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[idx[t]]);
+            sh->t_kind = a.y & 15u; sh->t_w0 = a.z; sh->t_w1 = a.w;
+        }
+        __syncthreads();
+        const uint32_t t_kind = sh->t_kind, t_w0 = sh->t_w0, t_w1 = sh->t_w1;
+        if (t_kind == 0) continue;  // cannot happen for a well-formed list (uniform: every thread reads the same word)
+        float fg[4] = {0.0f, 0.0f, 0.0f, 1.0f};  // Cmd_Circle paints black (metal:491)
+        const bool stroke = t_kind == PM_REC_STROKE, fill = t_kind == PM_REC_DRAWFILL;
+        const float half_width = pm_u2f(t_w0);
+        if (t_kind != PM_REC_CIRCLE) unpack_fg(lut, t_w1, fg);
+        float al = 1.0f;  // PM_REC_SOLID: a translucent full cover
+        if (fill || stroke) {
+            const bool mine = my_item == cur_item && (my_key & 15u) <= PM_REC_LINE;
+            if (__any_sync(PM_FULL_MASK, mine)) {
+                PmRecord rc;
+                rc.p[0] = rc.p[1] = rc.p[2] = rc.p[3] = 0.0f; rc.edge_y = 0.0f;
+                if (mine) rc = load_record(A.pool, idx[t]);
+                fine_pairs(acc_w, mine, my_key & 15u, rc.p[0], rc.p[1], rc.p[2], rc.p[3], rc.edge_y, stroke, half_width + 0.5f, tile_x0, tile_y0, lane);
+            }
+            __syncthreads();
+            const int a = acc_w->acc[my_cell];
+            acc_w->acc[my_cell] = 0;
+            if (fill) {
+                const int c = acc_w->cov[my_cell];
+                acc_w->cov[my_cell] = 0;
+                int run = c;  // covers of the pixels to the left carry into this one: inclusive scan over the row's 16 lanes
+                #pragma unroll
+                for (int o = 1; o < 16; o <<= 1) {
+                    const int v = __shfl_up_sync(PM_FULL_MASK, run, o, 16);
+                    if ((int)px >= o) run += v;
+                }
+                al = pm_resolve_fill_alpha(a + run, (int)t_w0);
+            } else {
+                al = a ? pm_saturate(half_width + 0.5f - __uint_as_float(~(uint32_t)a)) : 0.0f;  // renderDf, metal:58-60
+            }
+        } else if (t_kind == PM_REC_CIRCLE) {
+            al = pm_px_circle_alpha(t_w0, t_w1, tile_x0 + (float)px, tile_y0 + (float)prow);
+        }
+        al *= fg[3];
+        c0 = mix_fma(c0, fg[0], al); c1 = mix_fma(c1, fg[1], al); c2 = mix_fma(c2, fg[2], al);
+        __syncthreads();  // the accumulators are clear again before the next item adds to them
+    }
+    *reinterpret_cast<uint32_t *>(dst) = encode_pixel<EXACT>(c0, c1, c2);
+    if (F32) *dst32 = make_float4(linear_to_srgb<EXACT>(c0), linear_to_srgb<EXACT>(c1), linear_to_srgb<EXACT>(c2), 1.0f);
+    __syncthreads();
+}
+#endif  // PM_CTA_TILES
+
 __device__ __forceinline__ uint32_t fine_batch_claim(const PmFrameArgs &A, uint32_t lane) {
     uint32_t k = 0;  // (atom.inc: see fine_claim)
     if (lane == 0) asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(k) : "l"(&A.queue->batch_next) : "memory");
@@ -823,6 +972,25 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
         A.counters_next->n_heavy = 0;
     }
     __syncwarp();
+#if PM_CTA_TILES
+    {   // costly tiles first, a whole CTA each, claimed dynamically (the CTAs that are not resident yet must not own any)
+        const uint32_t n_costly = A.counters->n_costly;
+        const bool cta_mode = n_costly != 0 && n_costly <= PM_CTA_MAX_PER_CTA * gridDim.x;
+        if (blockIdx.x == 0 && threadIdx.x == 0) A.counters_next->n_costly = 0;
+        __shared__ uint32_t s_costly;
+        __syncthreads();  // (every warp has cleared its accumulators)
+        while (cta_mode) {
+            if (threadIdx.x == 0) s_costly = atomicAdd(&A.queue->costly_next, 1u);
+            __syncthreads();
+            const uint32_t h = s_costly;
+            __syncthreads();
+            if (h >= n_costly) break;
+            fine_cta_tile<F32, EXACT>(A, reinterpret_cast<FineWarpSmem *>(s_raw), A.complex_list[2u * A.n_rows * A.n_tx + h]);
+        }
+        if (lane == 0) w->st = cta_mode ? 0x1000u : 0u;  // (the pipeline adds its own bits below)
+        __syncwarp();
+    }
+#endif
     const uint32_t batches_per_row = (A.n_tx + 31u) / 32u;
     const uint32_t n_batches = batches_per_row * A.n_rows;
     bool complex_left = true, batches_left = true;
@@ -841,7 +1009,11 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
     uint32_t b_cur = 0, b_next = 0, bp = 0;
     bool b_started = false;
 #endif
+#if PM_CTA_TILES
+    if (lane == 0) w->st = (w->st & 0x1000u) | ((blockIdx.x & (PM_FINE_SUBQ - 1u)) << 4);
+#else
     if (lane == 0) w->st = (blockIdx.x & (PM_FINE_SUBQ - 1u)) << 4;
+#endif
     __syncwarp();
     while (complex_left || batches_left) {
         const bool take_complex = complex_left && (prefer_complex || !batches_left);

@@ -385,6 +385,12 @@ struct BinSink {
             const uint32_t h = atomicAdd(&A.counters->n_heavy, 1u);
             A.complex_list[A.n_rows * A.n_tx + h] = ((tile - t) / A.n_tx << 16) | t;
         }
+#if PM_CTA_TILES
+        if (pos == PM_CTA_MIN - 1u) {  // the tile has become "costly": third list, behind the heavy one
+            const uint32_t h = atomicAdd(&A.counters->n_costly, 1u);
+            A.complex_list[2u * A.n_rows * A.n_tx + h] = ((tile - t) / A.n_tx << 16) | t;
+        }
+#endif
         if (pos == 0) {  // first record of the tile this frame: queue it for the fill kernel
             cg::coalesced_group g = cg::coalesced_threads();
             uint32_t base = 0;
@@ -433,6 +439,9 @@ __global__ void __launch_bounds__(256, PM_SEG_CTAS) k_seg(const PmFrameArgs A) {
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         A.queue->batch_next = 0;
+#if PM_CTA_TILES
+        A.queue->costly_next = 0;
+#endif
         for (int s = 0; s < PM_FINE_SUBQ; s++) A.queue->sub[s][0] = 0;
     }
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;

@@ -5,13 +5,27 @@
 
 #include "pm_pixel_logic.h"
 
+// PM_CTA_TILES (build-time, default 0 = not compiled in; NOT yet validated on a GPU -- written at the end of
+// round 1 after the GPU budget was spent, to be measured in round 2): tiles with PM_CTA_MIN..PM_CTA_CAP records
+// are listed separately by binning and, when there are few of them, rendered by a whole CTA each (one thread
+// per pixel, the eight warps sharing the coverage accumulators) before the per-warp loop starts.  A single warp
+// issues ~0.1 instructions per cycle, so such a tile takes 60-110 us on its own and bounds the frame time of a
+// narrow multi-GPU strip.  Same per-pixel arithmetic, integer coverage sums: the pixels
+// are bit-identical to the per-warp path, so the choice may depend on the strip.
+#ifndef PM_CTA_TILES
+#define PM_CTA_TILES 0
+#endif
+#define PM_CTA_MIN 24u        // records from which a tile is "costly"
+#define PM_CTA_CAP 256u       // ... and up to which the CTA path takes it (its record index lives in shared memory)
+#define PM_CTA_MAX_PER_CTA 6u // the CTA path is used when there are at most this many costly tiles per launched CTA
+
 // Per-frame counters.  Two sets alternate by frame parity so that the fill kernel of frame f can
 // clear the set frame f+1 will use (no memset node in the frame).
 struct PmBinCounters {
     uint32_t n_complex;   // tiles that own at least one record
     uint32_t n_overflow;  // records that did not fit the inline slots of their tile
     uint32_t n_heavy;     // tiles with more records than inline slots
-    uint32_t pad;
+    uint32_t n_costly;    // tiles with at least PM_CTA_MIN records (only counted when PM_CTA_TILES is compiled in)
 };
 // Work queues of the fill kernel; cleared by the binning kernel of the same frame.
 // The list of tiles with records is handed out through PM_FINE_SUBQ counters instead of one: position
@@ -20,7 +34,8 @@ struct PmBinCounters {
 #define PM_FINE_SUBQ 8
 struct PmFineQueue {
     uint32_t batch_next;    // 32-tile batches of solid tiles
-    uint32_t pad[63];
+    uint32_t costly_next;   // costly tiles, claimed by whole CTAs (PM_CTA_TILES)
+    uint32_t pad[62];
     uint32_t sub[PM_FINE_SUBQ][64];  // [s][0]: next k of sub-queue s (each on a cache line of its own)
 };
 // Written by the device into mapped host memory at the end of every frame.

@@ -138,7 +138,7 @@ int alloc_surface(pm_renderer *r) {
         PM_CUDA(cudaMalloc(&r->occ, n_tiles * sizeof(unsigned long long)));
         PM_CUDA(cudaMalloc(&r->cnt, n_tiles * sizeof(unsigned long long)));
         PM_CUDA(cudaMalloc(&r->ovf, n_tiles * sizeof(unsigned long long)));
-        PM_CUDA(cudaMalloc(&r->complex_list, 2 * n_tiles * sizeof(uint32_t)));
+        PM_CUDA(cudaMalloc(&r->complex_list, (PM_CTA_TILES ? 3 : 2) * n_tiles * sizeof(uint32_t)));  // tiles with records | heavy | costly
         r->tiles_cap = n_tiles;
     }
     if (r->fb32) { PM_CUDA(cudaFree(r->fb32)); r->fb32 = nullptr; }
