@@ -13,7 +13,7 @@
 //     enumerate (record, pixel row) pairs (Cmd_Fill / Cmd_FillEdge, metal:508-534) or as the
 //     minimum distance to the item's segments (Cmd_Line, metal:495-498);
 //   * the linear colour of the tile's 256 pixels lives in a lane-private slice of shared memory
-//     (8 pixels per lane), which keeps the kernel at 64 registers = 32 resident warps per SM;
+//     (8 pixels per lane) instead of 24 registers (the kernel runs at 80 registers, 3 CTAs per SM);
 //   * the sRGB encode and the 128-bit framebuffer stores happen once per tile.
 //
 // The kernel is issue-bound and very sensitive to its instruction footprint (L1.5 instruction cache:
@@ -28,7 +28,10 @@
 // that adds serial work to a tile with many segments lengthens the critical path); the pipeline steps
 // (fine_step1 / fine_step3) as out-of-line functions (+12 %: the call sites sit in the hot path and the ABI
 // saves ~30 live registers around each call), unlike the heavy-tile loops, the circle coverage and the
-// dry-sub-queue walk, whose move out of line took the kernel from 137 to 122 us by itself.
+// dry-sub-queue walk, whose move out of line took the kernel from 137 to 122 us by itself.  Also rejected:
+// rendering costly tiles as four independent row-band jobs (the per-item fixed cost is replicated in every band
+// and dominates those tiles: no gain on the slowest tiles, +19 % on the frame) and pruning stroke pixels that an
+// earlier segment has already saturated (+9 %: the mask bookkeeping costs more than the skipped distances).
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
