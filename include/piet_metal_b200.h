@@ -132,6 +132,12 @@ int pm_scene_row_costs(const uint8_t *scene, size_t len, uint32_t width, uint32_
                        float *cost, size_t n_rows);
 int pm_balance_strips(const float *cost, uint32_t n_rows, uint32_t n_parts, uint32_t *bounds);
 
+/* Framebuffer egress (host only; SURVEY.md 8(f) rank 4: the step after the hot path).  The reference hands
+ * its texture to MTKView (TestApp/PietRenderer.m:90-101); a headless renderer writes a file: binary PPM
+ * (alpha dropped) or PNG (8-bit RGBA, stored deflate blocks).  rgba8 as returned by pm_renderer_read_rgba8. */
+int pm_write_ppm(const char *path, const uint8_t *rgba8, uint32_t width, uint32_t height, size_t stride);
+int pm_write_png(const char *path, const uint8_t *rgba8, uint32_t width, uint32_t height, size_t stride);
+
 /* ------------------------------------------------------------------------------------------- */
 /* Renderer (CUDA, sm_100a)                                                                     */
 /* ------------------------------------------------------------------------------------------- */

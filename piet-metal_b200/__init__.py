@@ -65,8 +65,8 @@ EXPORTS = [
     "pm_encoder_new", "pm_encoder_begin_group", "pm_encoder_end_group", "pm_encoder_circle",
     "pm_encoder_stroke_line", "pm_encoder_fill", "pm_encoder_polyline", "pm_encoder_bytes", "pm_encoder_free",
     "pm_flatten_svg_path", "pm_parse_color", "pm_scene_build", "pm_scene_from_pathlist", "pm_scene_validate",
-    "pm_scene_row_costs", "pm_balance_strips",
-    "pm_scene_row_costs", "pm_balance_strips",
+    "pm_scene_row_costs", "pm_balance_strips", "pm_write_ppm", "pm_write_png",
+    "pm_scene_row_costs", "pm_balance_strips", "pm_write_ppm", "pm_write_png",
     "pm_renderer_create", "pm_renderer_destroy", "pm_renderer_resize", "pm_renderer_set_strip",
     "pm_renderer_set_scene", "pm_renderer_set_scene_device", "pm_renderer_render", "pm_renderer_set_frame_events", "pm_renderer_sync",
     "pm_renderer_read_rgba8", "pm_renderer_render_host", "pm_renderer_framebuffer", "pm_renderer_stream",
@@ -107,6 +107,8 @@ def _lib():
         "pm_scene_validate": (cint, [vp, sz]),
         "pm_scene_row_costs": (cint, [vp, sz, u32, u32, vp, sz]),
         "pm_balance_strips": (cint, [vp, u32, u32, vp]),
+        "pm_write_ppm": (cint, [ctypes.c_char_p, vp, u32, u32, sz]),
+        "pm_write_png": (cint, [ctypes.c_char_p, vp, u32, u32, sz]),
         "pm_renderer_create": (cint, [ctypes.POINTER(vp), ctypes.POINTER(Config)]),
         "pm_renderer_destroy": (None, [vp]),
         "pm_renderer_resize": (cint, [vp, u32, u32]),
@@ -376,6 +378,13 @@ def balanced_strip_bounds(cost, world_size):
     bounds = np.zeros(world_size + 1, np.uint32)
     _check(_lib().pm_balance_strips(_ptr(cost), cost.size, world_size, _ptr(bounds)), "pm_balance_strips")
     return [int(b) for b in bounds]
+
+
+def write_image(path, rgba8):
+    """pm_write_png / pm_write_ppm (by extension) of an (H, W, 4) uint8 array."""
+    img = np.ascontiguousarray(rgba8, np.uint8)
+    fn = _lib().pm_write_ppm if str(path).lower().endswith(".ppm") else _lib().pm_write_png
+    _check(fn(str(path).encode(), _ptr(img), img.shape[1], img.shape[0], img.strides[0]), "pm_write_image")
 
 
 def strip_bounds(n_tile_rows, world_size):

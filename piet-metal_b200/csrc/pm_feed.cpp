@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <cstdio>
 #include <vector>
 
 #include "../../include/piet_metal_b200.h"
@@ -959,6 +960,89 @@ int pm_balance_strips(const float *cost, uint32_t n_rows, uint32_t n_parts, uint
     }
     bounds[n_parts] = n_rows;
     return PM_OK;
+}
+
+// ---- framebuffer egress (host only): the step after the hot path -------------
+// The reference hands its texture to MTKView; a headless renderer needs a file.  PPM (P6, alpha dropped) and
+// PNG (8-bit RGBA, stored deflate blocks: no compression library needed).
+static uint32_t crc32_update(uint32_t crc, const uint8_t *p, size_t n) {
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t i = 0; i < 256; i++) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; k++) c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+        init = true;
+    }
+    for (size_t i = 0; i < n; i++) crc = table[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
+    return crc;
+}
+static void put_be32(std::vector<uint8_t> &v, uint32_t x) { v.push_back(x >> 24); v.push_back(x >> 16); v.push_back(x >> 8); v.push_back(x); }
+static void png_chunk(std::vector<uint8_t> &out, const char *type, const std::vector<uint8_t> &data) {
+    put_be32(out, (uint32_t)data.size());
+    const size_t start = out.size();
+    out.insert(out.end(), type, type + 4);
+    out.insert(out.end(), data.begin(), data.end());
+    put_be32(out, crc32_update(0xffffffffu, out.data() + start, out.size() - start) ^ 0xffffffffu);
+}
+
+int pm_write_ppm(const char *path, const uint8_t *rgba8, uint32_t width, uint32_t height, size_t stride) {
+    if (!path || !rgba8 || width == 0 || height == 0 || stride < (size_t)width * 4) return PM_ERR_INVALID_ARG;
+    FILE *f = fopen(path, "wb");
+    if (!f) return PM_ERR_INVALID_ARG;
+    fprintf(f, "P6\n%u %u\n255\n", width, height);
+    std::vector<uint8_t> row((size_t)width * 3);
+    for (uint32_t y = 0; y < height; y++) {
+        const uint8_t *src = rgba8 + (size_t)y * stride;
+        for (uint32_t x = 0; x < width; x++) { row[3 * x] = src[4 * x]; row[3 * x + 1] = src[4 * x + 1]; row[3 * x + 2] = src[4 * x + 2]; }
+        if (fwrite(row.data(), 1, row.size(), f) != row.size()) { fclose(f); return PM_ERR_INVALID_ARG; }
+    }
+    return fclose(f) == 0 ? PM_OK : PM_ERR_INVALID_ARG;
+}
+
+int pm_write_png(const char *path, const uint8_t *rgba8, uint32_t width, uint32_t height, size_t stride) {
+    if (!path || !rgba8 || width == 0 || height == 0 || stride < (size_t)width * 4) return PM_ERR_INVALID_ARG;
+    // raw scanlines: filter byte 0 + RGBA
+    const size_t line = (size_t)width * 4 + 1, raw_len = line * height;
+    std::vector<uint8_t> idat;
+    idat.reserve(raw_len + raw_len / 65535 * 5 + 16);
+    idat.push_back(0x78); idat.push_back(0x01);  // zlib header, no compression
+    uint32_t a = 1, b = 0;                        // Adler-32 of the raw data
+    std::vector<uint8_t> raw(line);
+    size_t block_left = 0, done = 0;
+    for (uint32_t y = 0; y < height; y++) {
+        raw[0] = 0;
+        memcpy(raw.data() + 1, rgba8 + (size_t)y * stride, (size_t)width * 4);
+        for (size_t i = 0; i < line; i++) { a = (a + raw[i]) % 65521u; b = (b + a) % 65521u; }
+        size_t off = 0;
+        while (off < line) {
+            if (block_left == 0) {  // new stored block of at most 65535 bytes
+                const size_t remaining = raw_len - done;
+                const size_t len = remaining < 65535 ? remaining : 65535;
+                idat.push_back(len == remaining ? 1 : 0);  // BFINAL on the last one, BTYPE = 00
+                idat.push_back(len & 0xff); idat.push_back(len >> 8);
+                idat.push_back(~len & 0xff); idat.push_back((~len >> 8) & 0xff);
+                block_left = len;
+            }
+            const size_t take = std::min(block_left, line - off);
+            idat.insert(idat.end(), raw.begin() + off, raw.begin() + off + take);
+            off += take; block_left -= take; done += take;
+        }
+    }
+    put_be32(idat, (b << 16) | a);
+    std::vector<uint8_t> out = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    std::vector<uint8_t> ihdr;
+    put_be32(ihdr, width); put_be32(ihdr, height);
+    ihdr.push_back(8); ihdr.push_back(6); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);  // 8-bit RGBA, no interlace
+    png_chunk(out, "IHDR", ihdr);
+    png_chunk(out, "IDAT", idat);
+    png_chunk(out, "IEND", std::vector<uint8_t>());
+    FILE *f = fopen(path, "wb");
+    if (!f) return PM_ERR_INVALID_ARG;
+    const bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+    return (fclose(f) == 0 && ok) ? PM_OK : PM_ERR_INVALID_ARG;
 }
 
 }  // extern "C"

@@ -97,3 +97,37 @@ def test_synthetic_scenes_are_deterministic(pm):
     assert np.array_equal(a, b) and not np.array_equal(a, c)
     g = pm.build_scene(pm.SCENE_GLYPHS, 512, 512, count=300)
     assert int(g[:4].view(np.uint32)[0]) == 300 and pm.validate_scene(g) == 0
+
+
+def test_png_and_ppm_egress_round_trip(pm, oracle, tmp_path):
+    """pm_write_png / pm_write_ppm: decode what was written (PNG by hand: signature, chunk CRCs, zlib stream)."""
+    import struct
+    import zlib
+    w, h = 70, 37
+    scene = pm.build_scene(pm.SCENE_TIGER, 128, 128)
+    img = oracle.render(scene, 128, 128)["rgba8"][:h, :w].copy()
+    png, ppm = str(tmp_path / "t.png"), str(tmp_path / "t.ppm")
+    pm.write_image(png, img)
+    pm.write_image(ppm, img)
+    data = open(png, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, chunks = 8, {}
+    while pos < len(data):
+        n, typ = struct.unpack(">I4s", data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(typ + body)
+        chunks[typ] = body
+        pos += 12 + n
+    assert struct.unpack(">IIBBBBB", chunks[b"IHDR"]) == (w, h, 8, 6, 0, 0, 0)
+    raw = np.frombuffer(zlib.decompress(chunks[b"IDAT"]), np.uint8).reshape(h, 1 + 4 * w)
+    assert (raw[:, 0] == 0).all() and np.array_equal(raw[:, 1:].reshape(h, w, 4), img)
+    p = open(ppm, "rb").read()
+    header = b"P6\n%d %d\n255\n" % (w, h)
+    assert p.startswith(header) and np.array_equal(np.frombuffer(p[len(header):], np.uint8).reshape(h, w, 3), img[:, :, :3])
+    # a frame larger than one stored block (65535 bytes)
+    big = np.arange(300 * 200 * 4, dtype=np.uint32).astype(np.uint8).reshape(200, 300, 4)
+    pm.write_image(png, big)
+    d = open(png, "rb").read()
+    i = d.index(b"IDAT")
+    n = struct.unpack(">I", d[i - 4:i])[0]
+    assert np.array_equal(np.frombuffer(zlib.decompress(d[i + 4:i + 4 + n]), np.uint8).reshape(200, 1201)[:, 1:].reshape(200, 300, 4), big)
