@@ -203,6 +203,26 @@ int run_plan(pm_renderer *r) {
                           r->piece_info, (uint32_t)r->piece_cap, r->stream);
     PM_CUDA(cudaGetLastError());
     r->n_pieces = res.n_pieces;
+    if (getenv("PM_L2_PERSIST")) {
+        // Experiment switch (off by default, to be measured): keep the k_seg work list resident in L2 across
+        // frames.  Every frame streams its whole framebuffer through L2, so the plan-time tables are read from
+        // DRAM again each time (k_seg: 30 % L2 hit rate, latency bound).
+        int max_persist = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, r->device);
+        const size_t bytes = std::min<size_t>((size_t)r->n_pieces * sizeof(uint2), (size_t)std::max(max_persist, 0));
+        if (bytes) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes);
+            cudaStreamAttrValue v;
+            memset(&v, 0, sizeof v);
+            v.accessPolicyWindow.base_ptr = r->piece_info;
+            v.accessPolicyWindow.num_bytes = bytes;
+            v.accessPolicyWindow.hitRatio = 1.0f;
+            v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(r->stream, cudaStreamAttributeAccessPolicyWindow, &v);
+            cudaGetLastError();
+        }
+    }
     if (getenv("PM_DEBUG_SEG") || getenv("PM_DEBUG_FINE")) {
         if (r->debug) cudaFree(r->debug);
         PM_CUDA(cudaMalloc(&r->debug, (size_t)(1u << 20) * 8));
