@@ -123,9 +123,11 @@ int alloc_surface(pm_renderer *r) {
     const size_t pitch = (size_t)r->n_tx * PM_TILE_W * 4;
     const size_t fb_bytes = pitch * n_rows * PM_TILE_H;
     PM_CUDA(cudaStreamSynchronize(r->stream));
+    r->have_surface = false;  // until every buffer below exists
     if (fb_bytes > r->fb_cap) {
         if (r->fb) PM_CUDA(cudaFree(r->fb));
         r->fb = nullptr;
+        r->fb_cap = 0;
         PM_CUDA(cudaMalloc(&r->fb, fb_bytes));
         r->fb_cap = fb_bytes;
     }
@@ -135,6 +137,7 @@ int alloc_surface(pm_renderer *r) {
         if (r->ovf) PM_CUDA(cudaFree(r->ovf));
         if (r->complex_list) PM_CUDA(cudaFree(r->complex_list));
         r->occ = r->cnt = r->ovf = nullptr; r->complex_list = nullptr;
+        r->tiles_cap = 0;
         PM_CUDA(cudaMalloc(&r->occ, n_tiles * sizeof(unsigned long long)));
         PM_CUDA(cudaMalloc(&r->cnt, n_tiles * sizeof(unsigned long long)));
         PM_CUDA(cudaMalloc(&r->ovf, n_tiles * sizeof(unsigned long long)));
@@ -249,6 +252,7 @@ int run_plan(pm_renderer *r) {
 // Enqueue one frame.  debug_f32 also writes the fp32 parity buffer.
 int enqueue_frame(pm_renderer *r, bool debug_f32) {
     if (!r->have_scene || !r->have_surface) return PM_ERR_STATE;
+    if (!r->pool || !r->fb) { g_last_error = "surface allocation failed earlier"; return PM_ERR_NOMEM; }
     if (r->plan_dirty) { int st = run_plan(r); if (st != PM_OK) return st; }
     const size_t n_tiles = strip_tiles(r);
     r->stamp++;
