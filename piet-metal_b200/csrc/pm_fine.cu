@@ -59,6 +59,9 @@ typedef unsigned long long u64;
 #ifndef PM_FINE_TIMELINE
 #define PM_FINE_TIMELINE 0       // 1 (debug builds, tools/fine_timeline.py): per-warp timestamps into PmFrameArgs::debug
 #endif
+#ifndef PM_FINE_BULK
+#define PM_FINE_BULK 0           // 1 (NOT yet validated on a GPU; tools/cta_check.sh): the tile prefetch as TMA bulk copies
+#endif                           //    (cp.async.bulk + mbarrier, UBLKCP in SASS) instead of 35 cp.async (LDGSTS) per tile
 #ifndef PM_FINE_EARLY_CLAIM
 #define PM_FINE_EARLY_CLAIM 0    // 1: the next-but-one tile is claimed at the start of a tile; 0: before the encode
 #endif
@@ -83,7 +86,12 @@ struct FineWarpSmem {
     int cov[256];
     float4 rgb[3][2][32];
     uint4 rec[2][2 * PM_TILE_SLOTS];
+#if PM_FINE_BULK
+    u64 hdr[2][6];   // per buffer: the aligned 16-byte pairs that contain the tile's cnt / occ / ovf words
+    u64 mbar[2];     // per buffer: transaction barrier of the bulk copies (phase bits: w->st bits 14, 15)
+#else
     u64 hdr[2][4];
+#endif
     uint32_t idx[PM_FINE_LIST_CAP];  // heavy tiles: pool indices of the overflow records ...
     uint2 ovk[PM_FINE_LIST_CAP];     // ... and their (item, key), so that only the geometry is read from global memory
     uint32_t pkq[2];  // pipeline state of the walk over the tile list (see fine_entry)
@@ -125,6 +133,35 @@ __device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// the k-th header word (0 cnt, 1 occ, 2 ovf) of the tile prefetched into buffer p
+#if PM_FINE_BULK
+#define FINE_HDR(w, p, k, tile) ((w)->hdr[p][2 * (k) + ((tile) & 1u)])
+// TMA bulk copies (non-tensor): global -> shared, completion signalled on an mbarrier as a byte count.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, uint32_t bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#else
+#define FINE_HDR(w, p, k, tile) ((w)->hdr[p][k])
+#endif
 
 // metal:563.  The debug render and PM_FLAG_EXACT_SRGB use this form.
 template <bool EXACT>
@@ -375,9 +412,20 @@ __device__ __forceinline__ void fine_entry(const PmFrameArgs &A, uint32_t claim,
 // Starts the copy of a tile's header words and inline record slots into buffer `p`.
 __device__ __forceinline__ void fine_prefetch(const PmFrameArgs &A, FineWarpSmem *w, uint32_t p, uint32_t pk, uint32_t lane) {
     const size_t tile = (size_t)(pk >> 16) * A.n_tx + (pk & 0xffffu);
+#if PM_FINE_BULK
+    if (lane == 0) {  // one thread arms the barrier with the byte count and issues the four copies
+        const size_t pair = tile & ~(size_t)1;  // the header words are 8 bytes: fetch the aligned 16-byte pair that holds each
+        mbar_expect_tx(&w->mbar[p], PM_TILE_SLOTS * (uint32_t)sizeof(PmRecord) + 48u);
+        bulk_g2s(&w->rec[p][0], &A.pool[tile * PM_TILE_SLOTS], PM_TILE_SLOTS * (uint32_t)sizeof(PmRecord), &w->mbar[p]);
+        bulk_g2s(&w->hdr[p][0], &A.cnt[pair], 16u, &w->mbar[p]);
+        bulk_g2s(&w->hdr[p][2], &A.occ[pair], 16u, &w->mbar[p]);
+        bulk_g2s(&w->hdr[p][4], &A.ovf[pair], 16u, &w->mbar[p]);
+    }
+#else
     cp_async16(&w->rec[p][lane], reinterpret_cast<const uint4 *>(&A.pool[tile * PM_TILE_SLOTS]) + lane);
     if (lane < 3) cp_async8(&w->hdr[p][lane], lane == 0 ? &A.cnt[tile] : (lane == 1 ? &A.occ[tile] : &A.ovf[tile]));
     cp_async_commit();
+#endif
 }
 // Pipeline step, part 1 (once the tile's own set-up is done): the next tile's list entry, requested
 // when the previous tile was stored, has arrived; start the copy of that tile's data.
@@ -412,9 +460,13 @@ __device__ __noinline__ float4 fine_circle_alpha4(uint32_t bbox_lo, uint32_t bbo
 // Indexes the overflow records: the extension block (positions 16..63, contiguous) and the chain behind it.
 // w->n_over counts what was actually found (a frame whose overflow pool ran out has fewer records than cnt
 // says; the host re-renders such a frame, it only must not fault).
+#if PM_FINE_BULK
+__device__ __noinline__ void fine_heavy_index(const PmFrameArgs &A, FineWarpSmem *w, uint32_t p, uint32_t n, uint32_t lane, uint32_t hdr_tile) {
+#else
 __device__ __noinline__ void fine_heavy_index(const PmFrameArgs &A, FineWarpSmem *w, uint32_t p, uint32_t n, uint32_t lane) {
+#endif
     uint32_t n_over = 0, tail = 0;
-    const u64 vw = w->hdr[p][2];
+    const u64 vw = FINE_HDR(w, p, 2, hdr_tile);
     uint32_t base1 = (uint32_t)(vw >> 32) == A.stamp ? (uint32_t)vw : 0u;
     if (base1 == PM_EXT_FAILED) base1 = 0;
     if (base1) {
@@ -523,17 +575,26 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
     const uint32_t packed_tile = w->pkq[p];
     const bool skip_heavy = (w->st & FINE_ST_FULL(p)) != 0;
     const uint32_t trow = packed_tile >> 16, tx = packed_tile & 0xffffu;
+#if PM_FINE_BULK
+    const uint32_t hdr_tile = trow * A.n_tx + tx;
+    {   // the bulk copies of this tile have landed (phase bit of the buffer: w->st bit 14 + p)
+        const uint32_t st = w->st;
+        mbar_wait(&w->mbar[p], (st >> (14u + p)) & 1u);
+        __syncwarp();
+        w->st = st ^ (1u << (14u + p));
+    }
+#endif
 #if PM_FINE_EARLY_CLAIM
     const uint32_t claim = fine_step2(A, w, p, lane);
 #endif
     const uint4 *rec = w->rec[p];
-    const u64 cw = w->hdr[p][0], ow = w->hdr[p][1];
+    const u64 cw = FINE_HDR(w, p, 0, hdr_tile), ow = FINE_HDR(w, p, 1, hdr_tile);
     const uint32_t n = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
     const uint32_t occ_item1 = (uint32_t)(ow >> 32) == A.stamp ? (uint32_t)ow : 0u;
     const bool heavy = n > PM_TILE_SLOTS;
 #if PM_CTA_TILES
     const bool by_cta = (w->st & 0x1000u) != 0 && n >= PM_CTA_MIN && n <= PM_CTA_CAP &&
-                        (uint32_t)(w->hdr[p][2] >> 32) == A.stamp && (uint32_t)w->hdr[p][2] != PM_EXT_FAILED;  // the test of fine_cta_tile
+                        (uint32_t)(FINE_HDR(w, p, 2, hdr_tile) >> 32) == A.stamp && (uint32_t)FINE_HDR(w, p, 2, hdr_tile) != PM_EXT_FAILED;  // the test of fine_cta_tile
     if ((heavy && skip_heavy) || by_cta) {
 #else
     if (heavy && skip_heavy) {  // pass 1 rendered it
@@ -551,7 +612,11 @@ __device__ __forceinline__ void fine_complex_tile(const PmFrameArgs &A, FineWarp
     if (occ_item1) occ_rgba = __ldg(reinterpret_cast<const uint32_t *>(A.scene + A.items_ix + (size_t)(occ_item1 - 1u) * PM_ITEM_SIZE + PM_FILL_RGBA));
 
     const uint32_t n_inline = n < PM_TILE_SLOTS ? n : PM_TILE_SLOTS;
+#if PM_FINE_BULK
+    if (heavy) fine_heavy_index(A, w, p, n, lane, hdr_tile);
+#else
     if (heavy) fine_heavy_index(A, w, p, n, lane);
+#endif
 
     // this lane's inline record: item and key stay in registers, the geometry is re-read when needed
     uint32_t my_item = 0xffffffffu, my_key = 0;
@@ -962,6 +1027,14 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FineWarpSmem *w = reinterpret_cast<FineWarpSmem *>(s_raw) + warp;
     for (uint32_t i = lane; i < 256; i += 32) { w->acc[i] = 0; w->cov[i] = 0; }
+#if PM_FINE_BULK
+    if (lane == 0) {
+        mbar_init(&w->mbar[0], 1);
+        mbar_init(&w->mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+#endif
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // (programmatic dependent launch, see pm_kernels.cu)
     asm volatile("griddepcontrol.wait;" ::: "memory");               // binning has finished
     const uint32_t n_complex = A.counters->n_complex, n_heavy = A.counters->n_heavy;
