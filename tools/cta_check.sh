@@ -1,6 +1,7 @@
 #!/bin/bash
 # Round-2 starting point: validate and measure the CTA-cooperative path for costly tiles (PM_CTA_TILES, written at
-# the end of round 1 without GPU time left).  Run under gpurun from the repo root after `make -C piet-metal_b200 cta`.
+# the end of round 1 without GPU time left).  Run under gpurun from the repo root after `make -C piet-metal_b200 cta`
+# (CTA_FLAGS="-DPM_FINE_BULK=1" or "-DPM_CTA_TILES=1 -DPM_FINE_BULK=1" for the TMA bulk-copy prefetch).
 set -u
 V=$PWD/piet-metal_b200/variants/libpiet_metal_b200_cta.so
 [ -f "$V" ] || { echo "build it first: make -C piet-metal_b200 cta"; exit 1; }
