@@ -354,7 +354,7 @@ def main():
                          "bin_kernel_ms": (ms_sum - ms_fine_sum) / args.steps},
             "frame_stats": {"overflow_records": st.n_overflow_records, "complex_tiles": st.n_complex_tiles, "tiles": st.n_tiles},
         }
-        if not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline:  # (the CPU leg is timed at N=1 only)
             v, desc, threads = cpu_sample(scene_host, size, args.cpu_rows)
             out["cpu_baseline"] = {"value": v, "unit": "Mpixel/s", "cores": threads, "kind": "port", "sample": desc}
     r.close()
