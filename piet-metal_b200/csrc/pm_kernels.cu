@@ -3,7 +3,8 @@
 //   k_validate     bounds/finite check of an uploaded scene                      (the reference has none)
 //   k_plan         per-item prefixes: segments, (tile row, 32-tile chunk) units of k_row, backdrop-scratch
 //                  words; item table                                              (once per scene/size/strip)
-//   k_plan_pieces  per segment: the conservative list of (tile row, candidate tile) "pieces" = k_seg threads
+//   k_pieces_*     per segment: the conservative list of (tile row, candidate tile) "pieces" = k_seg threads
+//                  (count, prefix, fill: three kernels)
 //   k_seg          one thread per piece: the exact tile tests of TestApp/PietRender.metal:248-445 for one
 //                  segment and one tile; appends per-tile records, accumulates the row's backdrop deltas
 //   k_row          one warp per (item, tile row, 32-tile chunk): prefix-sums the backdrop deltas and closes

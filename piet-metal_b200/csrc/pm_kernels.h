@@ -58,8 +58,8 @@ struct PmFrameArgs {
     uint32_t items_ix;
     const unsigned long long *plan_a;  // per item: rows-before << 32 | segments-before (n_items + 1 entries)
     const unsigned long long *plan_b;  // per item: backdrop-scratch words before it
-    const uint2 *piece_info;           // per k_seg thread: segment, flags | tile row << 15 | tile column (k_plan_pieces)
-    const PmSegInfo *seg_info;         // per segment (k_plan_pieces)
+    const uint2 *piece_info;           // per k_seg thread: segment, flags | tile row << 15 | tile column (k_pieces_*)
+    const PmSegInfo *seg_info;         // per segment (k_pieces_*)
     const PmItemInfo *item_info;       // per item (k_plan)
     const uint2 *row_info;             // per k_row unit: item, tile row << 16 | 32-tile chunk
     uint32_t n_segments;        // segments of the Fill / Poly items that touch the strip
