@@ -417,7 +417,7 @@ struct BinSink {
     }
 };
 
-// One thread per piece (see k_plan_pieces): the exact tile tests of TestApp/PietRender.metal:248-445
+// One thread per piece (see k_pieces_count / k_pieces_fill): the exact tile tests of TestApp/PietRender.metal:248-445
 // of one segment for one candidate tile; the first piece of a (segment, tile row) also adds the
 // row's backdrop intervals.
 #ifndef PM_SEG_CTAS
