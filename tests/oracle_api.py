@@ -99,3 +99,60 @@ def tile_cmds(scene, tx, ty, flags=0):
 
 def max_threads():
     return _load(ORACLE_PATH).pmo_max_threads()
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle/_ref: the reference's own PietRender.metal compiled for the CPU (oracle/metal_shim/)
+# ---------------------------------------------------------------------------------------------
+REF_PATH = os.path.join(ROOT, "oracle", "_ref", "libpm_ref.so")
+REF_HALF_PATH = os.path.join(ROOT, "oracle", "_ref", "libpm_ref_half.so")
+REF_TILE_BUF = 4096
+# bytes of a 24-byte Cmd that its tag defines (GenTypes.h:340-495); the rest is padding the reference never writes
+CMD_FIELDS = {1: [], 9: [], 2: [(8, 16)], 3: [(8, 24)], 4: [(8, 24)], 5: [(4, 12)], 6: [(4, 12)], 7: [(4, 12)], 8: [(4, 8)]}
+
+
+def have_ref(half=False):
+    return os.path.exists(REF_HALF_PATH if half else REF_PATH)
+
+
+def ref_render(scene, width, height, threads=0, half=False, want_cmds=False):
+    """The reference's shaders (tileKernel, renderKernel, vertex/fragment composite) run by
+    oracle/metal_shim/ref_driver.cpp.  Surfaces up to 4096 x 4096; n_cmds[tile] == -1 marks a tile whose
+    list overflowed its 4096 bytes (the reference does not check) -- see `ref_trusted_tiles`."""
+    lib = _load(REF_HALF_PATH if half else REF_PATH)
+    scene = np.ascontiguousarray(scene, np.uint8)
+    nty, ntx = (height + 15) // 16, (width + 15) // 16
+    rgba8 = np.zeros((height, width, 4), np.uint8)
+    f32 = np.zeros((height, width, 4), np.float32)
+    solid = np.zeros(ntx * nty, np.uint32)
+    n_cmds = np.zeros(ntx * nty, np.int32)
+    cmds = np.zeros((ntx * nty, REF_TILE_BUF), np.uint8) if want_cmds else None
+    rc = lib.pmref_render(_vp(scene), ctypes.c_size_t(scene.size), ctypes.c_uint32(width), ctypes.c_uint32(height), ctypes.c_int(threads),
+                          _vp(rgba8), _vp(f32), _vp(solid), _vp(n_cmds), _vp(cmds))
+    if rc != 0:
+        raise ValueError("oracle/_ref rejected the frame (rc=%d): larger than 4096 x 4096?" % rc)
+    out = {"rgba8": rgba8, "rgba32f": f32, "solid": solid, "n_cmds": n_cmds}
+    if want_cmds:
+        out["cmds"] = cmds
+    return out
+
+
+def ref_trusted_tiles(n_cmds):
+    """Tiles whose command buffer is intact: neither overflowed nor overwritten by the left neighbour's overflow."""
+    bad = n_cmds < 0
+    excl = bad.copy()
+    excl[1:] |= bad[:-1]
+    return ~excl
+
+
+def canonical_cmds(cmds):
+    """A Cmd stream (CMD_DTYPE array or raw bytes) with every byte its tags do not define set to zero."""
+    raw = np.ascontiguousarray(cmds).view(np.uint8).reshape(-1, 24)
+    out = np.zeros_like(raw)
+    out[:, 0:4] = raw[:, 0:4]
+    tags = raw[:, 0:4].copy().view(np.uint32).reshape(-1)
+    for tag, spans in CMD_FIELDS.items():
+        rows = tags == tag
+        for a, b in spans:
+            out[rows, a:b] = raw[rows, a:b]
+    return out
