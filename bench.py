@@ -347,12 +347,12 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": fb_bytes,
                     "steps": args.e2e_steps, "call": "pm_renderer_render_host (pinned host buffers)"},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": int(st.n_launches) * args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_fine (fill/blend)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": fine_ms,
-                         "bin_kernel_ms": (ms_sum - ms_fine_sum) / args.steps},
-            "frame_stats": {"overflow_records": st.n_overflow_records, "complex_tiles": st.n_complex_tiles, "tiles": st.n_tiles},
+                         "bin_kernel_ms": st.ms_bin_sum / max(1, st.frames), "heavy_kernel_ms": st.ms_heavy_sum / max(1, st.frames)},
+            "frame_stats": {"overflow_records": st.n_overflow_records, "complex_tiles": st.n_complex_tiles, "heavy_tiles": st.n_heavy_tiles, "tiles": st.n_tiles},
         }
         if world == 1 and not args.no_cpu_baseline:  # (the CPU leg is timed at N=1 only)
             v, desc, threads = cpu_sample(scene_host, size, args.cpu_rows)

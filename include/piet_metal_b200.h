@@ -118,7 +118,9 @@ typedef struct pm_scene_desc {
 int64_t pm_scene_build(const pm_scene_desc *desc, uint8_t *buf, size_t cap);
 /* Same as make_tiger but for an arbitrary "path list" text (see tools/make_tiger_fixture.py). */
 int64_t pm_scene_from_pathlist(const char *text, size_t len, double scale, uint8_t *buf, size_t cap);
-/* Bounds-checks every ref/count of an encoded scene (the reference never does). */
+/* Bounds-checks every ref/count of an encoded scene (the reference never does).  items_ix and every points_ix
+ * must be multiples of 8 -- what the reference's encoder produces (src/lib.rs:132-163, :224-240); the kernels read
+ * points with 64-bit loads. */
 int pm_scene_validate(const uint8_t *scene, size_t len);
 
 /* Multi-GPU row-strip shard (host only).  The reference is single-device; tiles are independent
@@ -160,7 +162,7 @@ typedef struct pm_config {
 typedef struct pm_frame_stats {
     float ms_total;          /* device time of the last frame (CUDA events on the render stream) */
     float ms_bin;            /*   its binning kernel */
-    float ms_fine;           /*   its fill/blend kernel */
+    float ms_fine;           /*   its fill/blend kernel (k_fine: the kernel that stores the framebuffer) */
     uint32_t frames;         /* frames enqueued since the previous sync that the sums below cover */
     float ms_total_sum;      /* the same three times summed over those frames */
     float ms_bin_sum;
@@ -170,6 +172,10 @@ typedef struct pm_frame_stats {
     uint32_t n_complex_tiles;/* tiles that own at least one record (last frame) */
     uint32_t n_launches;     /* kernels launched per frame */
     uint32_t retries;        /* re-renders after growing the record pool */
+    float ms_heavy;          /* device time of the heavy-tile kernel of the last frame (it is part of neither ms_bin nor
+                                ms_fine; with frame events off it runs beside the fill/blend kernel) */
+    float ms_heavy_sum;
+    uint32_t n_heavy_tiles;  /* tiles with more records than inline slots (last frame) */
 } pm_frame_stats;
 
 int pm_renderer_create(pm_renderer **out, const pm_config *cfg);

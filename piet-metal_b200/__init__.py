@@ -51,7 +51,8 @@ class FrameStats(ctypes.Structure):
     _fields_ = [("ms_total", ctypes.c_float), ("ms_bin", ctypes.c_float), ("ms_fine", ctypes.c_float),
                 ("frames", ctypes.c_uint32), ("ms_total_sum", ctypes.c_float), ("ms_bin_sum", ctypes.c_float),
                 ("ms_fine_sum", ctypes.c_float), ("n_tiles", ctypes.c_uint32), ("n_overflow_records", ctypes.c_uint32),
-                ("n_complex_tiles", ctypes.c_uint32), ("n_launches", ctypes.c_uint32), ("retries", ctypes.c_uint32)]
+                ("n_complex_tiles", ctypes.c_uint32), ("n_launches", ctypes.c_uint32), ("retries", ctypes.c_uint32),
+                ("ms_heavy", ctypes.c_float), ("ms_heavy_sum", ctypes.c_float), ("n_heavy_tiles", ctypes.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -65,7 +66,6 @@ EXPORTS = [
     "pm_encoder_new", "pm_encoder_begin_group", "pm_encoder_end_group", "pm_encoder_circle",
     "pm_encoder_stroke_line", "pm_encoder_fill", "pm_encoder_polyline", "pm_encoder_bytes", "pm_encoder_free",
     "pm_flatten_svg_path", "pm_parse_color", "pm_scene_build", "pm_scene_from_pathlist", "pm_scene_validate",
-    "pm_scene_row_costs", "pm_balance_strips", "pm_write_ppm", "pm_write_png",
     "pm_scene_row_costs", "pm_balance_strips", "pm_write_ppm", "pm_write_png",
     "pm_renderer_create", "pm_renderer_destroy", "pm_renderer_resize", "pm_renderer_set_strip",
     "pm_renderer_set_scene", "pm_renderer_set_scene_device", "pm_renderer_render", "pm_renderer_set_frame_events", "pm_renderer_sync",

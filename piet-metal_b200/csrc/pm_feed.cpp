@@ -836,13 +836,13 @@ int pm_scene_validate(const uint8_t *scene, size_t len) {
     memcpy(&g, scene, sizeof g);
     uint64_t n = g.n_items;
     if (PM_GROUP_HEADER_SIZE + n * PM_BBOX_SIZE > len) return PM_ERR_SCENE_MALFORMED;
-    if ((g.items_ix & 3u) || (uint64_t)g.items_ix + n * PM_ITEM_SIZE > len) return PM_ERR_SCENE_MALFORMED;
+    if ((g.items_ix & 7u) || (uint64_t)g.items_ix + n * PM_ITEM_SIZE > len) return PM_ERR_SCENE_MALFORMED;
     for (uint64_t i = 0; i < n; i++) {
         pm_item_any it;
         memcpy(&it, scene + g.items_ix + i * PM_ITEM_SIZE, sizeof it);
         if (it.tag == PM_ITEM_FILL || it.tag == PM_ITEM_POLY) {
             uint32_t np = it.body[2], pix = it.body[3];  // n_points @12, points_ix @16 in both variants
-            if (np == 0 || (pix & 3u) || (uint64_t)pix + (uint64_t)np * 8 > len) return PM_ERR_SCENE_MALFORMED;
+            if (np == 0 || (pix & 7u) || (uint64_t)pix + (uint64_t)np * 8 > len) return PM_ERR_SCENE_MALFORMED;
         }
     }
     return PM_OK;

@@ -1,0 +1,365 @@
+// k_heavy: fill/blend of the tiles with more records than k_fine takes (PM_HEAVY_MIN = 17: more than the inline slots;
+// sm_100a), one CTA per tile.
+// Same arithmetic as k_fine (renderKernel, TestApp/PietRender.metal:457-566; pm_cover.cuh, pm_pixel_logic.h), other
+// decomposition: such a tile has tens to thousands of records -- coincident outlines, deep stacks of translucent
+// layers, a whole drawing squeezed into a few tiles -- and on one warp it is the frame's critical path (a warp
+// issues ~0.1 instructions per cycle: 60-110 us for the tiger's worst tiles at 8192^2, milliseconds at 256^2).
+//
+// Per tile, 8 warps:
+//   1. the tile's records (inline slots + the chain of overflow blocks, pm_pixel_logic.h) are keyed
+//      (item, trailer first, position) and sorted in shared memory (bitonic): the records of an item become a
+//      contiguous run, the runs are in painter's order;
+//   2. the items are taken eight at a time: warp w accumulates the coverage of item 8 g + w into its own coverage
+//      arrays (compositing is ordered, coverage is not: the eight items are independent);
+//   3. thread t owns pixel (t / 16, t % 16) with its linear colour in three registers and blends the eight layers
+//      in order; encode and store once per tile.
+// A tile with more than PM_HEAVY_SORT_CAP records (a 16x16-pixel tile crossed by > 4096 segments) is drawn without
+// the sort: one pass over all its records per item (correct, slow, never seen outside of stress tests).
+// Integer coverage sums and the same per-pixel functions as k_fine: which kernel draws a tile does not change a
+// single bit of its pixels.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/piet_metal_b200.h"
+#include "pm_cover.cuh"
+#include "pm_kernels.h"
+#include "pm_pixel_logic.h"
+#include "pm_scene_format.h"
+
+namespace {
+
+typedef unsigned long long u64;
+
+#define PM_HEAVY_WARPS 8
+#define PM_HEAVY_THREADS (PM_HEAVY_WARPS * 32)
+#define PM_HEAVY_SORT_CAP 4096u
+#define PM_HEAVY_DIR_CAP 128u   // overflow blocks indexed per tile: 1488 + 123 * 768 slots ~ 96 k records; the rest is not drawn
+
+struct HeavyMeta { uint32_t kind, w0, w1, pad; float4 paint; };
+
+struct HeavySmem {
+    int acc[PM_HEAVY_WARPS][256];
+    int cov[PM_HEAVY_WARPS][256];
+    u64 keys[PM_HEAVY_SORT_CAP];               // (item << 32) | (geometry ? 1 << 31 : 0) | position; dropped records: all ones
+    uint16_t starts[PM_HEAVY_SORT_CAP + 8];    // sorted position of every item's first record, then the number of live records
+    uint32_t dir[PM_HEAVY_DIR_CAP];            // 1 + pool index of the header of overflow block j
+    HeavyMeta meta[PM_HEAVY_WARPS];
+    u64 cw, ow, vw;
+    uint32_t red[PM_HEAVY_WARPS];
+    uint32_t entry, n_live, n_items, n_blocks, tile_next;
+};
+
+__device__ __forceinline__ PmRecord load_record(const PmRecord *pool, uint32_t idx) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(&pool[idx]);
+    const uint4 a = src[0], b = src[1];
+    PmRecord r;
+    r.item = a.x; r.key = a.y; r.p[0] = pm_u2f(a.z); r.p[1] = pm_u2f(a.w);
+    r.p[2] = pm_u2f(b.x); r.p[3] = pm_u2f(b.y); r.edge_y = pm_u2f(b.z); r.next = b.w;
+    return r;
+}
+
+// pool index of the tile's record at position pos (pos < the number of indexed records)
+__device__ __forceinline__ uint32_t heavy_index(const HeavySmem *sh, size_t tile, uint32_t pos) {
+    if (pos < PM_TILE_SLOTS) return (uint32_t)tile * PM_TILE_SLOTS + pos;
+    uint32_t j, off;
+    pm_ovf_locate(pos - PM_TILE_SLOTS, &j, &off);
+    return sh->dir[j] + off;
+}
+
+__device__ __forceinline__ uint32_t block_min(uint32_t v, HeavySmem *sh, uint32_t lane, uint32_t warp) {
+    v = __reduce_min_sync(PM_FULL_MASK, v);
+    if (lane == 0) sh->red[warp] = v;
+    __syncthreads();
+    uint32_t m = sh->red[0];
+    #pragma unroll
+    for (int k = 1; k < PM_HEAVY_WARPS; k++) m = sh->red[k] < m ? sh->red[k] : m;
+    __syncthreads();
+    return m;
+}
+
+// alpha of this thread's pixel for the layer whose coverage warp slot `s` holds; clears the slot's cell
+__device__ __forceinline__ float heavy_alpha(HeavySmem *sh, int s, const HeavyMeta &m, int cell, uint32_t px, float fx, float fy) {
+    const uint32_t kind = m.kind;
+    if (kind == PM_REC_DRAWFILL) {
+        const int a = sh->acc[s][cell], c = sh->cov[s][cell];
+        sh->acc[s][cell] = 0;
+        sh->cov[s][cell] = 0;
+        int run = c;  // covers of the pixels to the left carry into this one: inclusive scan over the row's 16 lanes
+        #pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const int v = __shfl_up_sync(PM_FULL_MASK, run, o, 16);
+            if ((int)px >= o) run += v;
+        }
+        return pm_resolve_fill_alpha(a + run, (int)m.w0);
+    }
+    if (kind == PM_REC_STROKE) {  // renderDf, metal:58-60
+        const int a = sh->acc[s][cell];
+        sh->acc[s][cell] = 0;
+        return a ? pm_saturate(pm_u2f(m.w0) + 0.5f - __uint_as_float(~(uint32_t)a)) : 0.0f;
+    }
+    if (kind == PM_REC_CIRCLE) return pm_px_circle_alpha(m.w0, m.w1, fx, fy);
+    return 1.0f;  // PM_REC_SOLID: a translucent full cover
+}
+
+template <bool F32, bool EXACT>
+__device__ void heavy_tile(const PmFrameArgs &A, HeavySmem *sh, uint32_t entry) {
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const uint32_t trow = entry >> 16, tx = entry & 0xffffu;
+    const size_t tile = (size_t)trow * A.n_tx + tx;
+    if (t == 0) { sh->cw = A.cnt[tile]; sh->ow = A.occ[tile]; sh->vw = A.ovf[tile]; sh->n_live = 0; }
+    __syncthreads();
+    const u64 cw = sh->cw, ow = sh->ow, vw = sh->vw;
+    uint32_t n = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
+    const uint32_t occ_item1 = (uint32_t)(ow >> 32) == A.stamp ? (uint32_t)ow : 0u;
+    // directory of the overflow blocks (a frame whose pool ran out has fewer blocks than cnt says: the host renders
+    // such a frame again with a larger pool, this pass only must not fault)
+    if (t == 0) {
+        uint32_t nb = 0, reach = PM_TILE_SLOTS;
+        if (n > PM_TILE_SLOTS) {
+            uint32_t link = (uint32_t)(vw >> 32) == A.stamp ? (uint32_t)vw : 0u;
+            while (link != 0 && link != PM_EXT_FAILED && nb < PM_HEAVY_DIR_CAP && reach < n) {
+                sh->dir[nb] = link;
+                reach += pm_blk_size(nb);
+                nb++;
+                if (reach < n) link = A.pool[link - 1u].next;
+            }
+        }
+        sh->n_blocks = nb;
+        sh->entry = reach;  // (records reachable; `entry` is reused as scratch here)
+    }
+    __syncthreads();
+    if (sh->entry < n) n = sh->entry;
+    __syncthreads();
+
+    const uint32_t prow = t >> 4, px = t & 15u;
+    uint8_t *dst = A.fb + (size_t)(trow * PM_TILE_H + prow) * A.pitch + (size_t)(tx * PM_TILE_W + px) * 4u;
+    float4 *dst32 = nullptr;
+    if (F32) dst32 = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(A.fb32) + (size_t)(trow * PM_TILE_H + prow) * A.pitch32) + (tx * PM_TILE_W + px);
+    const float tile_x0 = (float)(tx * PM_TILE_W), tile_y0 = (float)((A.tile_y0 + trow) * PM_TILE_H);
+    const float fx = tile_x0 + (float)px, fy = tile_y0 + (float)prow;
+    const int cell = pm_cov_swz((int)prow, (int)px);
+    // metal:470 white; then the cover's Cmd_Solid (metal:136-142, :546-551: opaque, the pixel becomes its colour)
+    float c0 = 1.0f, c1 = 1.0f, c2 = 1.0f;
+    if (occ_item1) { const float4 b = __ldg(&A.item_paint[occ_item1 - 1u]); c0 = b.x; c1 = b.y; c2 = b.z; }
+    int has_draw = 0;
+
+    if (n <= PM_HEAVY_SORT_CAP) {
+        // ---- 1. key and sort the records ----
+        uint32_t P = 32;
+        while (P < n) P <<= 1;
+        uint32_t live = 0;
+        for (uint32_t p = t; p < P; p += PM_HEAVY_THREADS) {
+            u64 key = ~0ull;
+            if (p < n) {
+                const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[heavy_index(sh, tile, p)]);
+                if (ik.x >= occ_item1) {  // (below the topmost opaque cover: rewound away, metal:132-135)
+                    const uint32_t kind = ik.y & 15u;
+                    key = ((u64)ik.x << 32) | (kind >= PM_REC_CIRCLE ? 0u : 0x80000000u) | p;
+                    live++;
+                    if (kind != PM_REC_SOLID) has_draw = 1;
+                }
+            }
+            sh->keys[p] = key;
+        }
+        if (live) atomicAdd(&sh->n_live, live);
+        has_draw = __syncthreads_or(has_draw);
+        if (has_draw) {
+            for (uint32_t k = 2; k <= P; k <<= 1)
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    for (uint32_t i = t; i < P; i += PM_HEAVY_THREADS) {
+                        const uint32_t ixj = i ^ j;
+                        if (ixj > i) {
+                            const u64 a = sh->keys[i], b = sh->keys[ixj];
+                            if ((a > b) == ((i & k) == 0)) { sh->keys[i] = b; sh->keys[ixj] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            // ---- item starts (compaction of the positions where the item id changes) ----
+            const uint32_t nl = sh->n_live;
+            const uint32_t per = (nl + PM_HEAVY_THREADS - 1) / PM_HEAVY_THREADS;
+            const uint32_t lo = t * per < nl ? t * per : nl, hi = lo + per < nl ? lo + per : nl;
+            uint32_t cnt = 0;
+            for (uint32_t i = lo; i < hi; i++) cnt += (i == 0 || (uint32_t)(sh->keys[i] >> 32) != (uint32_t)(sh->keys[i - 1] >> 32)) ? 1u : 0u;
+            uint32_t incl = cnt;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(PM_FULL_MASK, incl, o);
+                if (lane >= (uint32_t)o) incl += v;
+            }
+            if (lane == 31) sh->red[warp] = incl;
+            __syncthreads();
+            uint32_t before = 0;
+            for (uint32_t k = 0; k < warp; k++) before += sh->red[k];
+            uint32_t at = before + incl - cnt;
+            for (uint32_t i = lo; i < hi; i++)
+                if (i == 0 || (uint32_t)(sh->keys[i] >> 32) != (uint32_t)(sh->keys[i - 1] >> 32)) sh->starts[at++] = (uint16_t)i;
+            if (t == PM_HEAVY_THREADS - 1) { sh->n_items = before + incl; sh->starts[before + incl] = (uint16_t)nl; }
+            __syncthreads();
+            const uint32_t n_items = sh->n_items;
+
+            // ---- 2 + 3. eight items at a time: coverage per warp, then the layers blended in order ----
+            PmCoverAcc cacc{sh->acc[warp], sh->cov[warp]};
+            for (uint32_t k0 = 0; k0 < n_items; k0 += PM_HEAVY_WARPS) {
+                const uint32_t k = k0 + warp;
+                if (k < n_items) {
+                    const uint32_t s = sh->starts[k], e = sh->starts[k + 1];
+                    const u64 first = sh->keys[s];
+                    HeavyMeta m;
+                    m.kind = 0; m.w0 = m.w1 = m.pad = 0; m.paint = make_float4(0.0f, 0.0f, 0.0f, 1.0f);  // Cmd_Circle paints black (metal:491)
+                    if (!(first & 0x80000000ull)) {  // the item's closing record sorts first (an item without one is not drawn)
+                        const uint4 tr = *reinterpret_cast<const uint4 *>(&A.pool[heavy_index(sh, tile, (uint32_t)first & 0x7fffffffu)]);
+                        m.kind = tr.y & 15u; m.w0 = tr.z; m.w1 = tr.w;
+                        if (m.kind != PM_REC_CIRCLE) m.paint = __ldg(&A.item_paint[(uint32_t)(first >> 32)]);
+                        const bool stroke = m.kind == PM_REC_STROKE;
+                        if (stroke || m.kind == PM_REC_DRAWFILL) {
+                            const float reach = pm_u2f(m.w0) + 0.5f;
+                            for (uint32_t c = s + 1; c < e; c += 32) {
+                                const bool mine = c + lane < e;
+                                PmRecord rc;
+                                rc.key = 0; rc.p[0] = rc.p[1] = rc.p[2] = rc.p[3] = 0.0f; rc.edge_y = 0.0f;
+                                if (mine) rc = load_record(A.pool, heavy_index(sh, tile, (uint32_t)sh->keys[c + lane] & 0x7fffffffu));
+                                pm_cover_records(cacc, mine, rc.key & 15u, rc.p[0], rc.p[1], rc.p[2], rc.p[3], rc.edge_y, stroke, reach, tile_x0, tile_y0, lane);
+                            }
+                        }
+                    }
+                    if (lane == 0) sh->meta[warp] = m;
+                }
+                __syncthreads();
+                const uint32_t n_here = n_items - k0 < PM_HEAVY_WARPS ? n_items - k0 : PM_HEAVY_WARPS;
+                for (uint32_t s = 0; s < n_here; s++) {
+                    const HeavyMeta m = sh->meta[s];
+                    if (m.kind == 0) continue;
+                    const float al = heavy_alpha(sh, (int)s, m, cell, px, fx, fy) * m.paint.w;
+                    c0 = pm_mix_fma(c0, m.paint.x, al); c1 = pm_mix_fma(c1, m.paint.y, al); c2 = pm_mix_fma(c2, m.paint.z, al);
+                }
+                __syncthreads();
+            }
+        }
+    } else {
+        // ---- more records than the sort holds: one pass over all records per item ----
+        for (uint32_t p0 = 0; p0 < n; p0 += PM_HEAVY_THREADS) {
+            const uint32_t p = p0 + t;
+            if (p < n) {
+                const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[heavy_index(sh, tile, p)]);
+                if (ik.x >= occ_item1 && (ik.y & 15u) != PM_REC_SOLID) has_draw = 1;
+            }
+        }
+        has_draw = __syncthreads_or(has_draw);
+        PmCoverAcc cacc{sh->acc[0], sh->cov[0]};  // all warps add to one set of arrays
+        uint32_t lo_item = occ_item1;
+        while (has_draw) {
+            uint32_t cand = 0xffffffffu;
+            for (uint32_t p = t; p < n; p += PM_HEAVY_THREADS) {
+                const uint32_t it = A.pool[heavy_index(sh, tile, p)].item;
+                if (it >= lo_item && it < cand) cand = it;
+            }
+            const uint32_t cur = block_min(cand, sh, lane, warp);
+            if (cur == 0xffffffffu) break;
+            lo_item = cur + 1u;
+            if (t == 0) sh->meta[0].kind = 0;
+            __syncthreads();
+            for (uint32_t p = t; p < n; p += PM_HEAVY_THREADS) {  // the closing record
+                const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[heavy_index(sh, tile, p)]);
+                if (a.x == cur && (a.y & 15u) >= PM_REC_CIRCLE) {
+                    HeavyMeta m;
+                    m.kind = a.y & 15u; m.w0 = a.z; m.w1 = a.w; m.pad = 0;
+                    m.paint = m.kind != PM_REC_CIRCLE ? __ldg(&A.item_paint[cur]) : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+                    sh->meta[0] = m;
+                }
+            }
+            __syncthreads();
+            const HeavyMeta m = sh->meta[0];
+            if (m.kind == 0) continue;  // (uniform: every thread reads the same words)
+            const bool stroke = m.kind == PM_REC_STROKE;
+            if (stroke || m.kind == PM_REC_DRAWFILL) {
+                const float reach = pm_u2f(m.w0) + 0.5f;
+                for (uint32_t p0 = 0; p0 < n; p0 += PM_HEAVY_THREADS) {
+                    const uint32_t p = p0 + t;
+                    bool mine = false;
+                    PmRecord rc;
+                    rc.key = 0; rc.p[0] = rc.p[1] = rc.p[2] = rc.p[3] = 0.0f; rc.edge_y = 0.0f;
+                    if (p < n) {
+                        const uint32_t idx = heavy_index(sh, tile, p);
+                        const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[idx]);
+                        if (ik.x == cur && (ik.y & 15u) <= PM_REC_LINE) { mine = true; rc = load_record(A.pool, idx); }
+                    }
+                    if (__any_sync(PM_FULL_MASK, mine))
+                        pm_cover_records(cacc, mine, rc.key & 15u, rc.p[0], rc.p[1], rc.p[2], rc.p[3], rc.edge_y, stroke, reach, tile_x0, tile_y0, lane);
+                }
+            }
+            __syncthreads();
+            const float al = heavy_alpha(sh, 0, m, cell, px, fx, fy) * m.paint.w;
+            c0 = pm_mix_fma(c0, m.paint.x, al); c1 = pm_mix_fma(c1, m.paint.y, al); c2 = pm_mix_fma(c2, m.paint.z, al);
+            __syncthreads();
+        }
+    }
+
+    if (!has_draw) {  // only Solid commands after the last rewind: the tile Bails and shows solidColor (metal:145-147, :34-44)
+        uint32_t c = 0xffffffffu;
+        if (occ_item1) c = __ldg(reinterpret_cast<const uint32_t *>(A.scene + A.items_ix + (size_t)(occ_item1 - 1u) * PM_ITEM_SIZE + PM_FILL_RGBA));
+        *reinterpret_cast<uint32_t *>(dst) = c;
+        if (F32) *dst32 = make_float4((float)(c & 0xff) / 255.0f, (float)((c >> 8) & 0xff) / 255.0f, (float)((c >> 16) & 0xff) / 255.0f, (float)(c >> 24) / 255.0f);
+    } else {
+        *reinterpret_cast<uint32_t *>(dst) = pm_encode_pixel<EXACT>(c0, c1, c2);
+        if (F32) *dst32 = make_float4(pm_linear_to_srgb<EXACT>(c0), pm_linear_to_srgb<EXACT>(c1), pm_linear_to_srgb<EXACT>(c2), 1.0f);
+    }
+    __syncthreads();
+}
+
+template <bool F32, bool EXACT>
+__global__ void __launch_bounds__(PM_HEAVY_THREADS) k_heavy(const PmFrameArgs A) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    HeavySmem *sh = reinterpret_cast<HeavySmem *>(s_raw);
+    for (uint32_t i = threadIdx.x; i < PM_HEAVY_WARPS * 256; i += PM_HEAVY_THREADS) { (&sh->acc[0][0])[i] = 0; (&sh->cov[0][0])[i] = 0; }
+    // Programmatic dependent launch: wait for binning (k_row) to complete, THEN let k_fine launch beside this grid;
+    // k_fine itself does not wait at its start (see pm_fine.cu).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const uint32_t n_heavy = A.counters->n_heavy;
+    const uint32_t *list = A.complex_list + (size_t)A.n_rows * A.n_tx;
+    __syncthreads();
+    for (;;) {
+        if (threadIdx.x == 0) sh->tile_next = atomicAdd(&A.queue->heavy_next, 1u);
+        __syncthreads();
+        const uint32_t h = sh->tile_next;
+        __syncthreads();
+        if (h >= n_heavy) break;
+        heavy_tile<F32, EXACT>(A, sh, list[h]);
+    }
+}
+
+}  // namespace
+
+template <bool F32, bool EXACT>
+static cudaError_t heavy_attr() {
+    return cudaFuncSetAttribute(k_heavy<F32, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeavySmem));
+}
+
+int pm_heavy_setup(void) {
+    cudaError_t e;
+    if ((e = heavy_attr<false, false>()) != cudaSuccess) return (int)e;
+    if ((e = heavy_attr<false, true>()) != cudaSuccess) return (int)e;
+    if ((e = heavy_attr<true, false>()) != cudaSuccess) return (int)e;
+    if ((e = heavy_attr<true, true>()) != cudaSuccess) return (int)e;
+    return 0;
+}
+
+template <bool F32, bool EXACT>
+static cudaError_t heavy_launch(const PmFrameArgs &a, int grid, bool overlap, cudaStream_t s) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PM_HEAVY_THREADS); cfg.dynamicSmemBytes = sizeof(HeavySmem); cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = overlap ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k_heavy<F32, EXACT>, a);
+}
+
+cudaError_t pm_launch_heavy(const PmFrameArgs &a, int sm_count, bool overlap, cudaStream_t s) {
+    // persistent: the number of heavy tiles is only known on the device; CTAs without work leave at once
+    const int grid = sm_count * 2;
+    const bool exact = (a.flags & PM_FLAG_EXACT_SRGB) != 0;
+    if (a.fb32) return exact ? heavy_launch<true, true>(a, grid, overlap, s) : heavy_launch<true, false>(a, grid, overlap, s);
+    return exact ? heavy_launch<false, true>(a, grid, overlap, s) : heavy_launch<false, false>(a, grid, overlap, s);
+}

@@ -45,7 +45,7 @@ __global__ void k_validate(const uint8_t *scene, uint32_t len, uint32_t *err) {
     if (len < PM_GROUP_HEADER_SIZE) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(err, 1u); return; }
     const uint64_t n = ld_u32(scene);
     const uint64_t items_ix = ld_u32(scene + 4);
-    if (PM_GROUP_HEADER_SIZE + n * PM_BBOX_SIZE > len || (items_ix & 3u) || items_ix + n * PM_ITEM_SIZE > len) {
+    if (PM_GROUP_HEADER_SIZE + n * PM_BBOX_SIZE > len || (items_ix & 7u) || items_ix + n * PM_ITEM_SIZE > len) {
         if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(err, 1u);
         return;
     }
@@ -57,7 +57,7 @@ __global__ void k_validate(const uint8_t *scene, uint32_t len, uint32_t *err) {
         uint32_t tag = ld_u32(it);
         if (tag == PM_ITEM_FILL || tag == PM_ITEM_POLY) {
             uint64_t np = ld_u32(it + 12), pix = ld_u32(it + 16);
-            if (np == 0 || np >= PM_REC_SEG_MAX || (pix & 3u) || pix + np * 8 > len) {
+            if (np == 0 || np >= PM_REC_SEG_MAX || (pix & 7u) || pix + np * 8 > len) {
                 if (lane == 0) atomicOr(err, 2u);
                 continue;
             }
@@ -136,7 +136,8 @@ __device__ __forceinline__ u64 block_scan_excl(u64 v, u64 *warp_excl, u64 *block
 
 __global__ void __launch_bounds__(1024) k_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0,
                                                uint32_t tile_y1, uint32_t n_tx, u64 *plan_a, u64 *plan_b, PmItemInfo *item_info,
-                                               uint2 *row_info, uint32_t row_info_cap, PmPlanResult *result) {
+                                               uint2 *row_info, uint32_t row_info_cap, const float *srgb_lut, float4 *item_paint,
+                                               PmPlanResult *result) {
     __shared__ u64 warp_excl[32];
     __shared__ u64 total_a, total_b, carry_a, carry_b;
     const uint32_t tid = threadIdx.x;
@@ -163,6 +164,14 @@ __global__ void __launch_bounds__(1024) k_plan(const uint8_t *scene, uint32_t n_
                 PmItemInfo ii;
                 ii.t_lo = spi.t_lo; ii.t_hi = spi.t_hi; ii.r_lo = spi.r_lo; ii.rows = spi.rows; ii.bd_base = eb; ii.pad[0] = ii.pad[1] = 0;
                 item_info[i] = ii;
+                // the item's colour as the fill kernels blend it: unpack_unorm4x8_srgb_to_half (metal:503, :541, :548)
+                // through the look-up table; Cmd_Circle paints opaque black (metal:491)
+                float4 paint = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+                if (spi.tag == PM_ITEM_LINE || spi.tag == PM_ITEM_FILL || spi.tag == PM_ITEM_POLY) {
+                    const uint32_t rgba = ld_u32(scene + items_ix + (size_t)i * PM_ITEM_SIZE + (spi.tag == PM_ITEM_POLY ? PM_POLY_RGBA : PM_FILL_RGBA));
+                    paint = make_float4(srgb_lut[rgba & 0xffu], srgb_lut[(rgba >> 8) & 0xffu], srgb_lut[(rgba >> 16) & 0xffu], srgb_lut[256u + (rgba >> 24)]);
+                }
+                item_paint[i] = paint;
             }
             // second pass (row_info given): tabulate the item's (tile row, 32-tile chunk) units for k_row
             if (row_info && ca != 0) {
@@ -338,6 +347,16 @@ struct BinSink {
     uint32_t row_tile0;  // index of the row's first tile
     uint32_t item;
 
+    // bump-allocates overflow block j (header + slots); returns 1 + the header's pool index, or PM_EXT_FAILED
+    __device__ __forceinline__ uint32_t alloc_block(uint32_t ovf_region, uint32_t j) const {
+        const uint32_t size = pm_blk_size(j) + 1u;
+        const uint32_t o = atomicAdd(&A.counters->n_overflow, size);
+        if (o + size > A.overflow_cap || o + size < o) return PM_EXT_FAILED;
+        const uint32_t mine = ovf_region + o + 1u;
+        A.pool[mine - 1u].next = 0;
+        __threadfence();
+        return mine;
+    }
     __device__ __forceinline__ void append(uint32_t t, PmRecord r) {
         const uint32_t tile = row_tile0 + t;
         const uint32_t pos = tile_claim_slot(&A.cnt[tile], A.stamp);
@@ -346,52 +365,52 @@ struct BinSink {
         if (pos < PM_TILE_SLOTS) {
             idx = tile * PM_TILE_SLOTS + pos;
         } else {
-            // Records 16..63 of a tile go into its extension block: PM_EXT_BLOCK contiguous pool records,
-            // published in ovf[tile] (stamped).  Lock-free and without waiting: whoever finds the word
-            // unpublished allocates a block and tries to install it with a compare-and-swap; a loser adopts
-            // the winner's block (its own stays unused -- bump allocation cannot give it back; the count
-            // the host sees includes it).  The block's first record is a header whose `next` heads the
-            // chain of records 64...
+            // Later records go into the tile's chain of overflow blocks (layout: pm_pixel_logic.h).  Lock-free and
+            // without waiting: whoever finds a link unpublished allocates the block and tries to install it with a
+            // compare-and-swap; a loser adopts the winner's block (its own stays unused -- bump allocation cannot
+            // give it back; the count the host sees includes it).
+            uint32_t j, off;
+            pm_ovf_locate(pos - PM_TILE_SLOTS, &j, &off);
             const uint32_t ovf_region = A.n_rows * A.n_tx * PM_TILE_SLOTS;
-            uint32_t base1;  // 1 + pool index of the block header, or PM_EXT_FAILED
-            const u64 seen = *reinterpret_cast<volatile u64 *>(&A.ovf[tile]);
-            if ((uint32_t)(seen >> 32) == A.stamp) {
-                base1 = (uint32_t)seen;
-            } else {
-                const uint32_t o = atomicAdd(&A.counters->n_overflow, (uint32_t)PM_EXT_BLOCK);
-                uint32_t mine = PM_EXT_FAILED;  // the host sees n_overflow > overflow_cap, grows the pool and re-renders
-                if (o + PM_EXT_BLOCK <= A.overflow_cap) {
-                    mine = ovf_region + o + 1u;
-                    A.pool[mine - 1u].next = 0;
-                    __threadfence();
+            uint32_t base1;  // 1 + pool index of the header of block 0, or PM_EXT_FAILED
+            {
+                const u64 seen = *reinterpret_cast<volatile u64 *>(&A.ovf[tile]);
+                if ((uint32_t)(seen >> 32) == A.stamp) {
+                    base1 = (uint32_t)seen;
+                } else {
+                    const uint32_t mine = alloc_block(ovf_region, 0);
+                    const u64 prev = atomicCAS(&A.ovf[tile], seen, ((u64)A.stamp << 32) | (u64)mine);
+                    base1 = prev == seen ? mine : (uint32_t)prev;  // (a word that changed was published by somebody else, this frame)
                 }
-                const u64 prev = atomicCAS(&A.ovf[tile], seen, ((u64)A.stamp << 32) | (u64)mine);
-                base1 = prev == seen ? mine : (uint32_t)prev;  // (a word that changed was published by somebody else, this frame)
             }
-            if (base1 == PM_EXT_FAILED) return;
-            if (pos < PM_TILE_SLOTS + PM_EXT_SLOTS) {
-                idx = base1 + (pos - PM_TILE_SLOTS);
-            } else {
-                const uint32_t o = atomicAdd(&A.counters->n_overflow, 1u);
-                if (o >= A.overflow_cap) return;
-                idx = ovf_region + o;
-                r.next = atomicExch(&A.pool[base1 - 1u].next, idx + 1u);
+            for (uint32_t k = 0; k < j && base1 != PM_EXT_FAILED; k++) {
+                uint32_t *link = &A.pool[base1 - 1u].next;
+                uint32_t nxt = *reinterpret_cast<volatile uint32_t *>(link);
+                if (nxt == 0) {
+                    const uint32_t mine = alloc_block(ovf_region, k + 1u);
+                    const uint32_t prev = atomicCAS(link, 0u, mine);
+                    nxt = prev == 0 ? mine : prev;
+                }
+                base1 = nxt;
             }
+            if (base1 == PM_EXT_FAILED) return;  // the host sees n_overflow > overflow_cap, grows the pool and renders the frame again
+            idx = base1 + off;
         }
         uint4 *dst = reinterpret_cast<uint4 *>(&A.pool[idx]);
         const uint4 *src = reinterpret_cast<const uint4 *>(&r);
         dst[0] = src[0];
         dst[1] = src[1];
-        if (pos == PM_TILE_SLOTS) {  // first overflow record: the tile is "heavy", the fill kernel renders those first
+        if (pos == PM_HEAVY_MIN - 1u) {  // more records than a warp of k_fine holds: the tile is "heavy", k_heavy renders it
             const uint32_t h = atomicAdd(&A.counters->n_heavy, 1u);
             A.complex_list[A.n_rows * A.n_tx + h] = ((tile - t) / A.n_tx << 16) | t;
         }
-#if PM_CTA_TILES
-        if (pos == PM_CTA_MIN - 1u) {  // the tile has become "costly": third list, behind the heavy one
-            const uint32_t h = atomicAdd(&A.counters->n_costly, 1u);
-            A.complex_list[2u * A.n_rows * A.n_tx + h] = ((tile - t) / A.n_tx << 16) | t;
+        if (pos == PM_MEDIUM_MIN - 1u) {  // the tile has become "medium": k_fine walks these first (third list)
+            cg::coalesced_group g = cg::coalesced_threads();
+            uint32_t base = 0;
+            if (g.thread_rank() == 0) base = atomicAdd(&A.counters->n_medium, g.size());
+            base = g.shfl(base, 0);
+            A.complex_list[2u * A.n_rows * A.n_tx + base + g.thread_rank()] = ((tile - t) / A.n_tx << 16) | t;
         }
-#endif
         if (pos == 0) {  // first record of the tile this frame: queue it for the fill kernel
             cg::coalesced_group g = cg::coalesced_threads();
             uint32_t base = 0;
@@ -440,10 +459,8 @@ __global__ void __launch_bounds__(256, PM_SEG_CTAS) k_seg(const PmFrameArgs A) {
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         A.queue->batch_next = 0;
-#if PM_CTA_TILES
-        A.queue->costly_next = 0;
-#endif
-        for (int s = 0; s < PM_FINE_SUBQ; s++) A.queue->sub[s][0] = 0;
+        A.queue->tile_next = 0;
+        A.queue->heavy_next = 0;
     }
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= A.n_pieces) return;
@@ -549,8 +566,9 @@ void pm_launch_validate(const uint8_t *scene, uint32_t scene_len, uint32_t *err,
 
 void pm_launch_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1,
                     uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, PmItemInfo *item_info, uint2 *row_info,
-                    uint32_t row_info_cap, PmPlanResult *result, cudaStream_t s) {
-    k_plan<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, plan_b, item_info, row_info, row_info_cap, result);
+                    uint32_t row_info_cap, const float *srgb_lut, float4 *item_paint, PmPlanResult *result, cudaStream_t s) {
+    k_plan<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, plan_b, item_info, row_info, row_info_cap, srgb_lut,
+                              item_paint, result);
 }
 
 void pm_launch_pieces_count(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
@@ -567,23 +585,37 @@ void pm_launch_pieces_fill(const uint8_t *scene, uint32_t n_items, uint32_t item
 }
 
 template <class K>
-static void launch_overlapped(K kernel, dim3 grid, dim3 block, bool overlap, cudaStream_t s, const PmFrameArgs &a) {
+static cudaError_t launch_overlapped(K kernel, dim3 grid, dim3 block, bool overlap, cudaStream_t s, const PmFrameArgs &a) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = overlap ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kernel, a);
+    return cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
-void pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, bool overlap, cudaStream_t s) {
+cudaError_t pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, cudaEvent_t mid2, bool overlap, cudaStream_t s, uint32_t *n_launched) {
+    cudaError_t e;
+    uint32_t launched = 0;
     uint32_t grid_seg = (a.n_pieces + 255u) / 256u;
-    if (grid_seg == 0) grid_seg = 1;  // still clears the fill kernel's queues
-    launch_overlapped(k_seg, dim3(grid_seg), dim3(256), overlap, s, a);
+    if (grid_seg == 0) grid_seg = 1;  // still clears the fill kernels' queues
+    if ((e = launch_overlapped(k_seg, dim3(grid_seg), dim3(256), overlap, s, a)) != cudaSuccess) return e;
+    launched++;
     // (k_row runs even without units when the launches overlap: the chain of grid dependencies must not skip a kernel)
-    if (a.n_row_units || overlap)
-        launch_overlapped(k_row, dim3((a.n_row_units + PM_ROW_WARPS - 1) / PM_ROW_WARPS > 0 ? (a.n_row_units + PM_ROW_WARPS - 1) / PM_ROW_WARPS : 1), dim3(PM_ROW_WARPS * 32), overlap, s, a);
-    if (mid) cudaEventRecord(mid, s);
-    pm_launch_fine(a, sm_count, overlap, s);
+    if (a.n_row_units || overlap) {
+        const uint32_t grid_row = (a.n_row_units + PM_ROW_WARPS - 1) / PM_ROW_WARPS;
+        if ((e = launch_overlapped(k_row, dim3(grid_row ? grid_row : 1), dim3(PM_ROW_WARPS * 32), overlap, s, a)) != cudaSuccess) return e;
+        launched++;
+    }
+    if (mid && (e = cudaEventRecord(mid, s)) != cudaSuccess) return e;
+    // k_heavy before k_fine: its CTAs (one per heavy tile, the frame's longest jobs) start first; k_fine is released
+    // as soon as they have seen binning complete and runs beside them (see the notes on griddepcontrol in both kernels)
+    if ((e = pm_launch_heavy(a, sm_count, overlap, s)) != cudaSuccess) return e;
+    launched++;
+    if (mid2 && (e = cudaEventRecord(mid2, s)) != cudaSuccess) return e;
+    if ((e = pm_launch_fine(a, sm_count, overlap, s)) != cudaSuccess) return e;
+    launched++;
+    if (n_launched) *n_launched = launched;
+    return cudaSuccess;
 }

@@ -5,45 +5,44 @@
 
 #include "pm_pixel_logic.h"
 
-// PM_CTA_TILES (build-time, default 0 = not compiled in; NOT yet validated on a GPU -- written at the end of
-// round 1 after the GPU budget was spent, to be measured in round 2): tiles with PM_CTA_MIN..PM_CTA_CAP records
-// are listed separately by binning and, when there are few of them, rendered by a whole CTA each (one thread
-// per pixel, the eight warps sharing the coverage accumulators) before the per-warp loop starts.  A single warp
-// issues ~0.1 instructions per cycle, so such a tile takes 60-110 us on its own and bounds the frame time of a
-// narrow multi-GPU strip.  Same per-pixel arithmetic, integer coverage sums: the pixels
-// are bit-identical to the per-warp path, so the choice may depend on the strip.
-#ifndef PM_CTA_TILES
-#define PM_CTA_TILES 0
-#endif
-#define PM_CTA_MIN 24u        // records from which a tile is "costly"
-#define PM_CTA_CAP 256u       // ... and up to which the CTA path takes it (its record index lives in shared memory)
-#define PM_CTA_MAX_PER_CTA 6u // the CTA path is used when there are at most this many costly tiles per launched CTA
-
 // Per-frame counters.  Two sets alternate by frame parity so that the fill kernel of frame f can
-// clear the set frame f+1 will use (no memset node in the frame).
+// clear the set frame f+1 will use (no memset node in the frame).  Each counter sits on a cache line of its own:
+// binning adds to all of them concurrently, and atomics on one line are served one at a time.
 struct PmBinCounters {
     uint32_t n_complex;   // tiles that own at least one record
-    uint32_t n_overflow;  // records that did not fit the inline slots of their tile
-    uint32_t n_heavy;     // tiles with more records than inline slots
-    uint32_t n_costly;    // tiles with at least PM_CTA_MIN records (only counted when PM_CTA_TILES is compiled in)
+    uint32_t pad0[31];
+    uint32_t n_overflow;  // pool records allocated behind the inline slots (overflow blocks, headers included)
+    uint32_t pad1[31];
+    uint32_t n_heavy;     // tiles with at least PM_HEAVY_MIN records: rendered by k_heavy, a whole CTA each
+    uint32_t pad2[31];
+    uint32_t n_medium;    // tiles with at least PM_MEDIUM_MIN records: k_fine starts with these
+    uint32_t pad3[31];
 };
-// Work queues of the fill kernel; cleared by the binning kernel of the same frame.
-// The list of tiles with records is handed out through PM_FINE_SUBQ counters instead of one: position
-// s + PM_FINE_SUBQ * k belongs to counter s.  A single counter would see one atomic every few cycles,
-// which is what an L2 slice can do on one address: the claims would queue up for microseconds.
-#define PM_FINE_SUBQ 8
+#define PM_MEDIUM_MIN 6u
+// Records up to which a tile is k_fine's (one warp per tile); tiles with more go to k_heavy (one CTA per tile).
+// 16 = the inline slots.  k_fine can take up to 32 (one record per lane; records 16..31 are the start of the
+// tile's first overflow block), measured on the 8192^2 tiger: k_fine +6 us, the frame +7 us -- a 30-record tile
+// keeps one warp busy for tens of microseconds, which is exactly what k_heavy is for.
+#ifndef PM_WARP_RECORDS
+#define PM_WARP_RECORDS 16u
+#endif
+#define PM_HEAVY_MIN (PM_WARP_RECORDS + 1u)
+// Work queues of the fill kernels; cleared by the binning kernel of the same frame.  Each counter sits on a
+// cache line of its own.
 struct PmFineQueue {
-    uint32_t batch_next;    // 32-tile batches of solid tiles
-    uint32_t costly_next;   // costly tiles, claimed by whole CTAs (PM_CTA_TILES)
-    uint32_t pad[62];
-    uint32_t sub[PM_FINE_SUBQ][64];  // [s][0]: next k of sub-queue s (each on a cache line of its own)
+    uint32_t batch_next;    // k_fine: 32-tile batches of solid tiles
+    uint32_t pad0[31];
+    uint32_t tile_next;     // k_fine: position in the dynamically claimed part of its work list
+    uint32_t pad1[31];
+    uint32_t heavy_next;    // k_heavy: position in the list of heavy tiles, one CTA each
+    uint32_t pad2[31];
 };
 // Written by the device into mapped host memory at the end of every frame.
 struct PmFrameReport {
     uint32_t n_complex;
     uint32_t n_overflow;
     uint32_t frame;
-    uint32_t pad;
+    uint32_t n_heavy;
 };
 
 // Plan-time copies of what k_seg needs about a segment / an item, laid out for two 16-byte loads each
@@ -76,7 +75,7 @@ struct PmFrameArgs {
     unsigned long long *ovf;
     PmRecord *pool;             // [n_tiles * PM_TILE_SLOTS inline slots][overflow_cap records]
     uint32_t overflow_cap;
-    uint32_t *complex_list;     // 2 * n_rows * n_tx: tiles with records, then (second half) the heavy ones among them
+    uint32_t *complex_list;     // 3 * n_rows * n_tx: tiles with records | the heavy ones among them | the medium ones
     PmBinCounters *counters;    // this frame's set
     PmBinCounters *counters_next;
     PmFineQueue *queue;
@@ -89,6 +88,7 @@ struct PmFrameArgs {
     size_t pitch32;
     unsigned long long *debug;  // optional per-CTA cycle counts of k_seg (PM_DEBUG_SEG=1)
     const float *srgb_lut;      // 512 floats: [0,256) sRGB byte -> linear, [256,512) alpha byte / 255
+    const float4 *item_paint;   // per item: linear r, g, b and alpha of its colour (k_plan; Circle: opaque black)
 };
 
 struct PmPlanResult { uint32_t n_segments; uint32_t n_rows; unsigned long long bd_words; uint32_t error; uint32_t n_pieces; };
@@ -99,7 +99,7 @@ void pm_launch_validate(const uint8_t *scene, uint32_t scene_len, uint32_t *err,
 // Fills plan_a / plan_b [0..n_items] and result (device) for the given strip.
 void pm_launch_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1,
                     uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, PmItemInfo *item_info, uint2 *row_info,
-                    uint32_t row_info_cap, PmPlanResult *result, cudaStream_t s);
+                    uint32_t row_info_cap, const float *srgb_lut, float4 *item_paint, PmPlanResult *result, cudaStream_t s);
 // The k_seg work list: count + prefix (result->n_pieces, piece_cnt becomes the per-segment offset), then fill.
 void pm_launch_pieces_count(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
                             const unsigned long long *plan_a, uint32_t n_segments, PmSegInfo *seg_info, uint32_t *piece_cnt,
@@ -107,11 +107,16 @@ void pm_launch_pieces_count(const uint8_t *scene, uint32_t n_items, uint32_t ite
 void pm_launch_pieces_fill(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
                            const unsigned long long *plan_a, uint32_t n_segments, const uint32_t *piece_off, uint2 *piece_info,
                            uint32_t piece_cap, cudaStream_t s);
-// One frame: binning (k_seg, k_row) then fill/blend (k_fine).  `mid` (optional) is recorded before k_fine.
-// `overlap`: programmatic dependent launch between the frame's kernels and from one frame to the next (no event
-// may sit between them, so `mid` must be null).
-void pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, bool overlap, cudaStream_t s);
-// The fill/blend kernel alone (pm_fine.cu), and its one-time set-up on the current device
-// (shared-memory attributes of the kernel).
-void pm_launch_fine(const PmFrameArgs &a, int sm_count, bool overlap, cudaStream_t s);
+// One frame: binning (k_seg, k_row), then fill/blend: k_fine (solid tiles and tiles whose records fit the inline
+// slots, one warp per tile) and k_heavy (the other tiles, one CTA per tile).  `mid` / `mid2` (optional) are recorded
+// between binning and k_heavy / between k_heavy and k_fine.  `overlap`: programmatic dependent launch between the
+// frame's kernels and from one frame to the next (no event may sit between them, so the events must be null); k_heavy
+// and k_fine then run side by side.  Returns the first launch error.
+cudaError_t pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, cudaEvent_t mid2, bool overlap, cudaStream_t s,
+                            uint32_t *n_launched);
+// The fill/blend kernels (pm_fine.cu, pm_heavy.cu) and their one-time set-up on the current device
+// (shared-memory attributes).
+cudaError_t pm_launch_fine(const PmFrameArgs &a, int sm_count, bool overlap, cudaStream_t s);
+cudaError_t pm_launch_heavy(const PmFrameArgs &a, int sm_count, bool overlap, cudaStream_t s);
 int pm_fine_setup(void);
+int pm_heavy_setup(void);

@@ -59,6 +59,7 @@ struct pm_renderer {
     uint32_t *piece_off = nullptr;  // per segment: offset of its pieces in piece_info
     size_t seg_cap = 0;
     PmItemInfo *item_info = nullptr;
+    float4 *item_paint = nullptr;   // per item: linear colour + alpha (k_plan)
     uint2 *piece_info = nullptr, *row_info = nullptr;
     size_t piece_cap = 0, row_info_cap = 0;
     uint32_t *bd = nullptr;  // backdrop scratch, zero between frames
@@ -92,7 +93,8 @@ struct pm_renderer {
     float *lut = nullptr;
 
     // timing
-    cudaEvent_t ev_start[EVENT_RING], ev_mid[EVENT_RING], ev_end[EVENT_RING];
+    cudaEvent_t ev_start[EVENT_RING], ev_mid[EVENT_RING], ev_mid2[EVENT_RING], ev_end[EVENT_RING];
+    uint32_t n_launches = 0;    // kernels of the last frame
     uint32_t frame = 0, frames_unsynced = 0, stamp = 0;
     uint32_t retries = 0;
 };
@@ -141,7 +143,7 @@ int alloc_surface(pm_renderer *r) {
         PM_CUDA(cudaMalloc(&r->occ, n_tiles * sizeof(unsigned long long)));
         PM_CUDA(cudaMalloc(&r->cnt, n_tiles * sizeof(unsigned long long)));
         PM_CUDA(cudaMalloc(&r->ovf, n_tiles * sizeof(unsigned long long)));
-        PM_CUDA(cudaMalloc(&r->complex_list, (PM_CTA_TILES ? 3 : 2) * n_tiles * sizeof(uint32_t)));  // tiles with records | heavy | costly
+        PM_CUDA(cudaMalloc(&r->complex_list, 3 * n_tiles * sizeof(uint32_t)));  // tiles with records | the heavy ones among them | the medium ones
         r->tiles_cap = n_tiles;
     }
     if (r->fb32) { PM_CUDA(cudaFree(r->fb32)); r->fb32 = nullptr; }
@@ -151,6 +153,7 @@ int alloc_surface(pm_renderer *r) {
     PM_CUDA(cudaMemsetAsync(r->cnt, 0, n_tiles * sizeof(unsigned long long), r->stream));
     PM_CUDA(cudaMemsetAsync(r->ovf, 0, n_tiles * sizeof(unsigned long long), r->stream));
     PM_CUDA(cudaMemsetAsync(r->counters, 0, 2 * sizeof(PmBinCounters), r->stream));
+    memset(r->report, 0, sizeof(PmFrameReport));  // (a report of the previous surface must not trigger a pool growth for this one)
     {
         uint64_t want = r->pool_bytes_cfg ? r->pool_bytes_cfg / sizeof(PmRecord) : std::max<uint64_t>(1u << 16, n_tiles / 4);
         int st = ensure_pool(r, (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 64), 1u << 28));
@@ -167,7 +170,7 @@ int run_plan(pm_renderer *r) {
     for (int pass = 0; pass < 2; pass++) {
         PM_CUDA(cudaMemsetAsync(r->dev_plan, 0, sizeof(PmPlanResult), r->stream));
         pm_launch_plan(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, r->plan_b, r->item_info,
-                       r->row_info, (uint32_t)r->row_info_cap, r->dev_plan, r->stream);
+                       r->row_info, (uint32_t)r->row_info_cap, r->lut, r->item_paint, r->dev_plan, r->stream);
         PM_CUDA(cudaGetLastError());
         PM_CUDA(cudaMemcpyAsync(&res, r->dev_plan, sizeof res, cudaMemcpyDeviceToHost, r->stream));
         PM_CUDA(cudaStreamSynchronize(r->stream));
@@ -275,11 +278,12 @@ int enqueue_frame(pm_renderer *r, bool debug_f32) {
     a.fb = r->fb; a.pitch = r->pitch;
     a.fb32 = debug_f32 ? r->fb32 : nullptr; a.pitch32 = r->pitch32;
     a.srgb_lut = r->lut;
+    a.item_paint = r->item_paint;
     a.debug = r->debug;
     const uint32_t slot = r->frame % EVENT_RING;
     const bool events = r->frame_events || debug_f32;
     if (events) PM_CUDA(cudaEventRecord(r->ev_start[slot], r->stream));
-    pm_launch_frame(a, r->sm_count, events ? r->ev_mid[slot] : nullptr, !events, r->stream);
+    PM_CUDA(pm_launch_frame(a, r->sm_count, events ? r->ev_mid[slot] : nullptr, events ? r->ev_mid2[slot] : nullptr, !events, r->stream, &r->n_launches));
     if (events) PM_CUDA(cudaEventRecord(r->ev_end[slot], r->stream));
     PM_CUDA(cudaGetLastError());
     r->frame++;
@@ -292,7 +296,8 @@ int enqueue_frame(pm_renderer *r, bool debug_f32) {
 int finish_frames(pm_renderer *r, bool debug_f32) {
     for (int attempt = 0; attempt < 8; attempt++) {
         PM_CUDA(cudaStreamSynchronize(r->stream));
-        if (r->frame == 0 || r->report->n_overflow <= r->overflow_cap) return PM_OK;
+        // (the report is the last frame's only if its stamp says so: a stale one must not grow the pool)
+        if (r->frame == 0 || r->report->frame != r->stamp || r->report->n_overflow <= r->overflow_cap) return PM_OK;
         uint64_t want = std::max<uint64_t>((uint64_t)r->report->n_overflow + r->report->n_overflow / 4, (uint64_t)r->overflow_cap * 2);
         if (want > 0xf0000000ull) { g_last_error = "record pool would exceed 2^32 records"; return PM_ERR_NOMEM; }
         int st = ensure_pool(r, (uint32_t)want);
@@ -336,8 +341,10 @@ int install_scene(pm_renderer *r, const void *src, size_t len, cudaMemcpyKind ki
         PM_CUDA(cudaMalloc(&r->plan_a, ((size_t)r->n_items + 1) * sizeof(unsigned long long)));
         PM_CUDA(cudaMalloc(&r->plan_b, ((size_t)r->n_items + 1) * sizeof(unsigned long long)));
         if (r->item_info) PM_CUDA(cudaFree(r->item_info));
-        r->item_info = nullptr;
+        if (r->item_paint) PM_CUDA(cudaFree(r->item_paint));
+        r->item_info = nullptr; r->item_paint = nullptr;
         PM_CUDA(cudaMalloc(&r->item_info, ((size_t)r->n_items + 1) * sizeof(PmItemInfo)));
+        PM_CUDA(cudaMalloc(&r->item_paint, ((size_t)r->n_items + 1) * sizeof(float4)));
         r->plan_cap = (size_t)r->n_items + 1;
     }
     r->have_scene = true;
@@ -383,6 +390,7 @@ int pm_renderer_create(pm_renderer **out, const pm_config *cfg) {
     for (int i = 0; i < EVENT_RING; i++) {
         PM_TRY(cudaEventCreate(&r->ev_start[i]));
         PM_TRY(cudaEventCreate(&r->ev_mid[i]));
+        PM_TRY(cudaEventCreate(&r->ev_mid2[i]));
         PM_TRY(cudaEventCreate(&r->ev_end[i]));
     }
     PM_TRY(cudaMalloc(&r->counters, 2 * sizeof(PmBinCounters)));
@@ -399,6 +407,7 @@ int pm_renderer_create(pm_renderer **out, const pm_config *cfg) {
     for (int i = 0; i < 256; i++) { lut[i] = pm_srgb_byte_to_linear((uint32_t)i); lut[256 + i] = (float)i / 255.0f; }
     PM_TRY(cudaMemcpyAsync(r->lut, lut, sizeof lut, cudaMemcpyHostToDevice, r->stream));
     PM_TRY((cudaError_t)pm_fine_setup());
+    PM_TRY((cudaError_t)pm_heavy_setup());
     PM_TRY(cudaStreamSynchronize(r->stream));
 #undef PM_TRY
     *out = r;
@@ -409,13 +418,14 @@ void pm_renderer_destroy(pm_renderer *r) {
     if (!r) return;
     cudaSetDevice(r->device);
     if (r->stream) cudaStreamSynchronize(r->stream);
-    cudaFree(r->scene); cudaFree(r->plan_a); cudaFree(r->plan_b); cudaFree(r->bd); cudaFree(r->seg_info); cudaFree(r->piece_off); cudaFree(r->item_info); cudaFree(r->piece_info); cudaFree(r->row_info); cudaFree(r->debug); cudaFree(r->dev_err); cudaFree(r->dev_plan);
+    cudaFree(r->scene); cudaFree(r->plan_a); cudaFree(r->plan_b); cudaFree(r->bd); cudaFree(r->seg_info); cudaFree(r->piece_off); cudaFree(r->item_info); cudaFree(r->item_paint); cudaFree(r->piece_info); cudaFree(r->row_info); cudaFree(r->debug); cudaFree(r->dev_err); cudaFree(r->dev_plan);
     cudaFree(r->fb); cudaFree(r->fb32); cudaFree(r->occ); cudaFree(r->cnt); cudaFree(r->ovf); cudaFree(r->complex_list);
     cudaFree(r->pool); cudaFree(r->counters); cudaFree(r->queue); cudaFree(r->lut);
     if (r->report) cudaFreeHost(r->report);
     for (int i = 0; i < EVENT_RING; i++) {
         if (r->ev_start[i]) cudaEventDestroy(r->ev_start[i]);
         if (r->ev_mid[i]) cudaEventDestroy(r->ev_mid[i]);
+        if (r->ev_mid2[i]) cudaEventDestroy(r->ev_mid2[i]);
         if (r->ev_end[i]) cudaEventDestroy(r->ev_end[i]);
     }
     if (r->stream) cudaStreamDestroy(r->stream);
@@ -503,16 +513,19 @@ int pm_renderer_sync(pm_renderer *r, pm_frame_stats *stats) {
     if (stats) {
         memset(stats, 0, sizeof *stats);
         uint32_t n = r->frame_events ? std::min<uint32_t>(r->frames_unsynced, EVENT_RING) : 0;
-        double sum_total = 0, sum_bin = 0, sum_fine = 0;
+        double sum_total = 0, sum_bin = 0, sum_fine = 0, sum_heavy = 0;
         for (uint32_t k = 0; k < n; k++) {
             uint32_t slot = (r->frame - 1 - k) % EVENT_RING;
-            float t = 0, b = 0, f = 0;
+            float t = 0, b = 0, f = 0, h = 0;
             PM_CUDA(cudaEventElapsedTime(&t, r->ev_start[slot], r->ev_end[slot]));
             PM_CUDA(cudaEventElapsedTime(&b, r->ev_start[slot], r->ev_mid[slot]));
-            PM_CUDA(cudaEventElapsedTime(&f, r->ev_mid[slot], r->ev_end[slot]));
-            if (k == 0) { stats->ms_total = t; stats->ms_bin = b; stats->ms_fine = f; }
-            sum_total += t; sum_bin += b; sum_fine += f;
+            PM_CUDA(cudaEventElapsedTime(&h, r->ev_mid[slot], r->ev_mid2[slot]));
+            PM_CUDA(cudaEventElapsedTime(&f, r->ev_mid2[slot], r->ev_end[slot]));
+            if (k == 0) { stats->ms_total = t; stats->ms_bin = b; stats->ms_fine = f; stats->ms_heavy = h; }
+            sum_total += t; sum_bin += b; sum_fine += f; sum_heavy += h;
         }
+        stats->ms_heavy_sum = (float)sum_heavy;
+        stats->n_heavy_tiles = r->report->n_heavy;
         stats->frames = n;
         stats->ms_total_sum = (float)sum_total;
         stats->ms_bin_sum = (float)sum_bin;
@@ -520,7 +533,7 @@ int pm_renderer_sync(pm_renderer *r, pm_frame_stats *stats) {
         stats->n_tiles = (r->tile_y1 - r->tile_y0) * r->n_tx;
         stats->n_overflow_records = r->report->n_overflow;
         stats->n_complex_tiles = r->report->n_complex;
-        stats->n_launches = 3;  /* k_seg, k_row, k_fine */
+        stats->n_launches = r->n_launches;  /* k_seg, k_row, k_heavy, k_fine */
         stats->retries = r->retries - retries_before;
     }
     r->frames_unsynced = 0;
@@ -640,12 +653,14 @@ int pm_renderer_read_tile_items(pm_renderer *r, uint32_t *offsets, pm_tile_item 
             keyed.push_back({((uint64_t)q.item << 32) | q.key, idx});
         };
         for (uint32_t k = 0; k < std::min<uint32_t>(n, PM_TILE_SLOTS); k++) visit((uint32_t)(t * PM_TILE_SLOTS + k));
-        if (n > PM_TILE_SLOTS && (uint32_t)(ovf[t] >> 32) == stamp && (uint32_t)ovf[t] != PM_EXT_FAILED && (uint32_t)ovf[t] != 0) {
-            const uint32_t base1 = (uint32_t)ovf[t];  // 1 + index of the extension block's header
-            const uint32_t n_ext = std::min<uint32_t>(n, PM_TILE_SLOTS + PM_EXT_SLOTS) - PM_TILE_SLOTS;
-            for (uint32_t k = 0; k < n_ext && base1 + k < n_rec; k++) visit(base1 + k);
-            if (base1 - 1 < n_rec)
-                for (uint32_t cur = rec[base1 - 1].next; cur != 0 && cur - 1 < n_rec; cur = rec[cur - 1].next) visit(cur - 1);
+        if (n > PM_TILE_SLOTS && (uint32_t)(ovf[t] >> 32) == stamp) {
+            // the chain of overflow blocks (pm_pixel_logic.h): block j holds positions pm_blk_first(j) .. + pm_blk_size(j)
+            uint32_t link = (uint32_t)ovf[t], pos = PM_TILE_SLOTS;
+            for (uint32_t j = 0; link != 0 && link != PM_EXT_FAILED && link - 1 < n_rec && pos < n; j++) {
+                const uint32_t size = pm_blk_size(j);
+                for (uint32_t k = 0; k < size && pos < n && link + k < n_rec; k++, pos++) visit(link + k);
+                link = rec[link - 1].next;
+            }
         }
         std::sort(keyed.begin(), keyed.end());
         auto push = [&](uint32_t item, int32_t backdrop, uint32_t effect) {

@@ -112,7 +112,7 @@ def test_render_host_roundtrip(pm, renderer):
     renderer.init_scene(scene)
     renderer.draw()
     assert np.array_equal(img, renderer.read_rgba8())
-    assert stats.n_launches == 3 and stats.n_complex_tiles > 0
+    assert stats.n_launches == 4 and stats.n_complex_tiles > 0  # k_seg, k_row, k_heavy, k_fine
 
 
 def test_scene_device_pointer_path(pm, renderer):
@@ -138,6 +138,17 @@ def test_malformed_scene_is_rejected(pm, renderer):
     with pytest.raises(pm.PietMetalError) as e:
         renderer.init_scene(scene)
     assert e.value.status == pm.PM_ERR_SCENE_MALFORMED
+    # a points_ix that is 4 mod 8 would make the 64-bit point loads of binning fault: the device validator refuses it
+    scene = pm.build_scene(pm.SCENE_PATH_TEST, 320, 816).copy()
+    pix = int(scene[32:36].view(np.uint32)[0])
+    bad = np.concatenate([scene, np.zeros(8, np.uint8)])
+    bad[32:36].view(np.uint32)[0] = pix + 4
+    with pytest.raises(pm.PietMetalError) as e:
+        renderer.init_scene(bad)
+    assert e.value.status == pm.PM_ERR_SCENE_MALFORMED
+    renderer.init_scene(scene)  # ... and the renderer is still usable
+    renderer.draw()
+    renderer.read_rgba8()
 
 
 def test_deep_stacks_overflow_chain(pm, oracle, renderer):

@@ -77,6 +77,11 @@ def test_validate_rejects_out_of_range_refs(pm):
     assert pm.validate_scene(bad) == pm.PM_ERR_SCENE_MALFORMED
     bad = scene.copy(); bad[0:4].view(np.uint32)[0] = 1000         # n_items beyond the buffer
     assert pm.validate_scene(bad) == pm.PM_ERR_SCENE_MALFORMED
+    # refs must be 8-byte aligned (the kernels read points and Line end points with 64-bit loads; the reference's
+    # encoder only ever produces such refs, src/lib.rs:132-163, :224-240): 4 mod 8 is rejected, not faulted on
+    pix = int(scene[32:36].view(np.uint32)[0])
+    bad = np.concatenate([scene, np.zeros(8, np.uint8)]); bad[32:36].view(np.uint32)[0] = pix + 4
+    assert pm.validate_scene(bad) == pm.PM_ERR_SCENE_MALFORMED
 
 
 def test_library_exports_every_declared_symbol(pm):

@@ -5,6 +5,6 @@ for lib in piet-metal_b200/libpiet_metal_b200.so piet-metal_b200/variants/*.so; 
     PM_LIB=$PWD/$lib python bench.py --no-cpu-baseline --e2e-steps 1 ${BENCH_ARGS:-} 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']
-print('$lib rep$rep frame %.1f us fine %.1f us bin %.1f us'%(d['ms_per_step']*1e3, r['kernel_ms']*1e3, r['bin_kernel_ms']*1e3))"
+print('$lib rep$rep frame %.1f us fine %.1f us heavy %.1f us bin %.1f us'%(d['ms_per_step']*1e3, r['kernel_ms']*1e3, r.get('heavy_kernel_ms',0)*1e3, r['bin_kernel_ms']*1e3))"
   done
 done
