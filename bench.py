@@ -5,22 +5,23 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A step is one frame: the encoded scene (resident in HBM) -> binning kernels (k_seg, k_row) -> fill/blend
-kernel (k_fine) -> RGBA8 framebuffer in HBM.  With N GPUs the frame's tile rows are sharded into N contiguous
-row-strips (strong scaling: the frame is fixed); the scene is broadcast once over NCCL before the
-timed region and there is no collective per frame.  Rank 0 prints ONE JSON line.
+(k_heavy: the tiles with more than 16 records, one CTA or warp each; k_fine: every other tile, and the framebuffer)
+-> RGBA8 framebuffer in HBM.  With N GPUs the frame's tile rows are sharded into N contiguous row-strips (strong
+scaling: the frame is fixed); the scene is broadcast once over NCCL before the timed region and there is no
+collective per frame.  Rank 0 prints ONE JSON line.
 
-  value      whole-frame Mpixel/s, K frames back to back (launches overlapped, no per-frame events),
-             device-timed with CUDA events around the K frames, max over ranks
-  e2e        the same metric through the C-ABI call pm_renderer_render_host: scene bytes in pinned
-             host memory -> H2D -> frame -> D2H of the strip's pixels into pinned host memory
-  roofline   fill/blend kernel: algorithmic bytes (4*W*H_strip + scene) / its CUDA-event duration (a second
-             pass of K frames with per-frame events on the render stream), against the measured HBM copy
-             bandwidth in MEASURED_PEAKS.json
-  cpu_baseline   the oracle (scalar port of the reference's tile loop) on the host cores, on a
-             bounded band of tile rows of the same frame
+  value      whole-frame Mpixel/s: K frames, each bracketed by a CUDA event pair on the render stream; the step time
+             is the mean per-frame time, max over ranks.  The same method for every N; when a rank's strip fits the
+             L2, every rank flushes the L2 between frames (outside the event pairs)
+  e2e        the same metric through the C-ABI call pm_renderer_render_host: scene bytes in pinned host memory ->
+             H2D -> validate + plan -> frame -> D2H of the strip's pixels into pinned host memory
+  roofline   fill/blend kernel k_fine: algorithmic bytes (4*W*H_strip - heavy tiles + scene) / its CUDA-event
+             duration (second pass, every kernel group timed on its own), against the measured HBM copy bandwidth
+             in MEASURED_PEAKS.json
+  cpu_baseline   the oracle (CPU port of the reference's tile loop, pinned to the reference's own shader) on the
+             host cores: whole frames of the same workload for about 10 s
 
---impl reference times that CPU port alone (the reference itself is Metal/Rust/Objective-C and
-cannot be built here), rank 0 only.
+--impl reference times that CPU port alone on whole frames of the same workload, rank 0 only.
 """
 import argparse
 import json
@@ -48,9 +49,8 @@ def parse_args():
     ap.add_argument("--size", type=int, default=8192, help="surface edge in pixels (BASELINE: 8192)")
     ap.add_argument("--scene", default="tiger", choices=["tiger", "rand_bezier", "glyphs"])
     ap.add_argument("--e2e-steps", type=int, default=10)
-    ap.add_argument("--cpu-rows", type=int, default=0, help="tile rows in the CPU sample (0 = auto, ~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--frame-events", action="store_true", help="keep per-frame CUDA events in the headline pass (no launch overlap)")
+    ap.add_argument("--frame-events", action="store_true", help="(kept for old scripts; the kernel-time pass always runs)")
     ap.add_argument("--equal-strips", action="store_true", help="equal-height row strips instead of cost-balanced ones")
     ap.add_argument("--emulate-world", default="", help="experiments on 1 GPU: 'N:g' renders the strip rank g of N would own")
     return ap.parse_args()
@@ -121,62 +121,54 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def cpu_sample(scene, size, rows_hint, min_seconds=8.0):
-    """Time the oracle (all host cores) on the same frame: the whole frame, or a centred band of
-    `rows_hint` tile rows, repeated until about `min_seconds` of wall time have gone by."""
+def workload_name(args):
+    return "Ghostscript_Tiger %dx%d" % (args.size, args.size) if args.scene == "tiger" else "%s %dx%d" % (args.scene, args.size, args.size)
+
+
+def cpu_frames(scene, size, threads, n_frames=None, min_seconds=None):
+    """The oracle (all host cores) on WHOLE frames of the workload.  Either exactly n_frames, or as many as
+    fill min_seconds.  Returns (frames, seconds)."""
     import oracle_api
-    threads = host_threads()
     nty = (size + 15) // 16
-    rows = rows_hint if rows_hint > 0 else nty
-    y0 = max(0, nty // 2 - rows // 2)
-    y1 = min(nty, y0 + rows)
-    px = (min(y1 * 16, size) - y0 * 16) * size
-    oracle_api.render(scene, size, size, tile_y0=y0, tile_y1=min(y1, y0 + 2), threads=threads)  # warm the thread pool
+    oracle_api.render(scene, size, size, tile_y0=0, tile_y1=min(2, nty), threads=threads)  # warm the thread pool
     reps, t0 = 0, time.perf_counter()
     while True:
-        oracle_api.render(scene, size, size, tile_y0=y0, tile_y1=y1, threads=threads)
+        oracle_api.render(scene, size, size, threads=threads)
         reps += 1
         dt = time.perf_counter() - t0
-        if dt >= min_seconds or reps >= 200:
-            break
-    desc = "tile rows %d..%d of %d x %d repetitions, %.1f s wall on %d threads" % (y0, y1, nty, reps, dt, threads)
-    return px * reps / dt / 1e6, desc, threads
+        if (n_frames is not None and reps >= n_frames) or (min_seconds is not None and dt >= min_seconds):
+            return reps, dt
 
 
 def run_reference(args, rank):
-    """--impl reference: the CPU port of the reference's tile loop on this box's host cores (the
-    reference itself -- Metal kernels, Rust feed -- cannot be built here)."""
+    """--impl reference: the reference's tile loop on this box's host cores -- oracle/pm_oracle.c, the CPU port that
+    tests/test_ref_pin.py pins bit for bit to the reference's own PietRender.metal (oracle/_ref; that build is
+    limited to the reference's 4096 x 4096 surfaces and is 6x slower than the port, so the port is what is timed).
+    Every step renders the WHOLE frame of the same workload; if steps + warmup full frames would take more than
+    ~4 minutes, the step count is cut (and reported), never the frame."""
     if rank != 0:
         return
     import __graft_entry__ as ge
-    import oracle_api
     pm = ge.load_package()
     scene = scene_for(pm, args)
     threads = host_threads()
-    nty = (args.size + 15) // 16
-    # each step is a bounded sample (a centred band of tile rows) so that steps + warmup end within minutes
-    t = time.perf_counter()
-    oracle_api.render(scene, args.size, args.size, tile_y0=nty // 2, tile_y1=nty // 2 + 2, threads=threads)
-    per_row = (time.perf_counter() - t) / 2
-    budget = 120.0 / max(1, args.steps + args.warmup)
-    rows = int(max(1, min(nty, budget / max(per_row, 1e-6))))
-    y0 = max(0, nty // 2 - rows // 2)
-    y1 = min(nty, y0 + rows)
-    for _ in range(args.warmup):
-        oracle_api.render(scene, args.size, args.size, tile_y0=y0, tile_y1=y1, threads=threads)
-    t = time.perf_counter()
-    for _ in range(args.steps):
-        oracle_api.render(scene, args.size, args.size, tile_y0=y0, tile_y1=y1, threads=threads)
-    dt = time.perf_counter() - t
-    px = (min(y1 * 16, args.size) - y0 * 16) * args.size
-    value = px * args.steps / dt / 1e6
-    sample = "tile rows %d..%d of %d per step, %d threads" % (y0, y1, nty, threads)
+    _, t1 = cpu_frames(scene, args.size, threads, n_frames=1)
+    budget = 240.0
+    warmup = max(0, min(args.warmup, int(0.1 * budget / t1)))
+    steps = max(1, min(args.steps, int(0.9 * budget / t1)))
+    if warmup:
+        cpu_frames(scene, args.size, threads, n_frames=warmup)
+    _, dt = cpu_frames(scene, args.size, threads, n_frames=steps)
+    value = args.size * args.size * steps / dt / 1e6
+    sample = "%d whole frames, %.1f s wall on %d threads" % (steps, dt, threads)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Ghostscript_Tiger %dx%d" % (args.size, args.size) if args.scene == "tiger" else "%s %dx%d" % (args.scene, args.size, args.size),
-                   "implementation": "CPU port of the PietRender.metal tile loop (oracle/pm_oracle.c), OpenMP", "sample": sample},
+        "config": {"workload": workload_name(args), "tile": "16x16",
+                   "implementation": "CPU port of the PietRender.metal tile loop (oracle/pm_oracle.c, pinned to the reference's own "
+                                     "shader by tests/test_ref_pin.py), OpenMP over tile rows", "sample": sample,
+                   "requested_steps": args.steps, "requested_warmup": args.warmup},
         "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -237,7 +229,14 @@ def main():
     r.set_scene_device(scene_dev.data_ptr(), scene_bytes)
     strip_rows = r.strip_rows
     fb_bytes = strip_rows * size * 4
-    flush = fb_bytes <= L2_BYTES  # the strip would stay L2-resident between frames: flush L2 between timed frames
+    # Timing, decided once for ALL ranks: if ANY rank's strip fits the L2, every rank writes a 256 MiB buffer between
+    # frames so that each frame streams its framebuffer to HBM, and frames are timed by per-frame event pairs (the
+    # flush is outside them).  Otherwise the frames run back to back inside one event pair.  Inside a frame the
+    # kernels overlap either way (programmatic dependent launch, the heavy-tile kernel beside the fill/blend kernel).
+    t = torch.tensor([fb_bytes], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    flush = int(t.item()) <= L2_BYTES
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda") if flush else None
     stream = torch.cuda.ExternalStream(r.stream(), device=torch.device('cuda', local_rank))
 
@@ -247,28 +246,24 @@ def main():
         torch.cuda.synchronize()
 
     def frames(k):
-        """k frames; returns (device ms summed over the frames, fill-kernel ms summed)."""
-        if not flush:
-            for _ in range(k):
+        """k frames; returns (summed per-frame device ms, stats of the last sync)."""
+        total, done, st = 0.0, 0, None
+        while done < k:
+            chunk = min(256, k - done)  # (the renderer keeps the event pairs of the last 512 frames)
+            for _ in range(chunk):
+                if flush:
+                    with torch.cuda.stream(stream):
+                        flush_buf.zero_()
                 r.draw()
             st = r.sync()
-            scale = k / max(1, st.frames)  # per-frame event pairs kept for the last <= 512 frames (+ any pool-growth re-render)
-            return st.ms_total_sum * scale, st.ms_fine_sum * scale, st
-        total = fine = 0.0
-        st = None
-        for _ in range(k):
-            with torch.cuda.stream(stream):
-                flush_buf.zero_()
-            r.draw()
-            st = r.sync()
-            total += st.ms_total
-            fine += st.ms_fine
-        return total, fine, st
+            total += st.ms_total_sum * (chunk / max(1, st.frames))  # (st.frames > chunk only after a pool-growth re-render)
+            done += chunk
+        return total, st
 
-    # Headline pass: no per-frame events, so that the frame's kernels (and consecutive frames) overlap their
-    # launches; the fill kernel's own duration is measured in a second pass with per-frame events.
-    overlap = (not flush) and not args.frame_events
-    r.set_frame_events(not overlap)
+    # No flush (every strip larger than L2): the K frames are enqueued back to back without events -- consecutive
+    # frames are chained by programmatic dependent launch like the kernels inside a frame -- and timed by one event
+    # pair around all of them.  Flush: per-frame event pairs (the kernels inside a frame still overlap), summed.
+    r.set_frame_events(2 if flush else 0)
     frames(max(3, args.warmup))
     sampler = ClockSampler(local_rank)
     barrier()
@@ -277,41 +272,34 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         ev0.record()
-    ms_sum, ms_fine_sum, st = frames(args.steps)
+    ms_sum, st = frames(args.steps)
     with torch.cuda.stream(stream):
         ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    wall_ms = ev0.elapsed_time(ev1)
-    # back-to-back frames: the event bracket is the step time; with L2 flushes in between, the sum of the
-    # per-frame event pairs is (the flush is not part of a step)
-    if overlap:  # second pass, per-frame CUDA events on the render stream: binning / fill kernel times
-        r.set_frame_events(True)
-        frames(3)
-        ms_sum, ms_fine_sum, st = frames(args.steps)
-    my_ms = ms_sum if flush else wall_ms
-    t = torch.tensor([my_ms, ms_fine_sum], dtype=torch.float64, device="cuda")
+    if not flush:
+        ms_sum = ev0.elapsed_time(ev1)
+    # second pass, every kernel group timed on its own (serial): binning / heavy tiles / fill-blend
+    r.set_frame_events(1)
+    frames(3)
+    _, stk = frames(min(args.steps, 256))
+    nk = max(1, stk.frames)
+    fine_ms, bin_ms, heavy_ms = stk.ms_fine_sum / nk, stk.ms_bin_sum / nk, stk.ms_heavy_sum / nk
+    t = torch.tensor([ms_sum, fine_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_fine_total = float(t[0]), float(t[1])
+    ms_total, fine_ms_max = float(t[0]), float(t[1])
     ms_per_step = ms_total / args.steps
     value = size * size / (ms_per_step * 1e-3) / 1e6
 
     # ---- roofline of the fill/blend kernel (this rank's strip; max duration over ranks) ----
+    # algorithmic bytes: the strip's RGBA8 pixels, stored exactly once, minus the tiles k_heavy stores, plus the scene
     peak, peak_src = measured_peak()
-    fine_ms = ms_fine_total / args.steps
-    algo_bytes = fb_bytes + scene_bytes
-    achieved = algo_bytes / (fine_ms * 1e-3) / 1e9
-    traffic = None  # DRAM bytes per launch of the fill kernel from the committed ncu capture of this very workload
-    if world == 1 and size == 8192 and args.scene == "tiger":
-        try:
-            import glob
-            with open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_fine_traffic.json")))[-1]) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+    algo_bytes = fb_bytes - int(stk.n_heavy_tiles) * 1024 + scene_bytes
+    achieved = algo_bytes / (fine_ms_max * 1e-3) / 1e9
 
-    # ---- e2e: host scene bytes -> H2D -> frame -> D2H pixels, through pm_renderer_render_host ----
+    # ---- e2e: host scene bytes -> H2D -> plan -> frame -> D2H pixels, through pm_renderer_render_host ----
+    r.set_frame_events(0)
     host_scene = torch.empty(scene_bytes, dtype=torch.uint8).pin_memory()
     host_scene.copy_(scene_dev.cpu())
     host_out = torch.empty((strip_rows, size, 4), dtype=torch.uint8).pin_memory()
@@ -324,6 +312,7 @@ def main():
         r.render_host(hs, ho)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    plan_ms = r.sync().ms_plan
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -336,27 +325,33 @@ def main():
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "Ghostscript_Tiger %dx%d" % (size, size) if args.scene == "tiger" else "%s %dx%d" % (args.scene, size, size),
+                "workload": workload_name(args),
                 "scene_bytes": scene_bytes, "tile": "16x16", "parallelism": "row-strips x%d (%s)" % (world, "equal height" if args.equal_strips or world == 1 else "cost-balanced"),
-                "strip_tile_rows": [bounds[g + 1] - bounds[g] for g in range(world)],
-                "l2": ("flushed between timed frames (strip %.0f MiB <= L2)" % (fb_bytes / 2**20)) if flush
-                      else "framebuffer strip %.0f MiB > 126 MB L2: every frame streams to HBM" % (fb_bytes / 2**20),
-                "timing": "sum of per-frame CUDA event pairs" if flush else "CUDA events around %d back-to-back frames" % args.steps,
-                "launch_overlap": "programmatic dependent launch between the frame's kernels and between frames" if overlap else "none (per-frame events)",
+                "strip_tile_rows": [bounds[g + 1] - bounds[g] for g in range(len(bounds) - 1)],
+                "timing": ("per-frame CUDA event pairs on the render stream, summed (kernels of a frame overlapped by programmatic dependent launch)"
+                           if flush else "one CUDA event pair around %d back-to-back frames (kernels and consecutive frames overlapped by programmatic "
+                           "dependent launch)" % args.steps) + "; max over ranks; the choice is the same on every rank",
+                "l2": "256 MiB written between frames, outside the event pairs (a strip of this run fits the 126 MB L2)" if flush
+                      else "framebuffer strip %.0f MiB > 126 MB L2 on every rank: every frame streams to HBM" % (fb_bytes / 2**20),
             },
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": fb_bytes,
-                    "steps": args.e2e_steps, "call": "pm_renderer_render_host (pinned host buffers)"},
+                    "steps": args.e2e_steps, "call": "pm_renderer_render_host (pinned host buffers): upload, validate, plan, frame, read-back",
+                    "plan_ms": plan_ms},
             "gpu_launches": int(st.n_launches) * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "k_fine (fill/blend)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": fine_ms,
-                         "bin_kernel_ms": st.ms_bin_sum / max(1, st.frames), "heavy_kernel_ms": st.ms_heavy_sum / max(1, st.frames)},
+            "roofline": {"bound": "hbm", "kernel": "k_fine (fill/blend: stores the framebuffer)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "traffic_note": "not measured in this run; the ncu capture of this workload is profiles/r02_ncu_summary.json",
+                         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": fine_ms_max,
+                         "bin_kernel_ms": bin_ms, "heavy_kernel_ms": heavy_ms, "plan_ms": plan_ms,
+                         "note": "kernel times from a second pass with every kernel group timed on its own (no overlap)"},
             "frame_stats": {"overflow_records": st.n_overflow_records, "complex_tiles": st.n_complex_tiles, "heavy_tiles": st.n_heavy_tiles, "tiles": st.n_tiles},
         }
-        if world == 1 and not args.no_cpu_baseline:  # (the CPU leg is timed at N=1 only)
-            v, desc, threads = cpu_sample(scene_host, size, args.cpu_rows)
-            out["cpu_baseline"] = {"value": v, "unit": "Mpixel/s", "cores": threads, "kind": "port", "sample": desc}
+        if world == 1 and not args.no_cpu_baseline and not args.emulate_world:  # (the CPU leg is timed at N=1 only)
+            threads = host_threads()
+            reps, dt = cpu_frames(scene_host, size, threads, min_seconds=10.0)
+            out["cpu_baseline"] = {"value": size * size * reps / dt / 1e6, "unit": "Mpixel/s", "cores": threads, "kind": "port",
+                                   "sample": "%d whole frames of the same workload, %.1f s wall on %d threads" % (reps, dt, threads)}
     r.close()
     if world > 1:
         dist.barrier()

@@ -176,6 +176,8 @@ typedef struct pm_frame_stats {
                                 ms_fine; with frame events off it runs beside the fill/blend kernel) */
     float ms_heavy_sum;
     uint32_t n_heavy_tiles;  /* tiles with more records than inline slots (last frame) */
+    float ms_plan;           /* host wall time of the last per-scene plan (once per scene / size / strip; it is part of
+                                the first frame after set_scene and of every pm_renderer_render_host call) */
 } pm_frame_stats;
 
 int pm_renderer_create(pm_renderer **out, const pm_config *cfg);
@@ -195,10 +197,14 @@ int pm_renderer_set_scene_device(pm_renderer *r, const void *scene_dev, size_t l
 
 /* Enqueue one frame on the renderer's stream (asynchronous, like drawInMTKView's commit). */
 int pm_renderer_render(pm_renderer *r);
-/* Per-frame CUDA events (the ms_* fields of pm_frame_stats) are recorded by default.  With them disabled the
- * three kernels of a frame, and consecutive frames, are chained by programmatic dependent launch: each kernel's
- * launch and prologue overlap the tail of the one before it, like the reference's back-to-back command buffers
- * (TestApp/PietRenderer.m:59-103 commits and never waits).  pm_frame_stats then reports frames = 0 and no times. */
+/* Per-frame CUDA events (the ms_* fields of pm_frame_stats):
+ *   1 (default)  events around binning, the heavy-tile kernel and the fill/blend kernel: every kernel is timed, the
+ *                kernels of a frame run one after the other;
+ *   2            events around the frame only (ms_total): inside the frame the kernels are chained by programmatic
+ *                dependent launch -- each kernel's launch and prologue overlap the tail of the one before it, and the
+ *                heavy-tile kernel runs beside the fill/blend kernel;
+ *   0            no events: consecutive frames are chained the same way, like the reference's back-to-back command
+ *                buffers (TestApp/PietRenderer.m:59-103 commits and never waits); pm_frame_stats reports frames = 0. */
 int pm_renderer_set_frame_events(pm_renderer *r, int enabled);
 /* Wait for the stream; report the last frame's statistics (stats may be NULL). */
 int pm_renderer_sync(pm_renderer *r, pm_frame_stats *stats);

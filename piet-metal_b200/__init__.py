@@ -52,7 +52,8 @@ class FrameStats(ctypes.Structure):
                 ("frames", ctypes.c_uint32), ("ms_total_sum", ctypes.c_float), ("ms_bin_sum", ctypes.c_float),
                 ("ms_fine_sum", ctypes.c_float), ("n_tiles", ctypes.c_uint32), ("n_overflow_records", ctypes.c_uint32),
                 ("n_complex_tiles", ctypes.c_uint32), ("n_launches", ctypes.c_uint32), ("retries", ctypes.c_uint32),
-                ("ms_heavy", ctypes.c_float), ("ms_heavy_sum", ctypes.c_float), ("n_heavy_tiles", ctypes.c_uint32)]
+                ("ms_heavy", ctypes.c_float), ("ms_heavy_sum", ctypes.c_float), ("n_heavy_tiles", ctypes.c_uint32),
+                ("ms_plan", ctypes.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -302,8 +303,8 @@ class PietRenderer:
     render = draw
 
     def set_frame_events(self, enabled):
-        """Per-frame CUDA events on/off (off: the frame's kernels overlap their launches; no per-frame times)."""
-        _check(_lib().pm_renderer_set_frame_events(self._h, 1 if enabled else 0), "pm_renderer_set_frame_events")
+        """0 / False: no events, frames overlap; 1 / True: every kernel timed (serial); 2: the frame timed, its kernels overlap."""
+        _check(_lib().pm_renderer_set_frame_events(self._h, int(enabled)), "pm_renderer_set_frame_events")
 
     def sync(self):
         st = FrameStats()

@@ -36,11 +36,13 @@ namespace {
 
 typedef unsigned long long u64;
 
+// 4 CTAs of 7 warps per SM: 72 registers per thread, 28 resident warps.  Measured on the 8192^2 tiger (k_fine alone):
+// 7 x 4 at 72 registers 103 us, 8 x 3 at 80 registers 106 us, 8 x 4 at 64 registers (a few spills) 111 us.
 #ifndef PM_FINE_WARPS
-#define PM_FINE_WARPS 8
+#define PM_FINE_WARPS 7
 #endif
 #ifndef PM_FINE_CTAS
-#define PM_FINE_CTAS 4           // CTAs per SM the kernel is compiled for (4 x 8 warps: 64 registers)
+#define PM_FINE_CTAS 4
 #endif
 #ifndef PM_FINE_PEND
 #define PM_FINE_PEND 0           // 1: the claim of tile i+3 is in flight while tile i is rendered (measured: +6 us, the
@@ -50,7 +52,7 @@ typedef unsigned long long u64;
 #define PM_FINE_SOLID_EVERY 4    // one warp in this many prefers the solid batches, the rest the tiles with records
 #endif
 
-// Per-warp shared-memory state (6,720 bytes; 8 warps: 52.5 KB per CTA, four CTAs per SM).
+// Per-warp shared-memory state (6,720 bytes; 7 warps: 46 KB per CTA, four CTAs per SM).
 struct FineWarpSmem {
     int acc[256];             // coverage of the item being drawn (pm_cover.cuh)
     int cov[256];
@@ -423,7 +425,9 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
             if (v_next) {
                 fine_fetch_entry(L, w, 1, p, lane);
                 ph |= p >= L.n_medium ? 2u : 0u;
+#if PM_FINE_PEND
                 pend = fine_claim(A, lane);
+#endif
             }
             uint32_t b = 0;
             for (;;) {

@@ -1,27 +1,34 @@
-// k_heavy: fill/blend of the tiles with more records than k_fine takes (PM_HEAVY_MIN = 17: more than the inline slots;
-// sm_100a), one CTA per tile.
-// Same arithmetic as k_fine (renderKernel, TestApp/PietRender.metal:457-566; pm_cover.cuh, pm_pixel_logic.h), other
-// decomposition: such a tile has tens to thousands of records -- coincident outlines, deep stacks of translucent
-// layers, a whole drawing squeezed into a few tiles -- and on one warp it is the frame's critical path (a warp
-// issues ~0.1 instructions per cycle: 60-110 us for the tiger's worst tiles at 8192^2, milliseconds at 256^2).
+// k_heavy: fill/blend of the tiles with more records than k_fine takes (PM_HEAVY_MIN = 17: more than the inline
+// slots; sm_100a).  Same arithmetic as k_fine (renderKernel, TestApp/PietRender.metal:457-566; pm_cover.cuh,
+// pm_pixel_logic.h), other decompositions: such a tile has tens to thousands of records -- coincident outlines, deep
+// stacks of translucent layers, a whole drawing squeezed into a few tiles.  Rendered the way k_fine renders a light
+// tile, one of the tiger's worst tiles at 8192^2 keeps a warp busy for 60-110 us (a warp issues ~0.1 instructions per
+// cycle) and the whole 256^2 tiger takes milliseconds: that is the critical path of a narrow multi-GPU strip.
 //
-// Per tile, 8 warps:
-//   1. the tile's records (inline slots + the chain of overflow blocks, pm_pixel_logic.h) are keyed
-//      (item, trailer first, position) and sorted in shared memory (bitonic): the records of an item become a
-//      contiguous run, the runs are in painter's order;
-//   2. the items are taken eight at a time: warp w accumulates the coverage of item 8 g + w into its own coverage
-//      arrays (compositing is ordered, coverage is not: the eight items are independent);
-//   3. thread t owns pixel (t / 16, t % 16) with its linear colour in three registers and blends the eight layers
-//      in order; encode and store once per tile.
-// A tile with more than PM_HEAVY_SORT_CAP records (a 16x16-pixel tile crossed by > 4096 segments) is drawn without
-// the sort: one pass over all its records per item (correct, slow, never seen outside of stress tests).
-// Integer coverage sums and the same per-pixel functions as k_fine: which kernel draws a tile does not change a
-// single bit of its pixels.
+// Two modes, chosen per frame from the number of heavy tiles:
+//   * few heavy tiles (latency matters): one CTA of 8 warps per tile.
+//       1. the tile's records (inline slots + the chain of overflow blocks, pm_pixel_logic.h) are keyed
+//          (item, trailer first, position) and sorted in shared memory (bitonic): the records of an item become a
+//          contiguous run, the runs are in painter's order;
+//       2. the items are taken eight at a time: warp w accumulates the coverage of item 8 g + w into its own
+//          coverage arrays and resolves it to a per-pixel alpha (compositing is ordered, coverage is not);
+//       3. thread t owns pixel (t / 16, t % 16) with its linear colour in three registers and blends the eight
+//          layers in order: one load and two FMAs per channel and layer; encode and store once per tile.
+//     A tile with more than PM_HEAVY_SORT_CAP records (a 16x16-pixel tile crossed by > 4096 segments) is drawn
+//     without the sort: one pass over all its records per item (correct, slow, only seen in stress tests).
+//   * many heavy tiles (throughput matters: the 10 k Bezier and 100 k glyph scenes have 40 k+ of them): one WARP
+//     per tile with up to PM_HEAVY_WARP_CAP records (pm_heavy_warp.cuh); the few larger tiles are then drawn
+//     CTA-wise as above.
+// (Sixteen warps per CTA were measured: a heavy tile is not faster -- its time is sort, loads and the slowest
+// item -- and two such CTAs take all of an SM's registers away from k_fine.)
+// Integer coverage sums and the same per-pixel functions everywhere: which kernel or mode draws a tile does not
+// change a single bit of its pixels.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/piet_metal_b200.h"
 #include "pm_cover.cuh"
+#include "pm_heavy_warp.cuh"
 #include "pm_kernels.h"
 #include "pm_pixel_logic.h"
 #include "pm_scene_format.h"
@@ -33,38 +40,32 @@ typedef unsigned long long u64;
 #define PM_HEAVY_WARPS 8
 #define PM_HEAVY_THREADS (PM_HEAVY_WARPS * 32)
 #define PM_HEAVY_SORT_CAP 4096u
-#define PM_HEAVY_DIR_CAP 128u   // overflow blocks indexed per tile: 1488 + 123 * 768 slots ~ 96 k records; the rest is not drawn
+#define PM_HEAVY_DIR_CAP 128u     // overflow blocks indexed per tile (CTA mode): 1488 + 123 * 768 slots ~ 96 k records; the rest is not drawn
 
-struct HeavyMeta { uint32_t kind, w0, w1, pad; float4 paint; };
+struct HeavyWarpState {          // warp mode, per warp (shares its memory with the CTA mode's sort arrays)
+    float4 rgb[3][2][32];        // the tile's linear colour, lane-private (as in k_fine)
+    uint32_t dir[PM_HEAVY_WARP_DIR];
+    uint32_t pad[12];
+};
+
+struct HeavyMeta { float4 paint; uint32_t valid, pad[3]; };
 
 struct HeavySmem {
     int acc[PM_HEAVY_WARPS][256];
     int cov[PM_HEAVY_WARPS][256];
-    u64 keys[PM_HEAVY_SORT_CAP];               // (item << 32) | (geometry ? 1 << 31 : 0) | position; dropped records: all ones
-    uint16_t starts[PM_HEAVY_SORT_CAP + 8];    // sorted position of every item's first record, then the number of live records
+    union {
+        struct {
+            u64 keys[PM_HEAVY_SORT_CAP];           // CTA mode: (item << 32) | (geometry ? 1 << 31 : 0) | position; dropped records: all ones
+            uint16_t starts[PM_HEAVY_SORT_CAP + 8];// sorted position of every item's first record, then the number of live records
+        };
+        HeavyWarpState ws[PM_HEAVY_WARPS];         // warp mode
+    };
     uint32_t dir[PM_HEAVY_DIR_CAP];            // 1 + pool index of the header of overflow block j
     HeavyMeta meta[PM_HEAVY_WARPS];
     u64 cw, ow, vw;
     uint32_t red[PM_HEAVY_WARPS];
-    uint32_t entry, n_live, n_items, n_blocks, tile_next;
+    uint32_t reach, n_live, n_items, tile_next;
 };
-
-__device__ __forceinline__ PmRecord load_record(const PmRecord *pool, uint32_t idx) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(&pool[idx]);
-    const uint4 a = src[0], b = src[1];
-    PmRecord r;
-    r.item = a.x; r.key = a.y; r.p[0] = pm_u2f(a.z); r.p[1] = pm_u2f(a.w);
-    r.p[2] = pm_u2f(b.x); r.p[3] = pm_u2f(b.y); r.edge_y = pm_u2f(b.z); r.next = b.w;
-    return r;
-}
-
-// pool index of the tile's record at position pos (pos < the number of indexed records)
-__device__ __forceinline__ uint32_t heavy_index(const HeavySmem *sh, size_t tile, uint32_t pos) {
-    if (pos < PM_TILE_SLOTS) return (uint32_t)tile * PM_TILE_SLOTS + pos;
-    uint32_t j, off;
-    pm_ovf_locate(pos - PM_TILE_SLOTS, &j, &off);
-    return sh->dir[j] + off;
-}
 
 __device__ __forceinline__ uint32_t block_min(uint32_t v, HeavySmem *sh, uint32_t lane, uint32_t warp) {
     v = __reduce_min_sync(PM_FULL_MASK, v);
@@ -77,71 +78,53 @@ __device__ __forceinline__ uint32_t block_min(uint32_t v, HeavySmem *sh, uint32_
     return m;
 }
 
-// alpha of this thread's pixel for the layer whose coverage warp slot `s` holds; clears the slot's cell
-__device__ __forceinline__ float heavy_alpha(HeavySmem *sh, int s, const HeavyMeta &m, int cell, uint32_t px, float fx, float fy) {
-    const uint32_t kind = m.kind;
-    if (kind == PM_REC_DRAWFILL) {
-        const int a = sh->acc[s][cell], c = sh->cov[s][cell];
-        sh->acc[s][cell] = 0;
-        sh->cov[s][cell] = 0;
-        int run = c;  // covers of the pixels to the left carry into this one: inclusive scan over the row's 16 lanes
-        #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
-            const int v = __shfl_up_sync(PM_FULL_MASK, run, o, 16);
-            if ((int)px >= o) run += v;
-        }
-        return pm_resolve_fill_alpha(a + run, (int)m.w0);
-    }
-    if (kind == PM_REC_STROKE) {  // renderDf, metal:58-60
-        const int a = sh->acc[s][cell];
-        sh->acc[s][cell] = 0;
-        return a ? pm_saturate(pm_u2f(m.w0) + 0.5f - __uint_as_float(~(uint32_t)a)) : 0.0f;
-    }
-    if (kind == PM_REC_CIRCLE) return pm_px_circle_alpha(m.w0, m.w1, fx, fy);
-    return 1.0f;  // PM_REC_SOLID: a translucent full cover
+// ---------------------------------------------------------------------------------------------------------------
+// CTA mode
+// ---------------------------------------------------------------------------------------------------------------
+
+// The layer a warp has prepared: alpha * paint.a of every pixel goes into the warp's acc array as float bits.
+__device__ __forceinline__ void heavy_publish_layer(HeavySmem *sh, uint32_t warp, uint32_t kind, uint32_t w0, uint32_t w1, float4 paint,
+                                                    float tile_x0, float tile_y0, uint32_t lane) {
+    float al[8];
+    pm_heavy_resolve8(sh->acc[warp], sh->cov[warp], kind, w0, w1, tile_x0, tile_y0, lane, al);
+    const uint32_t prow = lane >> 1, half = lane & 1u;
+    const int off0 = pm_cov_swz((int)prow, (int)half * 8), off1 = pm_cov_swz((int)prow, (int)half * 8 + 4);
+    *reinterpret_cast<float4 *>(&sh->acc[warp][off0]) = make_float4(al[0] * paint.w, al[1] * paint.w, al[2] * paint.w, al[3] * paint.w);
+    *reinterpret_cast<float4 *>(&sh->acc[warp][off1]) = make_float4(al[4] * paint.w, al[5] * paint.w, al[6] * paint.w, al[7] * paint.w);
+    if (lane == 0) { sh->meta[warp].paint = paint; sh->meta[warp].valid = 1u; }
 }
 
 template <bool F32, bool EXACT>
-__device__ void heavy_tile(const PmFrameArgs &A, HeavySmem *sh, uint32_t entry) {
+__device__ void heavy_tile_cta(const PmFrameArgs &A, HeavySmem *sh, uint32_t entry, uint32_t n_min) {
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     const uint32_t trow = entry >> 16, tx = entry & 0xffffu;
     const size_t tile = (size_t)trow * A.n_tx + tx;
-    if (t == 0) { sh->cw = A.cnt[tile]; sh->ow = A.occ[tile]; sh->vw = A.ovf[tile]; sh->n_live = 0; }
-    __syncthreads();
-    const u64 cw = sh->cw, ow = sh->ow, vw = sh->vw;
-    uint32_t n = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
-    const uint32_t occ_item1 = (uint32_t)(ow >> 32) == A.stamp ? (uint32_t)ow : 0u;
-    // directory of the overflow blocks (a frame whose pool ran out has fewer blocks than cnt says: the host renders
-    // such a frame again with a larger pool, this pass only must not fault)
     if (t == 0) {
-        uint32_t nb = 0, reach = PM_TILE_SLOTS;
-        if (n > PM_TILE_SLOTS) {
-            uint32_t link = (uint32_t)(vw >> 32) == A.stamp ? (uint32_t)vw : 0u;
-            while (link != 0 && link != PM_EXT_FAILED && nb < PM_HEAVY_DIR_CAP && reach < n) {
-                sh->dir[nb] = link;
-                reach += pm_blk_size(nb);
-                nb++;
-                if (reach < n) link = A.pool[link - 1u].next;
-            }
-        }
-        sh->n_blocks = nb;
-        sh->entry = reach;  // (records reachable; `entry` is reused as scratch here)
+        const u64 cw = A.cnt[tile], vw = A.ovf[tile];
+        sh->cw = cw; sh->ow = A.occ[tile]; sh->vw = vw; sh->n_live = 0;
+        const uint32_t n0 = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
+        sh->reach = (n0 > PM_TILE_SLOTS && n0 >= n_min) ? pm_heavy_walk(A, vw, n0, sh->dir, PM_HEAVY_DIR_CAP) : n0;
     }
     __syncthreads();
-    if (sh->entry < n) n = sh->entry;
+    const u64 cw = sh->cw, ow = sh->ow;
+    const uint32_t n_cnt = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
+    const uint32_t n = sh->reach;
+    const uint32_t occ_item1 = (uint32_t)(ow >> 32) == A.stamp ? (uint32_t)ow : 0u;
     __syncthreads();
+    if (n_cnt < n_min) return;  // (drawn warp-wise in the pass before this one)
 
-    const uint32_t prow = t >> 4, px = t & 15u;
+    const bool owner = t < 256;  // owns pixel (t / 16, t % 16)
+    const uint32_t prow = (t >> 4) & 15u, px = t & 15u;
     uint8_t *dst = A.fb + (size_t)(trow * PM_TILE_H + prow) * A.pitch + (size_t)(tx * PM_TILE_W + px) * 4u;
     float4 *dst32 = nullptr;
     if (F32) dst32 = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(A.fb32) + (size_t)(trow * PM_TILE_H + prow) * A.pitch32) + (tx * PM_TILE_W + px);
     const float tile_x0 = (float)(tx * PM_TILE_W), tile_y0 = (float)((A.tile_y0 + trow) * PM_TILE_H);
-    const float fx = tile_x0 + (float)px, fy = tile_y0 + (float)prow;
     const int cell = pm_cov_swz((int)prow, (int)px);
     // metal:470 white; then the cover's Cmd_Solid (metal:136-142, :546-551: opaque, the pixel becomes its colour)
     float c0 = 1.0f, c1 = 1.0f, c2 = 1.0f;
     if (occ_item1) { const float4 b = __ldg(&A.item_paint[occ_item1 - 1u]); c0 = b.x; c1 = b.y; c2 = b.z; }
     int has_draw = 0;
+    PmCoverAcc cacc{sh->acc[warp], sh->cov[warp]};
 
     if (n <= PM_HEAVY_SORT_CAP) {
         // ---- 1. key and sort the records ----
@@ -151,7 +134,7 @@ __device__ void heavy_tile(const PmFrameArgs &A, HeavySmem *sh, uint32_t entry) 
         for (uint32_t p = t; p < P; p += PM_HEAVY_THREADS) {
             u64 key = ~0ull;
             if (p < n) {
-                const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[heavy_index(sh, tile, p)]);
+                const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[pm_heavy_index(sh->dir, tile, p)]);
                 if (ik.x >= occ_item1) {  // (below the topmost opaque cover: rewound away, metal:132-135)
                     const uint32_t kind = ik.y & 15u;
                     key = ((u64)ik.x << 32) | (kind >= PM_REC_CIRCLE ? 0u : 0x80000000u) | p;
@@ -198,40 +181,44 @@ __device__ void heavy_tile(const PmFrameArgs &A, HeavySmem *sh, uint32_t entry) 
             __syncthreads();
             const uint32_t n_items = sh->n_items;
 
-            // ---- 2 + 3. eight items at a time: coverage per warp, then the layers blended in order ----
-            PmCoverAcc cacc{sh->acc[warp], sh->cov[warp]};
+            // ---- 2 + 3. sixteen items at a time: coverage and alpha per warp, then the layers blended in order ----
             for (uint32_t k0 = 0; k0 < n_items; k0 += PM_HEAVY_WARPS) {
                 const uint32_t k = k0 + warp;
+                if (lane == 0) sh->meta[warp].valid = 0u;
+                __syncwarp();
                 if (k < n_items) {
                     const uint32_t s = sh->starts[k], e = sh->starts[k + 1];
                     const u64 first = sh->keys[s];
-                    HeavyMeta m;
-                    m.kind = 0; m.w0 = m.w1 = m.pad = 0; m.paint = make_float4(0.0f, 0.0f, 0.0f, 1.0f);  // Cmd_Circle paints black (metal:491)
                     if (!(first & 0x80000000ull)) {  // the item's closing record sorts first (an item without one is not drawn)
-                        const uint4 tr = *reinterpret_cast<const uint4 *>(&A.pool[heavy_index(sh, tile, (uint32_t)first & 0x7fffffffu)]);
-                        m.kind = tr.y & 15u; m.w0 = tr.z; m.w1 = tr.w;
-                        if (m.kind != PM_REC_CIRCLE) m.paint = __ldg(&A.item_paint[(uint32_t)(first >> 32)]);
-                        const bool stroke = m.kind == PM_REC_STROKE;
-                        if (stroke || m.kind == PM_REC_DRAWFILL) {
-                            const float reach = pm_u2f(m.w0) + 0.5f;
+                        const uint4 tr = *reinterpret_cast<const uint4 *>(&A.pool[pm_heavy_index(sh->dir, tile, (uint32_t)first & 0x7fffffffu)]);
+                        const uint32_t kind = tr.y & 15u;
+                        float4 paint = make_float4(0.0f, 0.0f, 0.0f, 1.0f);  // Cmd_Circle paints black (metal:491)
+                        if (kind != PM_REC_CIRCLE) paint = __ldg(&A.item_paint[(uint32_t)(first >> 32)]);
+                        const bool stroke = kind == PM_REC_STROKE;
+                        if (stroke || kind == PM_REC_DRAWFILL) {
+                            const float reach = pm_u2f(tr.z) + 0.5f;
                             for (uint32_t c = s + 1; c < e; c += 32) {
                                 const bool mine = c + lane < e;
                                 PmRecord rc;
                                 rc.key = 0; rc.p[0] = rc.p[1] = rc.p[2] = rc.p[3] = 0.0f; rc.edge_y = 0.0f;
-                                if (mine) rc = load_record(A.pool, heavy_index(sh, tile, (uint32_t)sh->keys[c + lane] & 0x7fffffffu));
+                                if (mine) rc = pm_load_record(A.pool, pm_heavy_index(sh->dir, tile, (uint32_t)sh->keys[c + lane] & 0x7fffffffu));
                                 pm_cover_records(cacc, mine, rc.key & 15u, rc.p[0], rc.p[1], rc.p[2], rc.p[3], rc.edge_y, stroke, reach, tile_x0, tile_y0, lane);
                             }
+                            __syncwarp();
                         }
+                        heavy_publish_layer(sh, warp, kind, tr.z, tr.w, paint, tile_x0, tile_y0, lane);
                     }
-                    if (lane == 0) sh->meta[warp] = m;
                 }
                 __syncthreads();
                 const uint32_t n_here = n_items - k0 < PM_HEAVY_WARPS ? n_items - k0 : PM_HEAVY_WARPS;
-                for (uint32_t s = 0; s < n_here; s++) {
-                    const HeavyMeta m = sh->meta[s];
-                    if (m.kind == 0) continue;
-                    const float al = heavy_alpha(sh, (int)s, m, cell, px, fx, fy) * m.paint.w;
-                    c0 = pm_mix_fma(c0, m.paint.x, al); c1 = pm_mix_fma(c1, m.paint.y, al); c2 = pm_mix_fma(c2, m.paint.z, al);
+                if (owner) {
+                    for (uint32_t s = 0; s < n_here; s++) {
+                        if (!sh->meta[s].valid) continue;
+                        const float4 paint = sh->meta[s].paint;
+                        const float al = __int_as_float(sh->acc[s][cell]);
+                        sh->acc[s][cell] = 0;
+                        c0 = pm_mix_fma(c0, paint.x, al); c1 = pm_mix_fma(c1, paint.y, al); c2 = pm_mix_fma(c2, paint.z, al);
+                    }
                 }
                 __syncthreads();
             }
@@ -241,68 +228,75 @@ __device__ void heavy_tile(const PmFrameArgs &A, HeavySmem *sh, uint32_t entry) 
         for (uint32_t p0 = 0; p0 < n; p0 += PM_HEAVY_THREADS) {
             const uint32_t p = p0 + t;
             if (p < n) {
-                const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[heavy_index(sh, tile, p)]);
+                const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[pm_heavy_index(sh->dir, tile, p)]);
                 if (ik.x >= occ_item1 && (ik.y & 15u) != PM_REC_SOLID) has_draw = 1;
             }
         }
         has_draw = __syncthreads_or(has_draw);
-        PmCoverAcc cacc{sh->acc[0], sh->cov[0]};  // all warps add to one set of arrays
+        PmCoverAcc call{sh->acc[0], sh->cov[0]};  // all warps add to one set of arrays
         uint32_t lo_item = occ_item1;
         while (has_draw) {
             uint32_t cand = 0xffffffffu;
             for (uint32_t p = t; p < n; p += PM_HEAVY_THREADS) {
-                const uint32_t it = A.pool[heavy_index(sh, tile, p)].item;
+                const uint32_t it = A.pool[pm_heavy_index(sh->dir, tile, p)].item;
                 if (it >= lo_item && it < cand) cand = it;
             }
             const uint32_t cur = block_min(cand, sh, lane, warp);
             if (cur == 0xffffffffu) break;
             lo_item = cur + 1u;
-            if (t == 0) sh->meta[0].kind = 0;
+            if (t == 0) sh->red[0] = 0u;  // (kind of the closing record)
             __syncthreads();
-            for (uint32_t p = t; p < n; p += PM_HEAVY_THREADS) {  // the closing record
-                const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[heavy_index(sh, tile, p)]);
-                if (a.x == cur && (a.y & 15u) >= PM_REC_CIRCLE) {
-                    HeavyMeta m;
-                    m.kind = a.y & 15u; m.w0 = a.z; m.w1 = a.w; m.pad = 0;
-                    m.paint = m.kind != PM_REC_CIRCLE ? __ldg(&A.item_paint[cur]) : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
-                    sh->meta[0] = m;
-                }
+            for (uint32_t p = t; p < n; p += PM_HEAVY_THREADS) {
+                const uint4 a = *reinterpret_cast<const uint4 *>(&A.pool[pm_heavy_index(sh->dir, tile, p)]);
+                if (a.x == cur && (a.y & 15u) >= PM_REC_CIRCLE) { sh->red[0] = a.y & 15u; sh->red[1] = a.z; sh->red[2] = a.w; }
             }
             __syncthreads();
-            const HeavyMeta m = sh->meta[0];
-            if (m.kind == 0) continue;  // (uniform: every thread reads the same words)
-            const bool stroke = m.kind == PM_REC_STROKE;
-            if (stroke || m.kind == PM_REC_DRAWFILL) {
-                const float reach = pm_u2f(m.w0) + 0.5f;
+            const uint32_t kind = sh->red[0], w0 = sh->red[1], w1 = sh->red[2];
+            __syncthreads();
+            if (kind == 0) continue;  // (uniform: every thread reads the same words)
+            const bool stroke = kind == PM_REC_STROKE;
+            if (stroke || kind == PM_REC_DRAWFILL) {
+                const float reach = pm_u2f(w0) + 0.5f;
                 for (uint32_t p0 = 0; p0 < n; p0 += PM_HEAVY_THREADS) {
                     const uint32_t p = p0 + t;
                     bool mine = false;
                     PmRecord rc;
                     rc.key = 0; rc.p[0] = rc.p[1] = rc.p[2] = rc.p[3] = 0.0f; rc.edge_y = 0.0f;
                     if (p < n) {
-                        const uint32_t idx = heavy_index(sh, tile, p);
+                        const uint32_t idx = pm_heavy_index(sh->dir, tile, p);
                         const uint2 ik = *reinterpret_cast<const uint2 *>(&A.pool[idx]);
-                        if (ik.x == cur && (ik.y & 15u) <= PM_REC_LINE) { mine = true; rc = load_record(A.pool, idx); }
+                        if (ik.x == cur && (ik.y & 15u) <= PM_REC_LINE) { mine = true; rc = pm_load_record(A.pool, idx); }
                     }
                     if (__any_sync(PM_FULL_MASK, mine))
-                        pm_cover_records(cacc, mine, rc.key & 15u, rc.p[0], rc.p[1], rc.p[2], rc.p[3], rc.edge_y, stroke, reach, tile_x0, tile_y0, lane);
+                        pm_cover_records(call, mine, rc.key & 15u, rc.p[0], rc.p[1], rc.p[2], rc.p[3], rc.edge_y, stroke, reach, tile_x0, tile_y0, lane);
                 }
             }
             __syncthreads();
-            const float al = heavy_alpha(sh, 0, m, cell, px, fx, fy) * m.paint.w;
-            c0 = pm_mix_fma(c0, m.paint.x, al); c1 = pm_mix_fma(c1, m.paint.y, al); c2 = pm_mix_fma(c2, m.paint.z, al);
+            if (warp == 0) {
+                const float4 paint = kind != PM_REC_CIRCLE ? __ldg(&A.item_paint[cur]) : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+                heavy_publish_layer(sh, 0, kind, w0, w1, paint, tile_x0, tile_y0, lane);
+            }
+            __syncthreads();
+            if (owner) {
+                const float4 paint = sh->meta[0].paint;
+                const float al = __int_as_float(sh->acc[0][cell]);
+                sh->acc[0][cell] = 0;
+                c0 = pm_mix_fma(c0, paint.x, al); c1 = pm_mix_fma(c1, paint.y, al); c2 = pm_mix_fma(c2, paint.z, al);
+            }
             __syncthreads();
         }
     }
 
-    if (!has_draw) {  // only Solid commands after the last rewind: the tile Bails and shows solidColor (metal:145-147, :34-44)
-        uint32_t c = 0xffffffffu;
-        if (occ_item1) c = __ldg(reinterpret_cast<const uint32_t *>(A.scene + A.items_ix + (size_t)(occ_item1 - 1u) * PM_ITEM_SIZE + PM_FILL_RGBA));
-        *reinterpret_cast<uint32_t *>(dst) = c;
-        if (F32) *dst32 = make_float4((float)(c & 0xff) / 255.0f, (float)((c >> 8) & 0xff) / 255.0f, (float)((c >> 16) & 0xff) / 255.0f, (float)(c >> 24) / 255.0f);
-    } else {
-        *reinterpret_cast<uint32_t *>(dst) = pm_encode_pixel<EXACT>(c0, c1, c2);
-        if (F32) *dst32 = make_float4(pm_linear_to_srgb<EXACT>(c0), pm_linear_to_srgb<EXACT>(c1), pm_linear_to_srgb<EXACT>(c2), 1.0f);
+    if (owner) {
+        if (!has_draw) {  // only Solid commands after the last rewind: the tile Bails and shows solidColor (metal:145-147, :34-44)
+            uint32_t c = 0xffffffffu;
+            if (occ_item1) c = __ldg(reinterpret_cast<const uint32_t *>(A.scene + A.items_ix + (size_t)(occ_item1 - 1u) * PM_ITEM_SIZE + PM_FILL_RGBA));
+            *reinterpret_cast<uint32_t *>(dst) = c;
+            if (F32) *dst32 = make_float4((float)(c & 0xff) / 255.0f, (float)((c >> 8) & 0xff) / 255.0f, (float)((c >> 16) & 0xff) / 255.0f, (float)(c >> 24) / 255.0f);
+        } else {
+            *reinterpret_cast<uint32_t *>(dst) = pm_encode_pixel<EXACT>(c0, c1, c2);
+            if (F32) *dst32 = make_float4(pm_linear_to_srgb<EXACT>(c0), pm_linear_to_srgb<EXACT>(c1), pm_linear_to_srgb<EXACT>(c2), 1.0f);
+        }
     }
     __syncthreads();
 }
@@ -311,6 +305,7 @@ template <bool F32, bool EXACT>
 __global__ void __launch_bounds__(PM_HEAVY_THREADS) k_heavy(const PmFrameArgs A) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     HeavySmem *sh = reinterpret_cast<HeavySmem *>(s_raw);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (uint32_t i = threadIdx.x; i < PM_HEAVY_WARPS * 256; i += PM_HEAVY_THREADS) { (&sh->acc[0][0])[i] = 0; (&sh->cov[0][0])[i] = 0; }
     // Programmatic dependent launch: wait for binning (k_row) to complete, THEN let k_fine launch beside this grid;
     // k_fine itself does not wait at its start (see pm_fine.cu).
@@ -319,13 +314,29 @@ __global__ void __launch_bounds__(PM_HEAVY_THREADS) k_heavy(const PmFrameArgs A)
     const uint32_t n_heavy = A.counters->n_heavy;
     const uint32_t *list = A.complex_list + (size_t)A.n_rows * A.n_tx;
     __syncthreads();
+    uint32_t n_min_cta = 0;
+    if (pm_heavy_warp_mode(n_heavy, gridDim.x)) {
+        // many heavy tiles: a warp each (up to PM_HEAVY_WARP_CAP records); what is left is drawn CTA-wise below
+        HeavyWarpState *ws = &sh->ws[warp];
+        for (;;) {
+            uint32_t h = 0;
+            if (lane == 0) h = atomicAdd(&A.queue->heavy_warp_next, 1u);
+            h = __shfl_sync(PM_FULL_MASK, h, 0);
+            if (h >= n_heavy) break;
+            pm_heavy_tile_warp<F32, EXACT>(A, sh->acc[warp], sh->cov[warp], ws->rgb, ws->dir, list[h], lane);
+            __syncwarp();
+        }
+        n_min_cta = PM_HEAVY_WARP_CAP + 1u;
+        __syncthreads();
+        // (the sort arrays held the warps' colour planes: nothing of them is live any more)
+    }
     for (;;) {
         if (threadIdx.x == 0) sh->tile_next = atomicAdd(&A.queue->heavy_next, 1u);
         __syncthreads();
         const uint32_t h = sh->tile_next;
         __syncthreads();
         if (h >= n_heavy) break;
-        heavy_tile<F32, EXACT>(A, sh, list[h]);
+        heavy_tile_cta<F32, EXACT>(A, sh, list[h], n_min_cta);
     }
 }
 
@@ -357,7 +368,8 @@ static cudaError_t heavy_launch(const PmFrameArgs &a, int grid, bool overlap, cu
 }
 
 cudaError_t pm_launch_heavy(const PmFrameArgs &a, int sm_count, bool overlap, cudaStream_t s) {
-    // persistent: the number of heavy tiles is only known on the device; CTAs without work leave at once
+    // Persistent: the number of heavy tiles is only known on the device; CTAs without work leave at once.  Two CTAs of
+    // eight warps per SM: half of the SM's registers stay free for k_fine's CTAs, which run beside this kernel.
     const int grid = sm_count * 2;
     const bool exact = (a.flags & PM_FLAG_EXACT_SRGB) != 0;
     if (a.fb32) return exact ? heavy_launch<true, true>(a, grid, overlap, s) : heavy_launch<true, false>(a, grid, overlap, s);

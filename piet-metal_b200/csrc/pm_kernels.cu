@@ -461,6 +461,7 @@ __global__ void __launch_bounds__(256, PM_SEG_CTAS) k_seg(const PmFrameArgs A) {
         A.queue->batch_next = 0;
         A.queue->tile_next = 0;
         A.queue->heavy_next = 0;
+        A.queue->heavy_warp_next = 0;
     }
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= A.n_pieces) return;
@@ -595,7 +596,8 @@ static cudaError_t launch_overlapped(K kernel, dim3 grid, dim3 block, bool overl
     return cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
-cudaError_t pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, cudaEvent_t mid2, bool overlap, cudaStream_t s, uint32_t *n_launched) {
+cudaError_t pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid, cudaEvent_t mid2, bool overlap, cudaStream_t s,
+                            uint32_t *n_launched) {
     cudaError_t e;
     uint32_t launched = 0;
     uint32_t grid_seg = (a.n_pieces + 255u) / 256u;

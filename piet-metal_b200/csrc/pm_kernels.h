@@ -36,6 +36,8 @@ struct PmFineQueue {
     uint32_t pad1[31];
     uint32_t heavy_next;    // k_heavy: position in the list of heavy tiles, one CTA each
     uint32_t pad2[31];
+    uint32_t heavy_warp_next; // k_heavy, warp mode: position in the same list, one warp each
+    uint32_t pad3[31];
 };
 // Written by the device into mapped host memory at the end of every frame.
 struct PmFrameReport {

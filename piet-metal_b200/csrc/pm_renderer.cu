@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 #include <string>
 #include <vector>
@@ -66,7 +67,9 @@ struct pm_renderer {
     unsigned long long *debug = nullptr;
     size_t bd_cap = 0, bd_words = 0;
     bool have_scene = false, plan_dirty = true;
-    bool frame_events = true;   // per-frame CUDA events (pm_frame_stats); off: the frame's kernels overlap their launches
+    int frame_events = 1;       // 0: no events, launches overlap across frames; 1: events around every kernel group (serial);
+                                // 2: events around the frame only, its kernels overlap (pm_renderer_set_frame_events)
+    double plan_ms = 0.0;       // host wall time of the last plan (validate is not included), milliseconds
     uint32_t *dev_err = nullptr;
     PmPlanResult *dev_plan = nullptr;
 
@@ -164,6 +167,7 @@ int alloc_surface(pm_renderer *r) {
     return PM_OK;
 }
 
+int run_plan_timed(pm_renderer *r);
 int run_plan(pm_renderer *r) {
     PmPlanResult res;
     // the k_row unit table is filled in the same pass that sizes it; a second pass only if it was too small
@@ -252,11 +256,21 @@ int run_plan(pm_renderer *r) {
     return PM_OK;
 }
 
+int run_plan_timed(pm_renderer *r) {
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    const int st = run_plan(r);
+    if (st == PM_OK) cudaStreamSynchronize(r->stream);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    r->plan_ms = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+    return st;
+}
+
 // Enqueue one frame.  debug_f32 also writes the fp32 parity buffer.
 int enqueue_frame(pm_renderer *r, bool debug_f32) {
     if (!r->have_scene || !r->have_surface) return PM_ERR_STATE;
     if (!r->pool || !r->fb) { g_last_error = "surface allocation failed earlier"; return PM_ERR_NOMEM; }
-    if (r->plan_dirty) { int st = run_plan(r); if (st != PM_OK) return st; }
+    if (r->plan_dirty) { int st = run_plan_timed(r); if (st != PM_OK) return st; }
     const size_t n_tiles = strip_tiles(r);
     r->stamp++;
     if (r->stamp == 0) {  // 2^32 frames: restart the stamps from a clean slate
@@ -281,9 +295,10 @@ int enqueue_frame(pm_renderer *r, bool debug_f32) {
     a.item_paint = r->item_paint;
     a.debug = r->debug;
     const uint32_t slot = r->frame % EVENT_RING;
-    const bool events = r->frame_events || debug_f32;
+    const int mode = debug_f32 ? 1 : r->frame_events;
+    const bool events = mode != 0, split = mode == 1;
     if (events) PM_CUDA(cudaEventRecord(r->ev_start[slot], r->stream));
-    PM_CUDA(pm_launch_frame(a, r->sm_count, events ? r->ev_mid[slot] : nullptr, events ? r->ev_mid2[slot] : nullptr, !events, r->stream, &r->n_launches));
+    PM_CUDA(pm_launch_frame(a, r->sm_count, split ? r->ev_mid[slot] : nullptr, split ? r->ev_mid2[slot] : nullptr, !split, r->stream, &r->n_launches));
     if (events) PM_CUDA(cudaEventRecord(r->ev_end[slot], r->stream));
     PM_CUDA(cudaGetLastError());
     r->frame++;
@@ -482,7 +497,7 @@ int pm_renderer_set_frame_events(pm_renderer *r, int enabled) {
     int st = use_device(r);
     if (st != PM_OK) return st;
     PM_CUDA(cudaStreamSynchronize(r->stream));
-    r->frame_events = enabled != 0;
+    r->frame_events = enabled < 0 || enabled > 2 ? 1 : enabled;
     r->frames_unsynced = 0;
     return PM_OK;
 }
@@ -513,19 +528,23 @@ int pm_renderer_sync(pm_renderer *r, pm_frame_stats *stats) {
     if (stats) {
         memset(stats, 0, sizeof *stats);
         uint32_t n = r->frame_events ? std::min<uint32_t>(r->frames_unsynced, EVENT_RING) : 0;
+        const bool split = r->frame_events == 1;
         double sum_total = 0, sum_bin = 0, sum_fine = 0, sum_heavy = 0;
         for (uint32_t k = 0; k < n; k++) {
             uint32_t slot = (r->frame - 1 - k) % EVENT_RING;
             float t = 0, b = 0, f = 0, h = 0;
             PM_CUDA(cudaEventElapsedTime(&t, r->ev_start[slot], r->ev_end[slot]));
-            PM_CUDA(cudaEventElapsedTime(&b, r->ev_start[slot], r->ev_mid[slot]));
-            PM_CUDA(cudaEventElapsedTime(&h, r->ev_mid[slot], r->ev_mid2[slot]));
-            PM_CUDA(cudaEventElapsedTime(&f, r->ev_mid2[slot], r->ev_end[slot]));
+            if (split) {
+                PM_CUDA(cudaEventElapsedTime(&b, r->ev_start[slot], r->ev_mid[slot]));
+                PM_CUDA(cudaEventElapsedTime(&h, r->ev_mid[slot], r->ev_mid2[slot]));
+                PM_CUDA(cudaEventElapsedTime(&f, r->ev_mid2[slot], r->ev_end[slot]));
+            }
             if (k == 0) { stats->ms_total = t; stats->ms_bin = b; stats->ms_fine = f; stats->ms_heavy = h; }
             sum_total += t; sum_bin += b; sum_fine += f; sum_heavy += h;
         }
         stats->ms_heavy_sum = (float)sum_heavy;
         stats->n_heavy_tiles = r->report->n_heavy;
+        stats->ms_plan = (float)r->plan_ms;
         stats->frames = n;
         stats->ms_total_sum = (float)sum_total;
         stats->ms_bin_sum = (float)sum_bin;

@@ -205,34 +205,75 @@ def test_full_size_properties_8192(pm, renderer):
     assert crc == crc_full
 
 
-def test_full_size_band_matches_oracle_8192(pm, oracle, renderer):
-    """Two tile rows through the middle of the 8192^2 tiger, GPU strip vs oracle strip."""
+def bands(n_rows, n_bands, rows_per_band):
+    """n_bands groups of rows_per_band tile rows spread evenly over the frame (first and last row included)."""
+    starts = np.linspace(0, n_rows - rows_per_band, n_bands).astype(int)
+    return [(int(y), int(y) + rows_per_band) for y in starts]
+
+
+def test_full_frame_matches_oracle_8192(pm, oracle, renderer):
+    """The headline workload, WHOLE frame: the tiger at 8192^2, every one of its 262,144 tiles -- per-tile item lists
+    and solid colours bit-exact, fp32 RGBA within 1e-5, RGBA8 within 1 LSB -- in eight strips of 64 tile rows to
+    bound the memory of the debug read-backs."""
     w = h = 8192
     scene = pm.build_scene(pm.SCENE_TIGER, w, h)
-    y0, y1 = 255, 257
-    gpu = gpu_render(renderer, scene, w, h, strip=(y0, y1))
-    ref = oracle.render(scene, w, h, tile_y0=y0, tile_y1=y1, f32=True, items=True)
-    check(gpu, ref, "tiger 8192 rows %d..%d" % (y0, y1))
+    for y0 in range(0, 512, 64):
+        gpu = gpu_render(renderer, scene, w, h, strip=(y0, y0 + 64))
+        ref = oracle.render(scene, w, h, tile_y0=y0, tile_y1=y0 + 64, f32=True, items=True)
+        check(gpu, ref, "tiger 8192 rows %d..%d" % (y0, y0 + 64))
 
 
-def test_config4_band_matches_oracle(pm, oracle, renderer):
-    """BASELINE config 4 (10k random filled Bezier paths, 8192^2): two tile rows against the oracle."""
+def test_tiger_16384_bands_match_oracle(pm, oracle, renderer):
+    """The size the strong-scaling target is quoted on: eight tile rows of the 16384^2 tiger (four bands of two,
+    top edge, two through the drawing, bottom edge) against the oracle."""
+    w = h = 16384
+    scene = pm.build_scene(pm.SCENE_TIGER, w, h)
+    for y0, y1 in bands(1024, 4, 2):
+        gpu = gpu_render(renderer, scene, w, h, strip=(y0, y1))
+        ref = oracle.render(scene, w, h, tile_y0=y0, tile_y1=y1, f32=True, items=True)
+        check(gpu, ref, "tiger 16384 rows %d..%d" % (y0, y1))
+
+
+def test_config4_bands_match_oracle(pm, oracle, renderer):
+    """BASELINE config 4 (10k random filled Bezier paths, 8192^2): 32 tile rows in eight bands spread over the frame."""
     w = h = 8192
     scene = pm.build_scene(pm.SCENE_RAND_BEZIER, w, h)
-    y0, y1 = 300, 302
-    gpu = gpu_render(renderer, scene, w, h, strip=(y0, y1))
-    ref = oracle.render(scene, w, h, tile_y0=y0, tile_y1=y1, f32=True, items=True)
-    check(gpu, ref, "rand_bezier 8192 rows %d..%d" % (y0, y1))
+    for y0, y1 in bands(512, 8, 4):
+        gpu = gpu_render(renderer, scene, w, h, strip=(y0, y1))
+        ref = oracle.render(scene, w, h, tile_y0=y0, tile_y1=y1, f32=True, items=True)
+        check(gpu, ref, "rand_bezier 8192 rows %d..%d" % (y0, y1))
 
 
-def test_config5_band_matches_oracle(pm, oracle, renderer):
-    """BASELINE config 5 (100k glyph-like outlines, 4096^2): four tile rows against the oracle."""
+def test_config5_bands_match_oracle(pm, oracle, renderer):
+    """BASELINE config 5 (100k glyph-like outlines, 4096^2): 32 tile rows in eight bands spread over the frame."""
     w = h = 4096
     scene = pm.build_scene(pm.SCENE_GLYPHS, w, h)
-    y0, y1 = 100, 104
-    gpu = gpu_render(renderer, scene, w, h, strip=(y0, y1))
-    ref = oracle.render(scene, w, h, tile_y0=y0, tile_y1=y1, f32=True, items=True)
-    check(gpu, ref, "glyphs 4096 rows %d..%d" % (y0, y1))
+    for y0, y1 in bands(256, 8, 4):
+        gpu = gpu_render(renderer, scene, w, h, strip=(y0, y1))
+        ref = oracle.render(scene, w, h, tile_y0=y0, tile_y1=y1, f32=True, items=True)
+        check(gpu, ref, "glyphs 4096 rows %d..%d" % (y0, y1))
+
+
+def test_dense_tiles_256(pm, oracle, renderer):
+    """The whole tiger squeezed into 256 x 256 pixels (the smoke frame): thousands of records per tile, every tile
+    drawn by k_heavy -- sorted path and overflow block chains."""
+    w = h = 256
+    scene = pm.build_scene(pm.SCENE_TIGER, w, h)
+    gpu = gpu_render(renderer, scene, w, h)
+    ref = oracle.render(scene, w, h, f32=True, items=True)
+    check(gpu, ref, "tiger 256")
+    assert gpu["stats"].n_heavy_tiles > 100
+
+
+def test_extreme_density_64(pm, oracle, renderer):
+    """The tiger in 64 x 64 pixels: more than 4096 records in a tile, i.e. beyond k_heavy's shared-memory sort (one
+    pass over all of the tile's records per item instead)."""
+    w = h = 64
+    scene = pm.build_scene(pm.SCENE_TIGER, w, h)
+    gpu = gpu_render(renderer, scene, w, h)
+    ref = oracle.render(scene, w, h, f32=True, items=True)
+    check(gpu, ref, "tiger 64")
+    assert gpu["stats"].n_overflow_records > 16 * 4096
 
 
 def test_empty_and_tiny_surfaces(pm, oracle, renderer):
