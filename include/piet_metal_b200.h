@@ -236,6 +236,34 @@ typedef struct pm_tile_item {
 int pm_renderer_read_tile_items(pm_renderer *r, uint32_t *offsets, pm_tile_item *items,
                                 size_t cap_items, size_t *n_items_out, uint32_t *solid_colors);
 
+/* ------------------------------------------------------------------------------------------- */
+/* Multi-GPU group (one host thread, the GPUs of one box)                                       */
+/* ------------------------------------------------------------------------------------------- */
+/* The reference renders on one device (TestApp/ViewController.m:16, TestApp/PietRenderer.m:48) and its
+ * -[PietRenderer initScene] (PietRenderer.m:203-205) fills that device's scene buffer.  A group is the same
+ * four-call life cycle over N GPUs: the frame's tile rows are cut into N contiguous, cost-balanced row-strips;
+ * pm_group_set_scene uploads the scene once and broadcasts it with ONE ncclBroadcast over NVLink (communicators from
+ * ncclCommInitAll: no launcher, no rendezvous; libnccl.so.2 is loaded with dlopen on first use); pm_group_render
+ * enqueues the frame on every GPU with no collective and no host synchronisation.  devices == NULL means 0..n-1. */
+typedef struct pm_group pm_group;
+int pm_group_create(pm_group **out, const int32_t *devices, uint32_t n_devices, uint32_t flags);
+void pm_group_destroy(pm_group *g);
+uint32_t pm_group_size(const pm_group *g);
+int pm_group_member(pm_group *g, uint32_t index, pm_renderer **out);   /* the renderer that owns strip `index` */
+int pm_group_resize(pm_group *g, uint32_t width, uint32_t height);
+int pm_group_set_scene(pm_group *g, const uint8_t *scene, size_t len); /* host scene -> device 0 -> ncclBroadcast -> validate + plan */
+int pm_group_strip_bounds(const pm_group *g, uint32_t *bounds, size_t cap); /* n + 1 tile-row bounds */
+int pm_group_set_frame_events(pm_group *g, int mode);                  /* pm_renderer_set_frame_events on every member */
+int pm_group_render(pm_group *g);
+/* Wait for every member; stats (optional, n_stats entries) per member; *ms_frame_max = the slowest member's last frame. */
+int pm_group_sync(pm_group *g, pm_frame_stats *stats, size_t n_stats, float *ms_frame_max);
+/* Off the hot path: the whole frame to host memory (row `stride` >= 4 * width), or gathered into one buffer on member
+ * `root`'s device (strips are of unequal height: ncclSend / ncclRecv, not an all-gather); *pitch_bytes = 64 * ceil(width / 16). */
+int pm_group_read_rgba8(pm_group *g, uint8_t *dst, size_t stride);
+int pm_group_gather_device(pm_group *g, uint32_t root, void **dev_ptr, size_t *pitch_bytes);
+/* NCCL_VERSION_CODE of the library that was loaded, 0 if none could be. */
+int pm_group_nccl_version(void);
+
 /* Pinned host memory for fast host<->device copies of scenes and frames. */
 int pm_host_alloc(void **out, size_t bytes);
 void pm_host_free(void *p);

@@ -72,6 +72,9 @@ EXPORTS = [
     "pm_renderer_set_scene", "pm_renderer_set_scene_device", "pm_renderer_render", "pm_renderer_set_frame_events", "pm_renderer_sync",
     "pm_renderer_read_rgba8", "pm_renderer_render_host", "pm_renderer_framebuffer", "pm_renderer_stream",
     "pm_renderer_read_rgba32f", "pm_renderer_read_tile_items", "pm_host_alloc", "pm_host_free",
+    "pm_group_create", "pm_group_destroy", "pm_group_size", "pm_group_member", "pm_group_resize", "pm_group_set_scene",
+    "pm_group_strip_bounds", "pm_group_set_frame_events", "pm_group_render", "pm_group_sync", "pm_group_read_rgba8",
+    "pm_group_gather_device", "pm_group_nccl_version",
 ]
 
 _LIB = None
@@ -127,6 +130,19 @@ def _lib():
         "pm_renderer_read_tile_items": (cint, [vp, vp, vp, sz, ctypes.POINTER(sz), vp]),
         "pm_host_alloc": (cint, [ctypes.POINTER(vp), sz]),
         "pm_host_free": (None, [vp]),
+        "pm_group_create": (cint, [ctypes.POINTER(vp), vp, u32, u32]),
+        "pm_group_destroy": (None, [vp]),
+        "pm_group_size": (u32, [vp]),
+        "pm_group_member": (cint, [vp, u32, ctypes.POINTER(vp)]),
+        "pm_group_resize": (cint, [vp, u32, u32]),
+        "pm_group_set_scene": (cint, [vp, vp, sz]),
+        "pm_group_strip_bounds": (cint, [vp, vp, sz]),
+        "pm_group_set_frame_events": (cint, [vp, cint]),
+        "pm_group_render": (cint, [vp]),
+        "pm_group_sync": (cint, [vp, vp, sz, ctypes.POINTER(flt)]),
+        "pm_group_read_rgba8": (cint, [vp, vp, sz]),
+        "pm_group_gather_device": (cint, [vp, u32, ctypes.POINTER(vp), ctypes.POINTER(sz)]),
+        "pm_group_nccl_version": (cint, []),
     }
     for name in EXPORTS:
         fn = getattr(lib, name)  # AttributeError if the library does not export what the header declares
@@ -391,3 +407,63 @@ def write_image(path, rgba8):
 def strip_bounds(n_tile_rows, world_size):
     """Contiguous row-strip shard of the frame's tile rows: rank g renders [b[g], b[g+1])."""
     return [(n_tile_rows * g) // world_size for g in range(world_size + 1)]
+
+
+class PietRendererGroup:
+    """N GPUs of one box behind one handle (pm_group_*): the scene is uploaded once and broadcast with NCCL inside
+    the library; every GPU renders one contiguous, cost-balanced strip of tile rows."""
+
+    def __init__(self, devices, flags=0):
+        devs = np.ascontiguousarray(list(devices), np.int32)
+        self._h = ctypes.c_void_p()
+        _check(_lib().pm_group_create(ctypes.byref(self._h), _ptr(devs), devs.size, flags), "pm_group_create")
+        self.n = devs.size
+        self.width = self.height = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib().pm_group_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def resize(self, width, height):
+        _check(_lib().pm_group_resize(self._h, width, height), "pm_group_resize")
+        self.width, self.height = width, height
+
+    def set_scene(self, scene):
+        scene = np.ascontiguousarray(scene, np.uint8)
+        _check(_lib().pm_group_set_scene(self._h, _ptr(scene), scene.size), "pm_group_set_scene")
+
+    def strip_bounds(self):
+        b = np.zeros(self.n + 1, np.uint32)
+        _check(_lib().pm_group_strip_bounds(self._h, _ptr(b), b.size), "pm_group_strip_bounds")
+        return [int(x) for x in b]
+
+    def set_frame_events(self, mode):
+        _check(_lib().pm_group_set_frame_events(self._h, int(mode)), "pm_group_set_frame_events")
+
+    def render(self):
+        _check(_lib().pm_group_render(self._h), "pm_group_render")
+
+    def sync(self):
+        """(list of FrameStats per member, slowest member's last frame in ms)"""
+        stats = (FrameStats * self.n)()
+        worst = ctypes.c_float(0)
+        _check(_lib().pm_group_sync(self._h, ctypes.cast(stats, ctypes.c_void_p), self.n, ctypes.byref(worst)), "pm_group_sync")
+        return list(stats), worst.value
+
+    def read_rgba8(self):
+        out = np.empty((self.height, self.width, 4), np.uint8)
+        _check(_lib().pm_group_read_rgba8(self._h, _ptr(out), out.strides[0]), "pm_group_read_rgba8")
+        return out
+
+    def gather_device(self, root=0):
+        """(device pointer, pitch in bytes) of the whole frame gathered on member `root`'s GPU."""
+        ptr, pitch = ctypes.c_void_p(), ctypes.c_size_t(0)
+        _check(_lib().pm_group_gather_device(self._h, root, ctypes.byref(ptr), ctypes.byref(pitch)), "pm_group_gather_device")
+        return ptr.value, pitch.value
+
+
+def nccl_version():
+    return _lib().pm_group_nccl_version()

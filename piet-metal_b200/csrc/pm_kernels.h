@@ -18,7 +18,9 @@ struct PmBinCounters {
     uint32_t n_medium;    // tiles with at least PM_MEDIUM_MIN records: k_fine starts with these
     uint32_t pad3[31];
 };
+#ifndef PM_MEDIUM_MIN
 #define PM_MEDIUM_MIN 6u
+#endif
 // Records up to which a tile is k_fine's (one warp per tile); tiles with more go to k_heavy (one CTA per tile).
 // 16 = the inline slots.  k_fine can take up to 32 (one record per lane; records 16..31 are the start of the
 // tile's first overflow block), measured on the 8192^2 tiger: k_fine +6 us, the frame +7 us -- a 30-record tile

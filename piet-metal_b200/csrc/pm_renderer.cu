@@ -43,6 +43,8 @@ const int EVENT_RING = 512;
 
 }  // namespace
 
+void pm_set_last_error(const char *text) { g_last_error = text ? text : ""; }  // (pm_group.cu reports through the same channel)
+
 struct pm_renderer {
     int device = 0;
     int sm_count = 0;
