@@ -77,6 +77,16 @@ int pm_encoder_stroke_line(pm_encoder *e, double x0, double y0, double x1, doubl
 int pm_encoder_fill(pm_encoder *e, const double *xy, uint32_t n_points, uint32_t rgba);   /* :195 */
 int pm_encoder_polyline(pm_encoder *e, const double *xy, uint32_t n_points, uint32_t rgba,
                         float width);                                    /* polyline       :209 */
+/* Extensions for what the reference leaves open ("need to deal with subpaths", src/lib.rs:194; flags "will be
+ * used for winding rule", TestApp/SceneEncoder.h:44).  pm_encoder_fill_rule is pm_encoder_fill with the item's flags word
+ * (PM_FILL_NONZERO / PM_FILL_EVEN_ODD; read by a renderer created with PM_FLAG_FILL_RULES).  pm_encoder_fill_subpaths
+ * writes ONE Fill item for a path of several closed subpaths -- holes are cut out instead of painted over: the
+ * subpaths are joined into a single closed point list by zero-area bridges (each subpath is closed explicitly and
+ * followed by a segment back to the first point of the path; every bridge is walked once in each direction, so its
+ * winding and area cancel), which the reference's own kernels can render as it is.  counts[i] = points of subpath i. */
+int pm_encoder_fill_rule(pm_encoder *e, const double *xy, uint32_t n_points, uint32_t rgba, uint32_t flags);
+int pm_encoder_fill_subpaths(pm_encoder *e, const double *xy, const uint32_t *counts, uint32_t n_subpaths,
+                             uint32_t rgba, uint32_t flags);
 /* Bytes used so far (free_space, lib.rs:112-116). */
 size_t pm_encoder_bytes(const pm_encoder *e);
 void pm_encoder_free(pm_encoder *e);
@@ -110,8 +120,13 @@ typedef struct pm_scene_desc {
     double scale;      /* TIGER: 0 = width/200; CARDIOID: 0 = 1 (coordinates as in the reference) */
     double rect[4];    /* RECT1 */
     uint32_t rgba;     /* RECT1 colour, 0xRRGGBBAA (0 = 0x3366ccff) */
-    uint32_t reserved;
+    uint32_t options;  /* PM_SCENE_OPT_* */
 } pm_scene_desc;
+enum {
+    PM_SCENE_OPT_COMPOUND_FILLS = 1u << 0, /* TIGER: one Fill item per <path> (pm_encoder_fill_subpaths, nonzero rule)
+                                              instead of one per subpath (src/lib.rs:342-347): holes are cut out */
+    PM_SCENE_OPT_EVEN_ODD = 1u << 1        /* ... with PM_FILL_EVEN_ODD in the items' flags */
+};
 
 /* Writes the scene into buf; returns bytes written, or a negative pm_status.  With buf == NULL it
  * returns the size needed. */
@@ -149,8 +164,13 @@ typedef struct pm_renderer pm_renderer;
 enum {
     PM_FLAG_FIX_POLY_PRECULL = 1u << 0, /* use the per-row polyline pre-cull instead of the
                                            reference's lane-row one */
-    PM_FLAG_EXACT_SRGB = 1u << 1        /* powf() for the linear->sRGB encode instead of ex2/lg2 */
+    PM_FLAG_EXACT_SRGB = 1u << 1,       /* powf() for the linear->sRGB encode instead of ex2/lg2 */
+    PM_FLAG_FILL_RULES = 1u << 2        /* honour PietFill.flags (the word the reference reserves "for winding rule",
+                                           TestApp/SceneEncoder.h:44, and never reads): bit 0 = PM_FILL_EVEN_ODD fills the
+                                           item by the even-odd rule, with the formula the reference names but leaves
+                                           out (TestApp/PietRender.metal:538-540).  Off: the word is ignored, as upstream */
 };
+enum { PM_FILL_NONZERO = 0u, PM_FILL_EVEN_ODD = 1u };  /* PietFill.flags */
 
 typedef struct pm_config {
     int32_t device;          /* CUDA device ordinal */

@@ -45,6 +45,12 @@ enum { CMD_END = 1, CMD_CIRCLE = 2, CMD_LINE = 3, CMD_FILL = 4, CMD_STROKE = 5, 
        CMD_FILLEDGE = 6, CMD_DRAWFILL = 7, CMD_SOLID = 8, CMD_BAIL = 9 };
 
 #define PMO_FLAG_FIX_POLY_PRECULL 1u
+/* Extension (off by default: the reference ignores the word): honour bit 0 of PietFill.flags as "even-odd fill
+ * rule" -- the rule the reference names but leaves unimplemented (PietRender.metal:538-540 gives the formula;
+ * SceneEncoder.h:44 reserves the word "for winding rule").  A DrawFill command of such an item carries 1 in the
+ * otherwise unused body word at byte 12. */
+#define PMO_FLAG_FILL_RULES 4u
+#define FILL_EVEN_ODD 1u
 
 typedef struct { uint32_t tag; uint32_t body[5]; } pmo_cmd; /* GenTypes.h:430-433, 24 bytes */
 typedef struct { uint32_t item; int32_t backdrop; uint32_t effect; } pmo_tile_item; /* effect 0 draw, 1 solid */
@@ -118,11 +124,12 @@ static void encode_fill_edge(encoder *e, float sign, float y) { /* :111-118 */
     c->body[0] = (uint32_t)(int32_t)sign; /* cmd.sign is an int (GenTypes.h:392-396) */
     c->body[1] = f_bits(y);
 }
-static void encode_draw_fill(encoder *e, uint32_t rgba, int backdrop) { /* :119-127 */
+static void encode_draw_fill(encoder *e, uint32_t rgba, int backdrop, uint32_t rule) { /* :119-127; rule: extension, 0 in the reference */
     pmo_cmd *c = enc_push(e);
     c->tag = CMD_DRAWFILL;
     c->body[0] = (uint32_t)backdrop;
     c->body[1] = rgba;
+    c->body[2] = rule;
     e->solid_color = 0;
 }
 static void encode_solid(encoder *e, uint32_t rgba) { /* :128-143 */
@@ -214,6 +221,7 @@ static uint32_t pmo_tile(const uint8_t *scene, uint32_t gx, uint32_t gy, uint32_
                 uint32_t rgba = rd_u32(item + 8);
                 uint32_t n_points = rd_u32(item + 12);
                 const uint8_t *pts = scene + rd_u32(item + 16);
+                const uint32_t rule = (flags & PMO_FLAG_FILL_RULES) ? (rd_u32(item + 4) & FILL_EVEN_ODD) : 0u;
                 float backdrop = 0;
                 int any_fill = 0;
                 for (uint32_t j = 0; j < n_points; j += 16) {
@@ -294,9 +302,9 @@ static uint32_t pmo_tile(const uint8_t *scene, uint32_t gx, uint32_t gy, uint32_
                     }
                 }
                 if (any_fill) { /* :359-363; float -> int conversion at the call (:119) */
-                    encode_draw_fill(enc, rgba, (int)backdrop);
+                    encode_draw_fill(enc, rgba, (int)backdrop, rule);
                     enc_log_item(enc, ix, (int)backdrop, 0);
-                } else if (backdrop != 0.0f) {
+                } else if (rule == FILL_EVEN_ODD ? ((int)backdrop & 1) != 0 : backdrop != 0.0f) { /* even-odd: covered iff the winding number is odd */
                     encode_solid(enc, rgba);
                     enc_log_item(enc, ix, 0, 1);
                 }
@@ -463,7 +471,8 @@ static int pmo_pixel(const pmo_cmd *src, uint32_t x, uint32_t y, float out[4]) {
         }
         case CMD_DRAWFILL: { /* :535-545 */
             float alpha = signed_area + (float)(int32_t)src->body[0];
-            alpha = fminf(fabsf(alpha), 1.0f); /* nonzero winding rule */
+            if (src->body[2] == FILL_EVEN_ODD) alpha = fabsf(alpha - 2.0f * roundf(0.5f * alpha)); /* the formula of :539 */
+            else alpha = fminf(fabsf(alpha), 1.0f); /* nonzero winding rule */
             float fg[4]; unpack_srgb(src->body[1], fg);
             for (int k = 0; k < 3; k++) rgb[k] = mixf(rgb[k], fg[k], fg[3] * alpha);
             signed_area = 0.0f;

@@ -26,6 +26,9 @@ PM_ERR_STATE = -6
 SCENE_RECT1, SCENE_PATH_TEST, SCENE_CARDIOID, SCENE_TIGER, SCENE_RAND_BEZIER, SCENE_GLYPHS = range(6)
 FLAG_FIX_POLY_PRECULL = 1
 FLAG_EXACT_SRGB = 2
+FLAG_FILL_RULES = 4
+FILL_NONZERO, FILL_EVEN_ODD = 0, 1
+SCENE_OPT_COMPOUND_FILLS, SCENE_OPT_EVEN_ODD = 1, 2
 
 
 class PietMetalError(RuntimeError):
@@ -40,7 +43,7 @@ class PietMetalError(RuntimeError):
 class SceneDesc(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_uint32), ("width", ctypes.c_uint32), ("height", ctypes.c_uint32),
                 ("count", ctypes.c_uint32), ("seed", ctypes.c_uint64), ("scale", ctypes.c_double),
-                ("rect", ctypes.c_double * 4), ("rgba", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("rect", ctypes.c_double * 4), ("rgba", ctypes.c_uint32), ("options", ctypes.c_uint32)]
 
 
 class Config(ctypes.Structure):
@@ -66,6 +69,7 @@ EXPORTS = [
     "pm_strerror", "pm_last_error", "pm_version", "init_test_scene",
     "pm_encoder_new", "pm_encoder_begin_group", "pm_encoder_end_group", "pm_encoder_circle",
     "pm_encoder_stroke_line", "pm_encoder_fill", "pm_encoder_polyline", "pm_encoder_bytes", "pm_encoder_free",
+    "pm_encoder_fill_rule", "pm_encoder_fill_subpaths",
     "pm_flatten_svg_path", "pm_parse_color", "pm_scene_build", "pm_scene_from_pathlist", "pm_scene_validate",
     "pm_scene_row_costs", "pm_balance_strips", "pm_write_ppm", "pm_write_png",
     "pm_renderer_create", "pm_renderer_destroy", "pm_renderer_resize", "pm_renderer_set_strip",
@@ -102,6 +106,8 @@ def _lib():
         "pm_encoder_stroke_line": (cint, [vp, dbl, dbl, dbl, dbl, flt, u32]),
         "pm_encoder_fill": (cint, [vp, vp, u32, u32]),
         "pm_encoder_polyline": (cint, [vp, vp, u32, u32, flt]),
+        "pm_encoder_fill_rule": (cint, [vp, vp, u32, u32, u32]),
+        "pm_encoder_fill_subpaths": (cint, [vp, vp, vp, u32, u32, u32]),
         "pm_encoder_bytes": (sz, [vp]),
         "pm_encoder_free": (None, [vp]),
         "pm_flatten_svg_path": (i64, [ctypes.c_char_p, dbl, dbl, vp, sz, vp, sz, ctypes.POINTER(sz)]),
@@ -167,10 +173,10 @@ def version():
 # ------------------------------------------------------------------------------------------------
 # feed
 # ------------------------------------------------------------------------------------------------
-def build_scene(kind, width, height, count=0, seed=0, scale=0.0, rect=(0.0, 0.0, 0.0, 0.0), rgba=0):
+def build_scene(kind, width, height, count=0, seed=0, scale=0.0, rect=(0.0, 0.0, 0.0, 0.0), rgba=0, options=0):
     """pm_scene_build: returns the encoded scene as a uint8 numpy array."""
     lib = _lib()
-    d = SceneDesc(kind=kind, width=width, height=height, count=count, seed=seed, scale=scale, rgba=rgba)
+    d = SceneDesc(kind=kind, width=width, height=height, count=count, seed=seed, scale=scale, rgba=rgba, options=options)
     for i in range(4):
         d.rect[i] = float(rect[i])
     need = lib.pm_scene_build(ctypes.byref(d), None, 0)
@@ -252,9 +258,18 @@ class Encoder:
     def stroke_line(self, p0, p1, width, rgba):
         _check(_lib().pm_encoder_stroke_line(self._h, p0[0], p0[1], p1[0], p1[1], width, rgba), "stroke_line")
 
-    def fill(self, points, rgba):
+    def fill(self, points, rgba, flags=None):
         pts = np.ascontiguousarray(points, np.float64)
-        _check(_lib().pm_encoder_fill(self._h, _ptr(pts), pts.shape[0], rgba), "fill")
+        if flags is None:
+            _check(_lib().pm_encoder_fill(self._h, _ptr(pts), pts.shape[0], rgba), "fill")
+        else:
+            _check(_lib().pm_encoder_fill_rule(self._h, _ptr(pts), pts.shape[0], rgba, flags), "fill_rule")
+
+    def fill_subpaths(self, subpaths, rgba, flags=0):
+        """One Fill item for a path of several closed subpaths (holes are cut out, not painted over)."""
+        pts = np.ascontiguousarray(np.concatenate([np.asarray(sp, np.float64).reshape(-1, 2) for sp in subpaths]), np.float64)
+        counts = np.ascontiguousarray([len(sp) for sp in subpaths], np.uint32)
+        _check(_lib().pm_encoder_fill_subpaths(self._h, _ptr(pts), _ptr(counts), counts.size, rgba, flags), "fill_subpaths")
 
     def polyline(self, points, rgba, width):
         pts = np.ascontiguousarray(points, np.float64)

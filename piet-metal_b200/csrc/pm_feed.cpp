@@ -150,16 +150,38 @@ int enc_stroke_line(EncoderImpl &e, Pt p0, Pt p1, float width, uint32_t rgba) { 
     return enc_add_item(e, &it, sizeof it, short_bbox(inflate(bb, hw, hw)));
 }
 
-int enc_fill(EncoderImpl &e, const Pt *pts, size_t n, uint32_t rgba) {  // lib.rs:195-207
+int enc_fill(EncoderImpl &e, const Pt *pts, size_t n, uint32_t rgba, uint32_t flags = 0) {  // lib.rs:195-207 (flags: always 0 there)
     size_t pix; Rect bb;
     if (!enc_points(e, pts, n, &pix, &bb)) return PM_ERR_INVALID_ARG;
     pm_item_fill it;
     memset(&it, 0, sizeof it);
     it.tag = PM_ITEM_FILL;
+    it.flags = flags;
     it.rgba = to_be(rgba);
     it.n_points = (uint32_t)n;
     it.points_ix = (uint32_t)pix;
     return enc_add_item(e, &it, 20, short_bbox(bb));
+}
+
+// Several closed subpaths as ONE Fill item ("need to deal with subpaths", lib.rs:194): subpath 0, then every further
+// subpath closed explicitly and followed by a bridge back to the first point of the path.  The kernels close the
+// list from its last point to its first (metal:262); every bridge is walked once in each direction, so winding
+// and signed area cancel and what is left is the union of the subpaths' own windings.
+int enc_fill_subpaths(EncoderImpl &e, const std::vector<std::vector<Pt>> &sub, uint32_t rgba, uint32_t flags) {
+    std::vector<Pt> joined;
+    for (size_t i = 0; i < sub.size(); i++) {
+        if (sub[i].empty()) continue;
+        if (joined.empty()) {
+            joined = sub[i];
+            joined.push_back(sub[i][0]);
+        } else {
+            joined.insert(joined.end(), sub[i].begin(), sub[i].end());
+            joined.push_back(sub[i][0]);
+            joined.push_back(joined[0]);
+        }
+    }
+    if (joined.empty()) return PM_ERR_INVALID_ARG;
+    return enc_fill(e, joined.data(), joined.size(), rgba, flags);
 }
 
 int enc_polyline(EncoderImpl &e, const Pt *pts, size_t n, uint32_t rgba, float width) {  // lib.rs:209-222
@@ -519,7 +541,9 @@ bool parse_pathlist(const char *text, size_t len, std::vector<PathListEntry> &ou
 }
 
 // make_tiger (lib.rs:286-328) generalised over the path list and the scale.
-int encode_pathlist(EncoderImpl &e, const std::vector<PathListEntry> &paths, double scale) {
+int encode_pathlist(EncoderImpl &e, const std::vector<PathListEntry> &paths, double scale, uint32_t options = 0) {
+    const bool compound = (options & PM_SCENE_OPT_COMPOUND_FILLS) != 0;
+    const uint32_t fill_flags = (options & PM_SCENE_OPT_EVEN_ODD) ? PM_FILL_EVEN_ODD : PM_FILL_NONZERO;
     struct Flat { std::vector<std::vector<Pt>> sub; bool ok; };
     std::vector<Flat> flats(paths.size());
     size_t n_items = 0;
@@ -529,7 +553,7 @@ int encode_pathlist(EncoderImpl &e, const std::vector<PathListEntry> &paths, dou
         if (!flats[i].ok) continue;
         scale_path(bp, scale);
         flatten_path(bp, TOLERANCE, flats[i].sub);
-        if (paths[i].fill != "-") n_items += flats[i].sub.size();    // count_fill_items   :332-335
+        if (paths[i].fill != "-") n_items += compound ? (flats[i].sub.empty() ? 0 : 1) : flats[i].sub.size();    // count_fill_items   :332-335
         if (paths[i].stroke != "-") n_items += flats[i].sub.size();  // count_stroke_items :337-340
     }
     enc_begin_group(e, n_items);
@@ -537,7 +561,8 @@ int encode_pathlist(EncoderImpl &e, const std::vector<PathListEntry> &paths, dou
         if (!flats[i].ok) continue;
         if (paths[i].fill != "-") {  // encode_path :342-347
             uint32_t rgba = parse_color(paths[i].fill.c_str());
-            for (auto &sp : flats[i].sub) enc_fill(e, sp.data(), sp.size(), rgba);
+            if (compound) { if (!flats[i].sub.empty()) enc_fill_subpaths(e, flats[i].sub, rgba, fill_flags); }
+            else for (auto &sp : flats[i].sub) enc_fill(e, sp.data(), sp.size(), rgba);
         }
         if (paths[i].stroke != "-") {  // :318-323 + encode_path_stroke :353-367
             if (paths[i].width == "-") return PM_ERR_PARSE;  // .unwrap() on stroke-width, :319
@@ -689,7 +714,7 @@ int build_scene(EncoderImpl &e, const pm_scene_desc &d) {
             if (!parse_pathlist(pm_tiger_pathlist_begin, (size_t)(pm_tiger_pathlist_end - pm_tiger_pathlist_begin), paths))
                 return PM_ERR_PARSE;
             double scale = d.scale != 0.0 ? d.scale : (double)d.width / 200.0;  // viewBox 0 0 200 200
-            return encode_pathlist(e, paths, scale);
+            return encode_pathlist(e, paths, scale, d.options);
         }
         case PM_SCENE_RAND_BEZIER:
             return build_rand_bezier(e, d.width, d.height, d.count ? d.count : 10000u, d.seed ? d.seed : 0x5EED0004ull);
@@ -760,6 +785,20 @@ int pm_encoder_stroke_line(pm_encoder *e, double x0, double y0, double x1, doubl
 int pm_encoder_fill(pm_encoder *e, const double *xy, uint32_t n_points, uint32_t rgba) {
     if (!e || !xy || n_points == 0) return PM_ERR_INVALID_ARG;
     return enc_status(e, enc_fill(e->impl, reinterpret_cast<const Pt *>(xy), n_points, rgba));
+}
+int pm_encoder_fill_rule(pm_encoder *e, const double *xy, uint32_t n_points, uint32_t rgba, uint32_t flags) {
+    if (!e || !xy || n_points == 0) return PM_ERR_INVALID_ARG;
+    return enc_status(e, enc_fill(e->impl, reinterpret_cast<const Pt *>(xy), n_points, rgba, flags));
+}
+int pm_encoder_fill_subpaths(pm_encoder *e, const double *xy, const uint32_t *counts, uint32_t n_subpaths, uint32_t rgba, uint32_t flags) {
+    if (!e || !xy || !counts || n_subpaths == 0) return PM_ERR_INVALID_ARG;
+    std::vector<std::vector<Pt>> sub(n_subpaths);
+    const Pt *p = reinterpret_cast<const Pt *>(xy);
+    for (uint32_t i = 0; i < n_subpaths; i++) {
+        sub[i].assign(p, p + counts[i]);
+        p += counts[i];
+    }
+    return enc_status(e, enc_fill_subpaths(e->impl, sub, rgba, flags));
 }
 int pm_encoder_polyline(pm_encoder *e, const double *xy, uint32_t n_points, uint32_t rgba, float width) {
     if (!e || !xy || n_points == 0) return PM_ERR_INVALID_ARG;

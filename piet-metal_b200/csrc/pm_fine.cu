@@ -222,7 +222,7 @@ __device__ __forceinline__ void fine_tile(const PmFrameArgs &A, FineWarpSmem *w,
         const uint32_t t_kind = tr.y & 15u, t_w0 = tr.z, t_w1 = tr.w;
         float4 paint = make_float4(0.0f, 0.0f, 0.0f, 1.0f);  // Cmd_Circle paints black (metal:491)
         if (t_kind != PM_REC_CIRCLE) paint = __ldg(&A.item_paint[cur_item]);
-        const bool stroke = t_kind == PM_REC_STROKE, fill = t_kind == PM_REC_DRAWFILL;
+        const bool stroke = t_kind == PM_REC_STROKE, fill = pm_rec_is_drawfill(t_kind), even_odd = t_kind == PM_REC_DRAWFILL_EO;
         const float half_width = pm_u2f(t_w0);
         int run = 0;  // fill: cover entering this lane's pixels from the left
         if (fill || stroke) {
@@ -262,10 +262,10 @@ __device__ __forceinline__ void fine_tile(const PmFrameArgs &A, FineWarpSmem *w,
                     const int4 c = *pc;
                     *pc = make_int4(0, 0, 0, 0);
                     const int backdrop = (int)t_w0;
-                    run += c.x; al[0] = pm_resolve_fill_alpha(a.x + run, backdrop);
-                    run += c.y; al[1] = pm_resolve_fill_alpha(a.y + run, backdrop);
-                    run += c.z; al[2] = pm_resolve_fill_alpha(a.z + run, backdrop);
-                    run += c.w; al[3] = pm_resolve_fill_alpha(a.w + run, backdrop);
+                    run += c.x; al[0] = pm_resolve_fill(a.x + run, backdrop, even_odd);
+                    run += c.y; al[1] = pm_resolve_fill(a.y + run, backdrop, even_odd);
+                    run += c.z; al[2] = pm_resolve_fill(a.z + run, backdrop, even_odd);
+                    run += c.w; al[3] = pm_resolve_fill(a.w + run, backdrop, even_odd);
                 } else {  // renderDf, metal:58-60
                     const float lim = half_width + 0.5f;
                     al[0] = a.x ? pm_saturate(lim - __uint_as_float(~(uint32_t)a.x)) : 0.0f;

@@ -195,7 +195,7 @@ __device__ void heavy_tile_cta(const PmFrameArgs &A, HeavySmem *sh, uint32_t ent
                         float4 paint = make_float4(0.0f, 0.0f, 0.0f, 1.0f);  // Cmd_Circle paints black (metal:491)
                         if (kind != PM_REC_CIRCLE) paint = __ldg(&A.item_paint[(uint32_t)(first >> 32)]);
                         const bool stroke = kind == PM_REC_STROKE;
-                        if (stroke || kind == PM_REC_DRAWFILL) {
+                        if (stroke || pm_rec_is_drawfill(kind)) {
                             const float reach = pm_u2f(tr.z) + 0.5f;
                             for (uint32_t c = s + 1; c < e; c += 32) {
                                 const bool mine = c + lane < e;
@@ -255,7 +255,7 @@ __device__ void heavy_tile_cta(const PmFrameArgs &A, HeavySmem *sh, uint32_t ent
             __syncthreads();
             if (kind == 0) continue;  // (uniform: every thread reads the same words)
             const bool stroke = kind == PM_REC_STROKE;
-            if (stroke || kind == PM_REC_DRAWFILL) {
+            if (stroke || pm_rec_is_drawfill(kind)) {
                 const float reach = pm_u2f(w0) + 0.5f;
                 for (uint32_t p0 = 0; p0 < n; p0 += PM_HEAVY_THREADS) {
                     const uint32_t p = p0 + t;

@@ -60,7 +60,8 @@ __device__ __forceinline__ uint32_t pm_heavy_walk(const PmFrameArgs &A, unsigned
 __device__ __forceinline__ void pm_heavy_resolve8(int *acc, int *cov, uint32_t kind, uint32_t w0, uint32_t w1, float tile_x0, float tile_y0, uint32_t lane, float al[8]) {
     const uint32_t prow = lane >> 1, half = lane & 1u;
     const int off0 = pm_cov_swz((int)prow, (int)half * 8), off1 = pm_cov_swz((int)prow, (int)half * 8 + 4);
-    if (kind == PM_REC_DRAWFILL) {
+    if (pm_rec_is_drawfill(kind)) {
+        const bool eo = kind == PM_REC_DRAWFILL_EO;
         int4 *pa0 = reinterpret_cast<int4 *>(&acc[off0]), *pa1 = reinterpret_cast<int4 *>(&acc[off1]);
         int4 *pc0 = reinterpret_cast<int4 *>(&cov[off0]), *pc1 = reinterpret_cast<int4 *>(&cov[off1]);
         const int4 a0 = *pa0, a1 = *pa1, c0 = *pc0, c1 = *pc1;
@@ -70,14 +71,14 @@ __device__ __forceinline__ void pm_heavy_resolve8(int *acc, int *cov, uint32_t k
         const int other = __shfl_xor_sync(PM_FULL_MASK, sum, 1);  // covers of the left half of the row carry into the right half
         int run = half ? other : 0;
         const int bd = (int)w0;
-        run += c0.x; al[0] = pm_resolve_fill_alpha(a0.x + run, bd);
-        run += c0.y; al[1] = pm_resolve_fill_alpha(a0.y + run, bd);
-        run += c0.z; al[2] = pm_resolve_fill_alpha(a0.z + run, bd);
-        run += c0.w; al[3] = pm_resolve_fill_alpha(a0.w + run, bd);
-        run += c1.x; al[4] = pm_resolve_fill_alpha(a1.x + run, bd);
-        run += c1.y; al[5] = pm_resolve_fill_alpha(a1.y + run, bd);
-        run += c1.z; al[6] = pm_resolve_fill_alpha(a1.z + run, bd);
-        run += c1.w; al[7] = pm_resolve_fill_alpha(a1.w + run, bd);
+        run += c0.x; al[0] = pm_resolve_fill(a0.x + run, bd, eo);
+        run += c0.y; al[1] = pm_resolve_fill(a0.y + run, bd, eo);
+        run += c0.z; al[2] = pm_resolve_fill(a0.z + run, bd, eo);
+        run += c0.w; al[3] = pm_resolve_fill(a0.w + run, bd, eo);
+        run += c1.x; al[4] = pm_resolve_fill(a1.x + run, bd, eo);
+        run += c1.y; al[5] = pm_resolve_fill(a1.y + run, bd, eo);
+        run += c1.z; al[6] = pm_resolve_fill(a1.z + run, bd, eo);
+        run += c1.w; al[7] = pm_resolve_fill(a1.w + run, bd, eo);
     } else if (kind == PM_REC_STROKE) {
         int4 *pa0 = reinterpret_cast<int4 *>(&acc[off0]), *pa1 = reinterpret_cast<int4 *>(&acc[off1]);
         const int4 a0 = *pa0, a1 = *pa1;
@@ -185,7 +186,7 @@ __device__ __noinline__ void pm_heavy_tile_warp(const PmFrameArgs &A, int *acc, 
         if (kind == 0) continue;  // cannot happen for a well-formed list
         const float4 paint = kind != PM_REC_CIRCLE ? __ldg(&A.item_paint[cur]) : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
         const bool stroke = kind == PM_REC_STROKE;
-        if (stroke || kind == PM_REC_DRAWFILL) {
+        if (stroke || pm_rec_is_drawfill(kind)) {
             const float reach = pm_u2f(w0) + 0.5f;
             for (uint32_t c = 0; c < n_chunks; c++) {
                 const uint32_t p = c * 32u + lane;

@@ -509,6 +509,8 @@ __global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) 
 
     if (sp.tag == PM_ITEM_FILL) {
         const uint32_t rgba = ld_u32(it + PM_FILL_RGBA);
+        // PM_FLAG_FILL_RULES: the item's flags word may ask for the even-odd rule (extension; the reference ignores it)
+        const bool even_odd = (A.flags & PM_FLAG_FILL_RULES) != 0 && (ld_u32(it + PM_FILL_FLAGS) & PM_FILL_EVEN_ODD) != 0;
         // backdrop entering this chunk: sum of the deltas of the tiles before it
         int carry = 0;
         for (uint32_t q = lane; q < j0; q += 32) carry += (int)bd[q] >> 1;
@@ -523,8 +525,8 @@ __global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) 
         if (j < span) {
             const uint32_t t = t_lo + j;
             if (v & 1u) {
-                sink.trailer(t, PM_REC_DRAWFILL, PM_REC_SEG_MAX, (uint32_t)backdrop, rgba);
-            } else if (backdrop != 0) {
+                sink.trailer(t, even_odd ? PM_REC_DRAWFILL_EO : PM_REC_DRAWFILL, PM_REC_SEG_MAX, (uint32_t)backdrop, rgba);
+            } else if (even_odd ? (backdrop & 1) != 0 : backdrop != 0) {  // covered: nonzero winding number / odd winding number
                 if ((rgba & 0xff000000u) == 0xff000000u) {  // opaque full cover: rewinds the tile (metal:132-135)
                     atomicMax(&A.occ[sink.row_tile0 + t], ((u64)A.stamp << 32) | (u64)(item + 1u));
                 } else {

@@ -694,7 +694,7 @@ int pm_renderer_read_tile_items(pm_renderer *r, uint32_t *offsets, pm_tile_item 
             const bool last_of_item = k + 1 == keyed.size() || (keyed[k + 1].first >> 32) != q.item;
             if (!last_of_item) continue;  // the item's trailer (DrawFill / Stroke) or its only record sorts last
             const uint32_t kind = q.key & 15u;
-            if (kind == PM_REC_DRAWFILL) push(q.item, (int32_t)pm_f2u(q.p[0]), 0);
+            if (pm_rec_is_drawfill(kind)) push(q.item, (int32_t)pm_f2u(q.p[0]), 0);
             else if (kind == PM_REC_SOLID) push(q.item, 0, 1);
             else push(q.item, 0, 0);
         }

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../include/piet_metal_b200.h"
 #include "../../piet-metal_b200/csrc/pm_pixel_logic.h"
 #include "../../piet-metal_b200/csrc/pm_scene_format.h"
 #include "../../piet-metal_b200/csrc/pm_tile_logic.h"
@@ -69,7 +70,7 @@ void apply_group(TileAcc &t, const std::vector<PmRecord> &recs, size_t j0, size_
     const PmRecord &last = recs[j1 - 1];
     const uint32_t kind = last.key & 15u;
     float fg[4];
-    if (kind == PM_REC_DRAWFILL) {
+    if (pm_rec_is_drawfill(kind)) {
         t.clear_fill();
         for (size_t j = j0; j + 1 < j1; j++) {
             const PmRecord &q = recs[j];
@@ -85,7 +86,7 @@ void apply_group(TileAcc &t, const std::vector<PmRecord> &recs, size_t j0, size_
             int run = 0;
             for (int x = 0; x < 16; x++) {
                 run += t.cov[row][x];
-                float alpha = pm_resolve_fill_alpha(t.acc[row][x] + run, backdrop);
+                float alpha = pm_resolve_fill(t.acc[row][x] + run, backdrop, kind == PM_REC_DRAWFILL_EO);
                 blend_px(t.rgb[row][x], fg, fg[3] * alpha);
             }
         }
@@ -122,7 +123,7 @@ struct pmh_tile_item { uint32_t item; int32_t backdrop; uint32_t effect; };
 
 namespace {
 // Binning of the strip [tile_y0, tile_y1): per-tile record lists and opaque covers.
-std::vector<std::vector<TileBin>> bin_scene(const uint8_t *scene, uint32_t n_tx, uint32_t tile_y0, uint32_t tile_y1, bool fix) {
+std::vector<std::vector<TileBin>> bin_scene(const uint8_t *scene, uint32_t n_tx, uint32_t tile_y0, uint32_t tile_y1, bool fix, uint32_t flags = 0) {
     const uint32_t n_rows = tile_y1 - tile_y0;
     const uint32_t n_items = rd_u32(scene), items_ix = rd_u32(scene + 4);
     std::vector<std::vector<TileBin>> tiles(n_rows, std::vector<TileBin>(n_tx));
@@ -147,6 +148,7 @@ std::vector<std::vector<TileBin>> bin_scene(const uint8_t *scene, uint32_t n_tx,
             const float y0 = (float)(row * 16);
             if (tag == PM_ITEM_FILL) {
                 uint32_t rgba = rd_u32(it + 8), n = rd_u32(it + 12);
+                const bool even_odd = (flags & PM_FLAG_FILL_RULES) != 0 && (rd_u32(it + 4) & PM_FILL_EVEN_ODD) != 0;
                 const uint8_t *pts = scene + rd_u32(it + 16);
                 for (uint32_t k = 0; k < n; k++) {
                     uint32_t k1 = k + 1 == n ? 0 : k + 1;
@@ -157,8 +159,8 @@ std::vector<std::vector<TileBin>> bin_scene(const uint8_t *scene, uint32_t n_tx,
                 for (uint32_t t = t_lo; t <= t_hi; t++) {
                     backdrop += delta[t];
                     if (em[t]) {
-                        rt[t].recs.push_back(pm_rec_words(item, PM_REC_DRAWFILL, PM_REC_SEG_MAX, (uint32_t)backdrop, rgba));
-                    } else if (backdrop != 0) {
+                        rt[t].recs.push_back(pm_rec_words(item, even_odd ? PM_REC_DRAWFILL_EO : PM_REC_DRAWFILL, PM_REC_SEG_MAX, (uint32_t)backdrop, rgba));
+                    } else if (even_odd ? (backdrop & 1) != 0 : backdrop != 0) {
                         if ((rgba & 0xff000000u) == 0xff000000u)
                             rt[t].occ_color = std::max(rt[t].occ_color, ((uint64_t)(item + 1) << 32) | rgba);
                         else
@@ -213,7 +215,7 @@ extern "C" int pmh_render(const uint8_t *scene, size_t len, uint32_t width, uint
     float lut[256];
     for (int i = 0; i < 256; i++) lut[i] = pm_srgb_byte_to_linear((uint32_t)i);
 
-    std::vector<std::vector<TileBin>> tiles = bin_scene(scene, n_tx, tile_y0, tile_y1, fix);
+    std::vector<std::vector<TileBin>> tiles = bin_scene(scene, n_tx, tile_y0, tile_y1, fix, flags);
 
     // ---- fill/blend: per tile, as k_fine does ----
     size_t total = 0;
@@ -239,7 +241,7 @@ extern "C" int pmh_render(const uint8_t *scene, size_t len, uint32_t width, uint
                 for (size_t k = 0; k < recs.size(); k++) {
                     if (k + 1 != recs.size() && recs[k + 1].item == recs[k].item) continue;
                     uint32_t kind = recs[k].key & 15u;
-                    if (kind == PM_REC_DRAWFILL) push(recs[k].item, (int32_t)pm_f2u(recs[k].p[0]), 0);
+                    if (pm_rec_is_drawfill(kind)) push(recs[k].item, (int32_t)pm_f2u(recs[k].p[0]), 0);
                     else if (kind == PM_REC_SOLID) push(recs[k].item, 0, 1);
                     else push(recs[k].item, 0, 0);
                 }
@@ -340,7 +342,7 @@ extern "C" int pmh_stats(const uint8_t *scene, uint32_t width, uint32_t height, 
                 for (size_t j = j0; j + 1 < j1; j++) {
                     const PmRecord &q = recs[j];
                     int ra, rb;
-                    if (kind == PM_REC_DRAWFILL) {
+                    if (pm_rec_is_drawfill(kind)) {
                         pm_fill_rows(q.p[1], q.p[3], ty0, &ra, &rb);
                         for (int row = ra; row <= rb; row++) {
                             AccCount c;
@@ -397,7 +399,7 @@ extern "C" int pmh_row_stats(const uint8_t *scene, uint32_t width, uint32_t heig
             for (size_t j = j0; j + 1 < j1; j++) {
                 const PmRecord &q = recs[j];
                 int ra, rb;
-                if (kind == PM_REC_DRAWFILL) {
+                if (pm_rec_is_drawfill(kind)) {
                     o[7]++;
                     pm_fill_rows(q.p[1], q.p[3], ty0, &ra, &rb);
                     for (int row = ra; row <= rb; row++) { AccCount c; pm_fill_pair(c, q.p, row, tile_x0, ty0); o[2]++; o[3] += c.n_near; }

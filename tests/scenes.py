@@ -2,7 +2,7 @@
 import numpy as np
 
 
-def random_scene(pm, seed, width, height, n_items, mode):
+def random_scene(pm, seed, width, height, n_items, mode, rules=False):
     """Mixed Fill / Poly / Line / Circle items.  `mode` picks the coordinate lattice: 'int16'
     puts vertices on multiples of 8 (tile corners and edges: knife-edge cull decisions), 'int' on
     integers, 'half' on half-integers, 'float' anywhere."""
@@ -30,7 +30,14 @@ def random_scene(pm, seed, width, height, n_items, mode):
                 pts[1] = (pts[1][0], pts[0][1])  # horizontal edge
             if rng.random() < 0.3 and n >= 3:
                 pts[2] = (pts[1][0], pts[2][1])  # vertical edge
-            enc.fill(np.array(pts), rgba)
+            if rules:  # extension: the item's flags word picks the fill rule (PM_FLAG_FILL_RULES), sometimes with a second subpath
+                fl = int(rng.integers(0, 2))
+                if rng.random() < 0.4:
+                    enc.fill_subpaths([pts, [pt() for _ in range(int(rng.integers(3, 6)))]], rgba, flags=fl)
+                else:
+                    enc.fill(np.array(pts), rgba, flags=fl)
+            else:
+                enc.fill(np.array(pts), rgba)
         elif kind < 8:
             n = int(rng.integers(1, 9))
             enc.polyline(np.array([pt() for _ in range(n)]), rgba, float(rng.choice([0.7, 1.0, 2.0, 5.5, 17.0])))
@@ -53,6 +60,15 @@ def fuzz_case(pm, seed):
     height = int(rng.choice([16, 40, 64, 130, 272]))
     scene = random_scene(pm, seed, width, height, int(rng.integers(1, 25)), mode)
     return scene, width, height, int(seed % 7 == 0)
+
+
+def rules_case(pm, seed):
+    """Fuzz scene whose Fill items carry random fill-rule flags and second subpaths (for PM_FLAG_FILL_RULES)."""
+    rng = np.random.default_rng(5000 + seed)
+    mode = FUZZ_MODES[1 + seed % 3]
+    width = int(rng.choice([48, 100, 256, 300]))
+    height = int(rng.choice([40, 64, 130, 272]))
+    return random_scene(pm, 7000 + seed, width, height, int(rng.integers(1, 20)), mode, rules=True), width, height
 
 
 def items_equal(a, b):

@@ -63,3 +63,14 @@ def test_row_strips(pm, oracle):
     full = oracle.harness_render(scene, 512, 512)["rgba8"]
     parts = [oracle.harness_render(scene, 512, 512, tile_y0=a, tile_y1=b)["rgba8"] for a, b in ((0, 11), (11, 12), (12, 32))]
     assert np.array_equal(np.concatenate(parts, axis=0), full)
+
+
+def test_fill_rules_extension(pm, oracle):
+    """PM_FLAG_FILL_RULES (extension): even-odd items and two-subpath fills through the device's binning / fill logic
+    (replayed on the CPU) against the oracle's literal loop with the same extension switched on."""
+    for seed in range(60):
+        scene, w, h = scenes.rules_case(pm, seed)
+        compare(oracle, scene, w, h, flags=pm.FLAG_FILL_RULES)
+    for opts in (pm.SCENE_OPT_COMPOUND_FILLS, pm.SCENE_OPT_COMPOUND_FILLS | pm.SCENE_OPT_EVEN_ODD):
+        scene = pm.build_scene(pm.SCENE_TIGER, 512, 512, options=opts)
+        compare(oracle, scene, 512, 512, flags=pm.FLAG_FILL_RULES)

@@ -75,6 +75,29 @@ def test_fuzz_knife_edges(pm, oracle):
         check(gpu, ref, "fuzz seed %d" % seed)
 
 
+def test_fill_rules_extension(pm, oracle):
+    """PM_FLAG_FILL_RULES: PietFill.flags bit 0 = even-odd rule (TestApp/PietRender.metal:538-540 gives the formula,
+    TestApp/SceneEncoder.h:44 reserves the word), multi-subpath fills (holes) through pm_encoder_fill_subpaths, the tiger with
+    one compound Fill item per <path>.  GPU against the oracle with the same extension switched on."""
+    r = pm.PietRenderer(device=0, flags=pm.FLAG_FILL_RULES)
+    try:
+        for seed in range(60):
+            scene, w, h = scenes.rules_case(pm, seed)
+            check(gpu_render(r, scene, w, h), oracle.render(scene, w, h, flags=pm.FLAG_FILL_RULES, f32=True, items=True), "rules seed %d" % seed)
+        for opts in (pm.SCENE_OPT_COMPOUND_FILLS, pm.SCENE_OPT_COMPOUND_FILLS | pm.SCENE_OPT_EVEN_ODD):
+            scene = pm.build_scene(pm.SCENE_TIGER, 1024, 1024, options=opts)
+            check(gpu_render(r, scene, 1024, 1024), oracle.render(scene, 1024, 1024, flags=pm.FLAG_FILL_RULES, f32=True, items=True), "compound tiger %d" % opts)
+    finally:
+        r.close()
+    # without the flag the word is ignored, as upstream: an even-odd item renders like a nonzero one
+    r = pm.PietRenderer(device=0)
+    try:
+        scene, w, h = scenes.rules_case(pm, 3)
+        check(gpu_render(r, scene, w, h), oracle.render(scene, w, h, f32=True, items=True), "rules ignored")
+    finally:
+        r.close()
+
+
 def test_exact_srgb_flag_is_tighter(pm, oracle):
     scene, w, h = pm.build_scene(pm.SCENE_TIGER, 512, 512), 512, 512
     r = pm.PietRenderer(device=0, flags=pm.FLAG_EXACT_SRGB)

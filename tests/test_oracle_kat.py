@@ -150,3 +150,68 @@ def test_golden_tiger_128(pm, oracle):
     gold = np.load(os.path.join(root, "golden", "tiger_128_rgba8.npy"))
     scene = pm.build_scene(pm.SCENE_TIGER, 128, 128)
     assert np.array_equal(oracle.render(scene, 128, 128)["rgba8"], gold)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Extension: even-odd rule and multi-subpath fills through PietFill.flags
+# ---------------------------------------------------------------------------------------------------
+PMO_FLAG_FILL_RULES = 4
+
+
+def _star(pm, flags, rgba=0x000000ff):
+    """A pentagram on 64 x 64: its centre pentagon has winding number 2.  (Centre off the tile grid: a vertex exactly on
+    a tile's left edge is a case the reference's left-edge split does not handle, with either rule.)"""
+    import math
+    cx, cy, r = 33.3, 32.7, 28.0
+    pts = [(cx + r * math.sin(2 * math.pi * (2 * k) / 5), cy - r * math.cos(2 * math.pi * (2 * k) / 5)) for k in range(5)]
+    enc = pm.Encoder(1 << 12)
+    enc.begin_group(1)
+    enc.fill(np.array(pts), rgba, flags=flags)
+    enc.end_group()
+    return enc.bytes()
+
+
+def test_even_odd_rule_empties_the_doubly_wound_centre(pm, oracle):
+    eo = _star(pm, pm.FILL_EVEN_ODD)
+    nonzero = oracle.render(eo, 64, 64)["rgba8"]                                 # the flag word is ignored by default, as upstream
+    assert np.array_equal(nonzero, oracle.render(_star(pm, 0), 64, 64)["rgba8"])
+    evenodd = oracle.render(eo, 64, 64, flags=PMO_FLAG_FILL_RULES)["rgba8"]
+    assert (nonzero[33, 33, :3] == 0).all() and (evenodd[33, 33, :3] == 255).all()  # centre: winding 2 -> filled / empty
+    assert (nonzero[12, 33, :3] == 0).all() and (evenodd[12, 33, :3] == 0).all()    # the top point of the star: winding 1
+    assert (evenodd[2, 2, :3] == 255).all()
+    # with the extension on, an item without the bit is still filled by the nonzero rule
+    assert np.array_equal(oracle.render(_star(pm, 0), 64, 64, flags=PMO_FLAG_FILL_RULES)["rgba8"], nonzero)
+
+
+def test_subpaths_cut_holes(pm, oracle):
+    """One Fill item of two subpaths (pm_encoder_fill_subpaths): an outer square and an inner square wound the other
+    way.  Nonzero rule, default renderer: the hole is cut out -- the reference's per-subpath fills would paint it over
+    (src/lib.rs:194 'need to deal with subpaths')."""
+    # (slightly tilted quadrilaterals: an exactly horizontal edge that crosses a tile boundary gets FillEdge sign 0 in
+    # the reference's left-edge split, metal:336-338, and is lost -- with one subpath as with two)
+    outer = [(8.3, 8.1), (88.2, 9.4), (87.1, 56.3), (9.2, 55.2)]
+    inner = [(30.4, 20.2), (29.6, 44.1), (70.3, 43.2), (69.5, 19.3)]
+    enc = pm.Encoder(1 << 12)
+    enc.begin_group(1)
+    enc.fill_subpaths([outer, inner], 0x203040ff)
+    enc.end_group()
+    img = oracle.render(enc.bytes(), 96, 64)["rgba8"]
+    assert (img[32, 50, :3] == 255).all()          # inside the hole
+    assert (img[32, 20, :3] != 255).any()          # in the ring
+    assert (img[12, 50, :3] != 255).any()
+    assert (img[2, 2, :3] == 255).all()
+    # the bridges between the subpaths leave no trace: the picture equals "outer filled, then inner painted white"
+    enc2 = pm.Encoder(1 << 12)
+    enc2.begin_group(2)
+    enc2.fill(np.array(outer), 0x203040ff)
+    enc2.fill(np.array(inner), 0xffffffff)
+    enc2.end_group()
+    two = oracle.render(enc2.bytes(), 96, 64)["rgba8"]
+    assert np.abs(img.astype(int) - two.astype(int)).max() <= 1
+    # same-direction inner square + even-odd rule cuts the same hole
+    enc = pm.Encoder(1 << 12)
+    enc.begin_group(1)
+    enc.fill_subpaths([outer, inner[::-1]], 0x203040ff, flags=pm.FILL_EVEN_ODD)
+    enc.end_group()
+    img2 = oracle.render(enc.bytes(), 96, 64, flags=PMO_FLAG_FILL_RULES)["rgba8"]
+    assert np.array_equal(img2, img)
