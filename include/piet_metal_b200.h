@@ -215,6 +215,29 @@ int pm_renderer_set_scene(pm_renderer *r, const uint8_t *scene, size_t len);
  * it is copied device-to-device on the render stream and validated on the device. */
 int pm_renderer_set_scene_device(pm_renderer *r, const void *scene_dev, size_t len);
 
+/* Flattening and scene encoding ON THE DEVICE (the step in front of the hot path: src/flatten.rs:10-47 + Encoder::fill /
+ * polyline, src/lib.rs:195-240, which the reference runs on the CPU).  The caller hands over path control points as they
+ * are -- one item per subpath, in painter's order, exactly what make_tiger produces after BezPath::from_svg (lib.rs:296-323)
+ * -- and the renderer builds the encoded scene in its own scene buffer: every coordinate times `scale` (Affine::scale,
+ * lib.rs:297), cubics cut into n = max(1, ceil((|3 p2 - p3 - 3 p1 + p0|^2 / (432 (tolerance / 100)^2))^(1/6))) uniform
+ * steps in f64, points narrowed to f32, u16 bounding boxes, PietFill / PietStrokePolyLine items.  Host arrays; the
+ * renderer copies them.  pm_renderer_read_scene copies the scene the renderer holds (however it was set) back out. */
+enum { PM_VERB_LINE = 0u, PM_VERB_CURVE = 1u };
+typedef struct pm_path_set {
+    uint32_t n_subpaths;            /* one item per subpath */
+    uint32_t n_segments;            /* LineTo / CurveTo elements of all subpaths */
+    const uint32_t *first_segment;  /* n_subpaths + 1 entries: subpath i owns segments [first_segment[i], first_segment[i+1]) */
+    const double *start;            /* n_subpaths x 2: the subpath's MoveTo point */
+    const uint8_t *verb;            /* n_segments: PM_VERB_LINE / PM_VERB_CURVE */
+    const double *ctrl;             /* n_segments x 6: CurveTo c1.x c1.y c2.x c2.y end.x end.y; LineTo: its end point in the last two */
+    const uint32_t *tag;            /* n_subpaths: 3 (PietFill) or 4 (PietStrokePolyLine) */
+    const uint32_t *rgba;           /* n_subpaths: 0xRRGGBBAA */
+    const float *width;             /* n_subpaths: stroke width (read for tag 4) */
+    const uint32_t *flags;          /* n_subpaths or NULL: PietFill.flags */
+} pm_path_set;
+int pm_renderer_set_scene_paths(pm_renderer *r, const pm_path_set *paths, double scale, double tolerance);
+int pm_renderer_read_scene(pm_renderer *r, uint8_t *dst, size_t cap, size_t *len);
+
 /* Enqueue one frame on the renderer's stream (asynchronous, like drawInMTKView's commit). */
 int pm_renderer_render(pm_renderer *r);
 /* Per-frame CUDA events (the ms_* fields of pm_frame_stats):

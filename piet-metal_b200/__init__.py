@@ -62,6 +62,12 @@ class FrameStats(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class PathSetC(ctypes.Structure):
+    _fields_ = [("n_subpaths", ctypes.c_uint32), ("n_segments", ctypes.c_uint32), ("first_segment", ctypes.c_void_p),
+                ("start", ctypes.c_void_p), ("verb", ctypes.c_void_p), ("ctrl", ctypes.c_void_p), ("tag", ctypes.c_void_p),
+                ("rgba", ctypes.c_void_p), ("width", ctypes.c_void_p), ("flags", ctypes.c_void_p)]
+
+
 TILE_ITEM_DTYPE = np.dtype([("item", np.uint32), ("backdrop", np.int32), ("effect", np.uint32)])
 
 # every entry point declared in include/piet_metal_b200.h
@@ -76,6 +82,7 @@ EXPORTS = [
     "pm_renderer_set_scene", "pm_renderer_set_scene_device", "pm_renderer_render", "pm_renderer_set_frame_events", "pm_renderer_sync",
     "pm_renderer_read_rgba8", "pm_renderer_render_host", "pm_renderer_framebuffer", "pm_renderer_stream",
     "pm_renderer_read_rgba32f", "pm_renderer_read_tile_items", "pm_host_alloc", "pm_host_free",
+    "pm_renderer_set_scene_paths", "pm_renderer_read_scene",
     "pm_group_create", "pm_group_destroy", "pm_group_size", "pm_group_member", "pm_group_resize", "pm_group_set_scene",
     "pm_group_strip_bounds", "pm_group_set_frame_events", "pm_group_render", "pm_group_sync", "pm_group_read_rgba8",
     "pm_group_gather_device", "pm_group_nccl_version",
@@ -136,6 +143,8 @@ def _lib():
         "pm_renderer_read_tile_items": (cint, [vp, vp, vp, sz, ctypes.POINTER(sz), vp]),
         "pm_host_alloc": (cint, [ctypes.POINTER(vp), sz]),
         "pm_host_free": (None, [vp]),
+        "pm_renderer_set_scene_paths": (cint, [vp, ctypes.POINTER(PathSetC), dbl, dbl]),
+        "pm_renderer_read_scene": (cint, [vp, vp, sz, ctypes.POINTER(sz)]),
         "pm_group_create": (cint, [ctypes.POINTER(vp), vp, u32, u32]),
         "pm_group_destroy": (None, [vp]),
         "pm_group_size": (u32, [vp]),
@@ -324,6 +333,19 @@ class PietRenderer:
 
     set_scene = init_scene
 
+    def set_scene_paths(self, path_set, scale=1.0, tolerance=0.1):
+        """Flatten and encode a PathSet on the device (src/flatten.rs + Encoder::fill / polyline, which the reference runs on the CPU)."""
+        c, keep = path_set.arrays()
+        _check(_lib().pm_renderer_set_scene_paths(self._h, ctypes.byref(c), scale, tolerance), "pm_renderer_set_scene_paths")
+        del keep
+
+    def read_scene(self):
+        n = ctypes.c_size_t(0)
+        _lib().pm_renderer_read_scene(self._h, None, 0, ctypes.byref(n))
+        buf = np.empty(n.value, np.uint8)
+        _check(_lib().pm_renderer_read_scene(self._h, _ptr(buf), buf.size, ctypes.byref(n)), "pm_renderer_read_scene")
+        return buf
+
     def set_scene_device(self, dev_ptr, nbytes):
         _check(_lib().pm_renderer_set_scene_device(self._h, ctypes.c_void_p(dev_ptr), nbytes), "pm_renderer_set_scene_device")
 
@@ -422,6 +444,36 @@ def write_image(path, rgba8):
 def strip_bounds(n_tile_rows, world_size):
     """Contiguous row-strip shard of the frame's tile rows: rank g renders [b[g], b[g+1])."""
     return [(n_tile_rows * g) // world_size for g in range(world_size + 1)]
+
+
+class PathSet:
+    """Path control points for pm_renderer_set_scene_paths (flattening + encoding on the device): one item per subpath."""
+
+    def __init__(self):
+        self.first, self.start, self.verb, self.ctrl = [0], [], [], []
+        self.tag, self.rgba, self.width, self.flags = [], [], [], []
+
+    def begin(self, x, y, tag, rgba, width=0.0, flags=0):
+        """MoveTo: a new subpath = a new item (tag 3 = PietFill, 4 = PietStrokePolyLine)."""
+        self.start.append((float(x), float(y)))
+        self.tag.append(tag); self.rgba.append(rgba); self.width.append(width); self.flags.append(flags)
+        self.first.append(self.first[-1])
+
+    def line_to(self, x, y):
+        self.verb.append(0); self.ctrl.append((0.0, 0.0, 0.0, 0.0, float(x), float(y))); self.first[-1] += 1
+
+    def curve_to(self, c1x, c1y, c2x, c2y, x, y):
+        self.verb.append(1); self.ctrl.append((float(c1x), float(c1y), float(c2x), float(c2y), float(x), float(y))); self.first[-1] += 1
+
+    def arrays(self):
+        a = {"first": np.ascontiguousarray(self.first, np.uint32), "start": np.ascontiguousarray(self.start, np.float64).reshape(-1, 2),
+             "verb": np.ascontiguousarray(self.verb, np.uint8), "ctrl": np.ascontiguousarray(self.ctrl, np.float64).reshape(-1, 6),
+             "tag": np.ascontiguousarray(self.tag, np.uint32), "rgba": np.ascontiguousarray(self.rgba, np.uint32),
+             "width": np.ascontiguousarray(self.width, np.float32), "flags": np.ascontiguousarray(self.flags, np.uint32)}
+        c = PathSetC(n_subpaths=len(self.tag), n_segments=len(self.verb), first_segment=a["first"].ctypes.data, start=a["start"].ctypes.data,
+                     verb=a["verb"].ctypes.data if len(self.verb) else None, ctrl=a["ctrl"].ctypes.data if len(self.verb) else None,
+                     tag=a["tag"].ctypes.data, rgba=a["rgba"].ctypes.data, width=a["width"].ctypes.data, flags=a["flags"].ctypes.data)
+        return c, a  # (keep `a` alive while `c` is in use)
 
 
 class PietRendererGroup:

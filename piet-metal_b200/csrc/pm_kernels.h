@@ -95,6 +95,22 @@ struct PmFrameArgs {
     const float4 *item_paint;   // per item: linear r, g, b and alpha of its colour (k_plan; Circle: opaque black)
 };
 
+// A set of paths in device memory (pm_flatten.cu; the host-side description is pm_path_set in the public header).
+struct PmPathSetDev {
+    uint32_t n_subpaths, n_segments;
+    const uint32_t *first;   // n_subpaths + 1
+    const double *start;     // n_subpaths x 2
+    const uint8_t *verb;     // n_segments
+    const double *ctrl;      // n_segments x 6
+    const uint32_t *tag, *rgba, *flags;  // n_subpaths (flags may be null)
+    const float *width;      // n_subpaths
+};
+// Flattening + scene encoding on the device: counts and their prefix (cnt becomes the offsets, *total the number of
+// emitted points without the MoveTo points), then points, bounding boxes, items and header into `scene`.
+void pm_launch_flat_count(const PmPathSetDev &P, double scale, double tolerance, uint32_t *cnt, long long *bbox, unsigned long long *total, cudaStream_t s);
+void pm_launch_flat_emit(const PmPathSetDev &P, double scale, double tolerance, const uint32_t *off, unsigned long long total_points, uint8_t *scene,
+                         uint32_t items_ix, uint32_t pts_base, long long *bbox, cudaStream_t s);
+
 struct PmPlanResult { uint32_t n_segments; uint32_t n_rows; unsigned long long bd_words; uint32_t error; uint32_t n_pieces; };
 
 // Validates an encoded scene on the device.  *err (device) becomes non-zero if a ref or count is

@@ -327,18 +327,20 @@ int finish_frames(pm_renderer *r, bool debug_f32) {
     return PM_ERR_NOMEM;
 }
 
-int install_scene(pm_renderer *r, const void *src, size_t len, cudaMemcpyKind kind) {
-    if (!src || len < PM_GROUP_HEADER_SIZE || len > 0xfffffff0ull) return len < PM_GROUP_HEADER_SIZE ? PM_ERR_SCENE_MALFORMED : PM_ERR_INVALID_ARG;
-    PM_CUDA(cudaStreamSynchronize(r->stream));
+int ensure_scene_cap(pm_renderer *r, size_t len) {
     if (len > r->scene_cap) {
         if (r->scene) PM_CUDA(cudaFree(r->scene));
         r->scene = nullptr;
+        r->scene_cap = 0;
         size_t cap = (len + 255) & ~(size_t)255;
         PM_CUDA(cudaMalloc(&r->scene, cap));
         r->scene_cap = cap;
     }
-    r->have_scene = false;
-    PM_CUDA(cudaMemcpyAsync(r->scene, src, len, kind, r->stream));
+    return PM_OK;
+}
+
+// The scene bytes are in r->scene (enqueued on the stream): validate them on the device and size the per-item tables.
+int adopt_scene(pm_renderer *r, size_t len) {
     PM_CUDA(cudaMemsetAsync(r->dev_err, 0, sizeof(uint32_t), r->stream));
     pm_launch_validate(r->scene, (uint32_t)len, r->dev_err, r->stream);
     PM_CUDA(cudaGetLastError());
@@ -367,6 +369,79 @@ int install_scene(pm_renderer *r, const void *src, size_t len, cudaMemcpyKind ki
     r->have_scene = true;
     r->plan_dirty = true;
     return PM_OK;
+}
+
+int install_scene(pm_renderer *r, const void *src, size_t len, cudaMemcpyKind kind) {
+    if (!src || len < PM_GROUP_HEADER_SIZE || len > 0xfffffff0ull) return len < PM_GROUP_HEADER_SIZE ? PM_ERR_SCENE_MALFORMED : PM_ERR_INVALID_ARG;
+    PM_CUDA(cudaStreamSynchronize(r->stream));
+    int st = ensure_scene_cap(r, len);
+    if (st != PM_OK) return st;
+    r->have_scene = false;
+    PM_CUDA(cudaMemcpyAsync(r->scene, src, len, kind, r->stream));
+    return adopt_scene(r, len);
+}
+
+// Flattening + encoding on the device (pm_flatten.cu).  One temporary allocation holds the uploaded path set and the
+// scratch of the kernels; it is freed before returning (this runs once per scene, not per frame).
+int install_paths(pm_renderer *r, const pm_path_set *ps, double scale, double tolerance) {
+    const size_t ns = ps->n_subpaths, ng = ps->n_segments;
+    if (ns == 0 || ns > 0x3fffffffull || ng > 0x7fffffffull) return PM_ERR_INVALID_ARG;
+    if (!ps->first_segment || !ps->start || !ps->tag || !ps->rgba || !ps->width || (ng && (!ps->verb || !ps->ctrl))) return PM_ERR_INVALID_ARG;
+    if (ps->first_segment[0] != 0 || ps->first_segment[ns] != ng) return PM_ERR_INVALID_ARG;
+    for (size_t i = 0; i < ns; i++) {
+        if (ps->first_segment[i] > ps->first_segment[i + 1]) return PM_ERR_INVALID_ARG;
+        if (ps->tag[i] != PM_ITEM_FILL && ps->tag[i] != PM_ITEM_POLY) return PM_ERR_INVALID_ARG;
+    }
+    if (!(scale == scale) || !(tolerance > 0.0)) return PM_ERR_INVALID_ARG;
+    PM_CUDA(cudaStreamSynchronize(r->stream));
+    r->have_scene = false;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_first = 0, o_start = o_first + al((ns + 1) * 4), o_ctrl = o_start + al(ns * 16), o_verb = o_ctrl + al(ng * 48 + 16),
+                 o_tag = o_verb + al(ng + 1), o_rgba = o_tag + al(ns * 4), o_flags = o_rgba + al(ns * 4), o_width = o_flags + al(ns * 4),
+                 o_cnt = o_width + al(ns * 4), o_bbox = o_cnt + al((ng + 1) * 4), o_total = o_bbox + al(ns * 32), total_bytes = o_total + 256;
+    uint8_t *tmp = nullptr;
+    PM_CUDA(cudaMalloc(&tmp, total_bytes));
+    auto fail = [&](int st) { cudaFree(tmp); return st; };
+#define PM_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(cuda_fail(e_, #call, __LINE__)); } while (0)
+    PM_TRY(cudaMemcpyAsync(tmp + o_first, ps->first_segment, (ns + 1) * 4, cudaMemcpyHostToDevice, r->stream));
+    PM_TRY(cudaMemcpyAsync(tmp + o_start, ps->start, ns * 16, cudaMemcpyHostToDevice, r->stream));
+    if (ng) {
+        PM_TRY(cudaMemcpyAsync(tmp + o_ctrl, ps->ctrl, ng * 48, cudaMemcpyHostToDevice, r->stream));
+        PM_TRY(cudaMemcpyAsync(tmp + o_verb, ps->verb, ng, cudaMemcpyHostToDevice, r->stream));
+    }
+    PM_TRY(cudaMemcpyAsync(tmp + o_tag, ps->tag, ns * 4, cudaMemcpyHostToDevice, r->stream));
+    PM_TRY(cudaMemcpyAsync(tmp + o_rgba, ps->rgba, ns * 4, cudaMemcpyHostToDevice, r->stream));
+    PM_TRY(cudaMemcpyAsync(tmp + o_width, ps->width, ns * 4, cudaMemcpyHostToDevice, r->stream));
+    if (ps->flags) PM_TRY(cudaMemcpyAsync(tmp + o_flags, ps->flags, ns * 4, cudaMemcpyHostToDevice, r->stream));
+    PmPathSetDev P;
+    P.n_subpaths = (uint32_t)ns; P.n_segments = (uint32_t)ng;
+    P.first = reinterpret_cast<const uint32_t *>(tmp + o_first);
+    P.start = reinterpret_cast<const double *>(tmp + o_start);
+    P.ctrl = reinterpret_cast<const double *>(tmp + o_ctrl);
+    P.verb = tmp + o_verb;
+    P.tag = reinterpret_cast<const uint32_t *>(tmp + o_tag);
+    P.rgba = reinterpret_cast<const uint32_t *>(tmp + o_rgba);
+    P.flags = ps->flags ? reinterpret_cast<const uint32_t *>(tmp + o_flags) : nullptr;
+    P.width = reinterpret_cast<const float *>(tmp + o_width);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(tmp + o_cnt);
+    long long *bbox = reinterpret_cast<long long *>(tmp + o_bbox);
+    unsigned long long *total_dev = reinterpret_cast<unsigned long long *>(tmp + o_total);
+    pm_launch_flat_count(P, scale, tolerance, cnt, bbox, total_dev, r->stream);
+    PM_TRY(cudaGetLastError());
+    unsigned long long total = 0;
+    PM_TRY(cudaMemcpyAsync(&total, total_dev, 8, cudaMemcpyDeviceToHost, r->stream));
+    PM_TRY(cudaStreamSynchronize(r->stream));
+    const unsigned long long items_ix = PM_GROUP_HEADER_SIZE + ns * PM_BBOX_SIZE, pts_base = items_ix + ns * PM_ITEM_SIZE;
+    const unsigned long long len = pts_base + 8ull * (total + ns);
+    if (len > 0xfffffff0ull) { g_last_error = "the flattened scene would exceed 4 GiB"; return fail(PM_ERR_NOMEM); }
+    int st = ensure_scene_cap(r, (size_t)len);
+    if (st != PM_OK) return fail(st);
+    pm_launch_flat_emit(P, scale, tolerance, cnt, total, r->scene, (uint32_t)items_ix, (uint32_t)pts_base, bbox, r->stream);
+    PM_TRY(cudaGetLastError());
+#undef PM_TRY
+    st = adopt_scene(r, (size_t)len);  // (synchronises the stream: the temporary can go)
+    cudaFree(tmp);
+    return st;
 }
 
 }  // namespace
@@ -485,6 +560,25 @@ int pm_renderer_set_scene_device(pm_renderer *r, const void *scene_dev, size_t l
     int st = use_device(r);
     if (st != PM_OK) return st;
     return install_scene(r, scene_dev, len, cudaMemcpyDeviceToDevice);
+}
+
+int pm_renderer_set_scene_paths(pm_renderer *r, const pm_path_set *paths, double scale, double tolerance) {
+    if (!r || !paths) return PM_ERR_INVALID_ARG;
+    int st = use_device(r);
+    if (st != PM_OK) return st;
+    return install_paths(r, paths, scale, tolerance);
+}
+
+int pm_renderer_read_scene(pm_renderer *r, uint8_t *dst, size_t cap, size_t *len) {
+    if (!r) return PM_ERR_INVALID_ARG;
+    if (!r->have_scene) return PM_ERR_STATE;
+    if (len) *len = r->scene_len;
+    if (!dst || cap < r->scene_len) return PM_ERR_BUFFER_TOO_SMALL;
+    int st = use_device(r);
+    if (st != PM_OK) return st;
+    PM_CUDA(cudaMemcpyAsync(dst, r->scene, r->scene_len, cudaMemcpyDeviceToHost, r->stream));
+    PM_CUDA(cudaStreamSynchronize(r->stream));
+    return PM_OK;
 }
 
 int pm_renderer_render(pm_renderer *r) {
