@@ -307,6 +307,35 @@ int pm_group_gather_device(pm_group *g, uint32_t root, void **dev_ptr, size_t *p
 /* NCCL_VERSION_CODE of the library that was loaded, 0 if none could be. */
 int pm_group_nccl_version(void);
 
+/* ------------------------------------------------------------------------------------------- */
+/* RenderContext facade (host side; the drawing is flattened and encoded on the device)          */
+/* ------------------------------------------------------------------------------------------- */
+/* The piet calls the reference's README aspires to (README.md:3) and its `Encoder` stops short of (src/lib.rs:165-222):
+ * clear, transform / save / restore, fill, fill_even_odd, stroke with a solid colour (0xRRGGBBAA), finish.  Paths are
+ * BezPath-like element lists; quadratics are raised to cubics; a filled path with several subpaths becomes one item
+ * (holes are holes); strokes follow make_tiger: one polyline item per subpath, thin-stroke rule (lib.rs:353-362).
+ * finish() installs the drawing as the renderer's scene (pm_renderer_set_scene_paths) and empties the context;
+ * render and read back with pm_renderer_render / pm_renderer_read_rgba8 as usual. */
+enum { PM_EL_MOVE = 0u, PM_EL_LINE = 1u, PM_EL_QUAD = 2u, PM_EL_CURVE = 3u, PM_EL_CLOSE = 4u };
+typedef struct pm_path_el {
+    uint32_t verb;   /* PM_EL_* */
+    uint32_t pad;
+    double x[6];     /* MOVE / LINE: x y; QUAD: cx cy x y; CURVE: c1x c1y c2x c2y x y */
+} pm_path_el;
+typedef struct pm_context pm_context;
+int pm_context_new(pm_context **out, pm_renderer *renderer, uint32_t width, uint32_t height);
+void pm_context_free(pm_context *c);
+int pm_context_save(pm_context *c);
+int pm_context_restore(pm_context *c);
+int pm_context_transform(pm_context *c, const double affine[6]);   /* kurbo order [a b c d e f]: x' = a x + c y + e */
+int pm_context_clear(pm_context *c, uint32_t rgba);
+int pm_context_fill(pm_context *c, const pm_path_el *els, size_t n, uint32_t rgba);
+int pm_context_fill_even_odd(pm_context *c, const pm_path_el *els, size_t n, uint32_t rgba);
+int pm_context_stroke(pm_context *c, const pm_path_el *els, size_t n, uint32_t rgba, double width);
+uint32_t pm_context_item_count(const pm_context *c);
+int pm_context_path_set(pm_context *c, pm_path_set *out);          /* the recorded drawing (pointers into the context) */
+int pm_context_finish(pm_context *c, double tolerance);            /* tolerance <= 0: the reference's 0.1 (lib.rs:330) */
+
 /* Pinned host memory for fast host<->device copies of scenes and frames. */
 int pm_host_alloc(void **out, size_t bytes);
 void pm_host_free(void *p);

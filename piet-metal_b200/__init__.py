@@ -83,6 +83,8 @@ EXPORTS = [
     "pm_renderer_read_rgba8", "pm_renderer_render_host", "pm_renderer_framebuffer", "pm_renderer_stream",
     "pm_renderer_read_rgba32f", "pm_renderer_read_tile_items", "pm_host_alloc", "pm_host_free",
     "pm_renderer_set_scene_paths", "pm_renderer_read_scene",
+    "pm_context_new", "pm_context_free", "pm_context_save", "pm_context_restore", "pm_context_transform", "pm_context_clear",
+    "pm_context_fill", "pm_context_fill_even_odd", "pm_context_stroke", "pm_context_item_count", "pm_context_path_set", "pm_context_finish",
     "pm_group_create", "pm_group_destroy", "pm_group_size", "pm_group_member", "pm_group_resize", "pm_group_set_scene",
     "pm_group_strip_bounds", "pm_group_set_frame_events", "pm_group_render", "pm_group_sync", "pm_group_read_rgba8",
     "pm_group_gather_device", "pm_group_nccl_version",
@@ -145,6 +147,18 @@ def _lib():
         "pm_host_free": (None, [vp]),
         "pm_renderer_set_scene_paths": (cint, [vp, ctypes.POINTER(PathSetC), dbl, dbl]),
         "pm_renderer_read_scene": (cint, [vp, vp, sz, ctypes.POINTER(sz)]),
+        "pm_context_new": (cint, [ctypes.POINTER(vp), vp, u32, u32]),
+        "pm_context_free": (None, [vp]),
+        "pm_context_save": (cint, [vp]),
+        "pm_context_restore": (cint, [vp]),
+        "pm_context_transform": (cint, [vp, vp]),
+        "pm_context_clear": (cint, [vp, u32]),
+        "pm_context_fill": (cint, [vp, vp, sz, u32]),
+        "pm_context_fill_even_odd": (cint, [vp, vp, sz, u32]),
+        "pm_context_stroke": (cint, [vp, vp, sz, u32, dbl]),
+        "pm_context_item_count": (u32, [vp]),
+        "pm_context_path_set": (cint, [vp, ctypes.POINTER(PathSetC)]),
+        "pm_context_finish": (cint, [vp, dbl]),
         "pm_group_create": (cint, [ctypes.POINTER(vp), vp, u32, u32]),
         "pm_group_destroy": (None, [vp]),
         "pm_group_size": (u32, [vp]),
@@ -474,6 +488,90 @@ class PathSet:
                      verb=a["verb"].ctypes.data if len(self.verb) else None, ctrl=a["ctrl"].ctypes.data if len(self.verb) else None,
                      tag=a["tag"].ctypes.data, rgba=a["rgba"].ctypes.data, width=a["width"].ctypes.data, flags=a["flags"].ctypes.data)
         return c, a  # (keep `a` alive while `c` is in use)
+
+
+PATH_EL_DTYPE = np.dtype([("verb", np.uint32), ("pad", np.uint32), ("x", np.float64, 6)])
+
+
+class BezPath:
+    """kurbo-style path builder for RenderContext."""
+
+    def __init__(self):
+        self.els = []
+
+    def move_to(self, x, y): self.els.append((0, (x, y, 0, 0, 0, 0))); return self
+    def line_to(self, x, y): self.els.append((1, (x, y, 0, 0, 0, 0))); return self
+    def quad_to(self, cx, cy, x, y): self.els.append((2, (cx, cy, x, y, 0, 0))); return self
+    def curve_to(self, c1x, c1y, c2x, c2y, x, y): self.els.append((3, (c1x, c1y, c2x, c2y, x, y))); return self
+    def close_path(self): self.els.append((4, (0, 0, 0, 0, 0, 0))); return self
+
+    def array(self):
+        a = np.zeros(len(self.els), PATH_EL_DTYPE)
+        for i, (v, x) in enumerate(self.els):
+            a[i]["verb"] = v
+            a[i]["x"] = x
+        return a
+
+
+class RenderContext:
+    """The piet RenderContext calls over a PietRenderer: clear, transform, save / restore, fill, fill_even_odd, stroke
+    (solid colours 0xRRGGBBAA), finish -- which installs the drawing as the renderer's scene, flattened and encoded on the
+    device.  Create the renderer with FLAG_FILL_RULES for fill_even_odd to be honoured."""
+
+    def __init__(self, renderer, width=None, height=None):
+        self.renderer = renderer
+        self._h = ctypes.c_void_p()
+        _check(_lib().pm_context_new(ctypes.byref(self._h), renderer._h if renderer is not None else None,
+                                     width or renderer.width, height or renderer.height), "pm_context_new")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib().pm_context_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @staticmethod
+    def solid_brush(rgba):
+        return rgba
+
+    def clear(self, rgba): _check(_lib().pm_context_clear(self._h, rgba), "clear")
+    def save(self): _check(_lib().pm_context_save(self._h), "save")
+    def restore(self): _check(_lib().pm_context_restore(self._h), "restore")
+
+    def transform(self, affine):
+        m = np.ascontiguousarray(affine, np.float64)
+        _check(_lib().pm_context_transform(self._h, _ptr(m)), "transform")
+
+    def fill(self, path, brush):
+        a = path.array()
+        _check(_lib().pm_context_fill(self._h, _ptr(a), a.size, brush), "fill")
+
+    def fill_even_odd(self, path, brush):
+        a = path.array()
+        _check(_lib().pm_context_fill_even_odd(self._h, _ptr(a), a.size, brush), "fill_even_odd")
+
+    def stroke(self, path, brush, width):
+        a = path.array()
+        _check(_lib().pm_context_stroke(self._h, _ptr(a), a.size, brush, width), "stroke")
+
+    def item_count(self):
+        return _lib().pm_context_item_count(self._h)
+
+    def path_set(self):
+        """The recorded drawing as numpy arrays (copies): first, start, verb, ctrl, tag, rgba, width, flags."""
+        c = PathSetC()
+        _check(_lib().pm_context_path_set(self._h, ctypes.byref(c)), "path_set")
+        ns, ng = c.n_subpaths, c.n_segments
+
+        def arr(ptr, dtype, n):
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(n,)).copy() if n else np.zeros(0, dtype)
+        return {"first": arr(c.first_segment, np.uint32, ns + 1), "start": arr(c.start, np.float64, 2 * ns).reshape(-1, 2),
+                "verb": arr(c.verb, np.uint8, ng), "ctrl": arr(c.ctrl, np.float64, 6 * ng).reshape(-1, 6), "tag": arr(c.tag, np.uint32, ns),
+                "rgba": arr(c.rgba, np.uint32, ns), "width": arr(c.width, np.float32, ns), "flags": arr(c.flags, np.uint32, ns)}
+
+    def finish(self, tolerance=0.1):
+        _check(_lib().pm_context_finish(self._h, tolerance), "finish")
 
 
 class PietRendererGroup:
