@@ -38,6 +38,9 @@ namespace {
 typedef unsigned long long u64;
 
 #define PM_HEAVY_WARPS 8
+#ifndef PM_HEAVY_GRID_PER_SM
+#define PM_HEAVY_GRID_PER_SM 1   // CTAs launched per SM.  One CTA of 8 warps at 64 registers leaves three of k_fine's four CTA slots free
+#endif                           // (measured on the 8192^2 tiger, frame: 2 per SM at 80 registers 160.9 us, 1 per SM at 64 registers 152.5 us)
 #define PM_HEAVY_THREADS (PM_HEAVY_WARPS * 32)
 #define PM_HEAVY_SORT_CAP 4096u
 #define PM_HEAVY_DIR_CAP 128u     // overflow blocks indexed per tile (CTA mode): 1488 + 123 * 768 slots ~ 96 k records; the rest is not drawn
@@ -301,8 +304,11 @@ __device__ void heavy_tile_cta(const PmFrameArgs &A, HeavySmem *sh, uint32_t ent
     __syncthreads();
 }
 
+#ifndef PM_HEAVY_CTAS
+#define PM_HEAVY_CTAS 4   // resident CTAs per SM the kernel is compiled for (4: 64 registers, a few spills; 3: 80 registers)
+#endif
 template <bool F32, bool EXACT>
-__global__ void __launch_bounds__(PM_HEAVY_THREADS) k_heavy(const PmFrameArgs A) {
+__global__ void __launch_bounds__(PM_HEAVY_THREADS, PM_HEAVY_CTAS) k_heavy(const PmFrameArgs A) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     HeavySmem *sh = reinterpret_cast<HeavySmem *>(s_raw);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -315,7 +321,7 @@ __global__ void __launch_bounds__(PM_HEAVY_THREADS) k_heavy(const PmFrameArgs A)
     const uint32_t *list = A.complex_list + (size_t)A.n_rows * A.n_tx;
     __syncthreads();
     uint32_t n_min_cta = 0;
-    if (pm_heavy_warp_mode(n_heavy, gridDim.x)) {
+    if (pm_heavy_warp_mode(n_heavy, gridDim.x, A.counters->n_complex)) {
         // many heavy tiles: a warp each (up to PM_HEAVY_WARP_CAP records); what is left is drawn CTA-wise below
         HeavyWarpState *ws = &sh->ws[warp];
         for (;;) {
@@ -368,9 +374,9 @@ static cudaError_t heavy_launch(const PmFrameArgs &a, int grid, bool overlap, cu
 }
 
 cudaError_t pm_launch_heavy(const PmFrameArgs &a, int sm_count, bool overlap, cudaStream_t s) {
-    // Persistent: the number of heavy tiles is only known on the device; CTAs without work leave at once.  Two CTAs of
-    // eight warps per SM: half of the SM's registers stay free for k_fine's CTAs, which run beside this kernel.
-    const int grid = sm_count * 2;
+    // Persistent: the number of heavy tiles is only known on the device; CTAs without work leave at once.  One CTA of
+    // eight warps per SM: three quarters of the SM's registers stay free for k_fine's CTAs, which run beside this kernel.
+    const int grid = sm_count * PM_HEAVY_GRID_PER_SM;
     const bool exact = (a.flags & PM_FLAG_EXACT_SRGB) != 0;
     if (a.fb32) return exact ? heavy_launch<true, true>(a, grid, overlap, s) : heavy_launch<true, false>(a, grid, overlap, s);
     return exact ? heavy_launch<false, true>(a, grid, overlap, s) : heavy_launch<false, false>(a, grid, overlap, s);

@@ -18,8 +18,14 @@
 #define PM_HEAVY_WARP_CAP 128u    // warp mode: tiles up to this many records (4 chunks of 32); needs 2 overflow blocks at most
 #define PM_HEAVY_WARP_DIR 4u      // overflow blocks a warp indexes
 
-// Warp mode when there are more heavy tiles than a CTA each could take in about the time a warp needs for one.
-__device__ __forceinline__ bool pm_heavy_warp_mode(uint32_t n_heavy, uint32_t n_ctas) { return n_heavy > 6u * n_ctas; }
+// Warp mode when there are more heavy tiles than a CTA each could take in about the time a warp needs for one -- or when
+// the frame has so many tiles with records that the fill/blend kernel runs longer than a warp needs for a heavy tile anyway.
+#ifndef PM_HEAVY_WARP_MODE_COMPLEX
+#define PM_HEAVY_WARP_MODE_COMPLEX 32768u   // (the 8192^2 tiger, 49 k tiles with records, 619 of them heavy: frame 158 -> 152 us)
+#endif
+__device__ __forceinline__ bool pm_heavy_warp_mode(uint32_t n_heavy, uint32_t n_ctas, uint32_t n_complex) {
+    return n_heavy > 6u * n_ctas || n_complex > PM_HEAVY_WARP_MODE_COMPLEX;
+}
 
 __device__ __forceinline__ PmRecord pm_load_record(const PmRecord *pool, uint32_t idx) {
     const uint4 *src = reinterpret_cast<const uint4 *>(&pool[idx]);
