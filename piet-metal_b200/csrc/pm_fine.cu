@@ -44,9 +44,14 @@ typedef unsigned long long u64;
 #ifndef PM_FINE_CTAS
 #define PM_FINE_CTAS 4
 #endif
-#ifndef PM_FINE_PEND
-#define PM_FINE_PEND 0           // 1: the claim of tile i+3 is in flight while tile i is rendered (measured: +6 us, the
-                                 //    register that waits for the atomic does not survive the tile untouched); 0: claimed when needed
+#ifndef PM_FINE_CHUNK
+#define PM_FINE_CHUNK 4u         // positions per ticket in the bulk of the list of light tiles (fine_next)
+#endif
+#ifndef PM_FINE_CHUNK_TAIL
+#define PM_FINE_CHUNK_TAIL 5u    // the last 1/5 of that list is handed out in twos and ones
+#endif
+#ifndef PM_FINE_MAGIC_ROUND
+#define PM_FINE_MAGIC_ROUND 1    // sRGB bytes rounded with an FADD2 (magic number) instead of cvt.rni.sat.u8 on the XU pipe
 #endif
 #ifndef PM_FINE_SOLID_EVERY
 #define PM_FINE_SOLID_EVERY 4    // one warp in this many prefers the solid batches, the rest the tiles with records
@@ -98,6 +103,11 @@ __device__ __forceinline__ void srgb_bytes4(const float4 v, uint32_t out[4]) {
         out[0] = pm_srgb_byte<true>(v.x); out[1] = pm_srgb_byte<true>(v.y); out[2] = pm_srgb_byte<true>(v.z); out[3] = pm_srgb_byte<true>(v.w);
         return;
     }
+#if PM_FINE_PROBE_NOENC  // (performance probe, wrong pixels: the encode without its six MUFU per pixel)
+    out[0] = __float_as_uint(v.x * 255.0f + 12582912.0f); out[1] = __float_as_uint(v.y * 255.0f + 12582912.0f);
+    out[2] = __float_as_uint(v.z * 255.0f + 12582912.0f); out[3] = __float_as_uint(v.w * 255.0f + 12582912.0f);
+    return;
+#endif
     float l0, l1, l2, l3;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(v.x));
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(v.y));
@@ -119,10 +129,33 @@ __device__ __forceinline__ void srgb_bytes4(const float4 v, uint32_t out[4]) {
     upk2(s01, s0, s1); upk2(s23, s2, s3);
     upk2(n01, n0, n1); upk2(n23, n2, n3);
     const float r0 = v.x < 0.0031308f ? n0 : s0, r1 = v.y < 0.0031308f ? n1 : s1, r2 = v.z < 0.0031308f ? n2 : s2, r3 = v.w < 0.0031308f ? n3 : s3;
+#if PM_FINE_MAGIC_ROUND
+    // round to nearest even by adding 1.5 * 2^23: the byte is the low byte of the sum's bit pattern.  The value is
+    // within [-0.5, 255.5) (a blend of colours in [0, 1] with weights in [0, 1] stays there up to an ulp), so no clamp;
+    // an FADD2 on the FMA pipe instead of four conversions on the XU pipe, which is the busiest unit of this kernel.
+    const u64 mg = pk2(12582912.0f, 12582912.0f);
+    u64 q01, q23;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(q01) : "l"(pk2(r0, r1)), "l"(mg));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(q23) : "l"(pk2(r2, r3)), "l"(mg));
+    float f0, f1, f2, f3;
+    upk2(q01, f0, f1);
+    upk2(q23, f2, f3);
+    out[0] = __float_as_uint(f0); out[1] = __float_as_uint(f1); out[2] = __float_as_uint(f2); out[3] = __float_as_uint(f3);  // low byte valid
+#else
     asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(out[0]) : "f"(r0));
     asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(out[1]) : "f"(r1));
     asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(out[2]) : "f"(r2));
     asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(out[3]) : "f"(r3));
+#endif
+}
+
+// pixel = bytes r | g << 8 | b << 16 | 0xff << 24 from the (low bytes of the) three channel words
+__device__ __forceinline__ uint32_t pack_rgb(uint32_t r, uint32_t g, uint32_t b) {
+#if PM_FINE_MAGIC_ROUND
+    return __byte_perm(__byte_perm(r, g, 0x0040), b | 0xff00u, 0x5410);  // (b's word is 0x4b4000bb: byte 1 is zero)
+#else
+    return r | (g << 8) | (b << 16) | 0xff000000u;
+#endif
 }
 
 // Cmd_Circle coverage of four consecutive pixels (out of line: rare)
@@ -225,6 +258,7 @@ __device__ __forceinline__ void fine_tile(const PmFrameArgs &A, FineWarpSmem *w,
         const bool stroke = t_kind == PM_REC_STROKE, fill = pm_rec_is_drawfill(t_kind), even_odd = t_kind == PM_REC_DRAWFILL_EO;
         const float half_width = pm_u2f(t_w0);
         int run = 0;  // fill: cover entering this lane's pixels from the left
+        const int bd_fx = pm_clamp_i((int)t_w0, -64, 64) << PM_FX_SHIFT;  // the backdrop term of pm_resolve_fill_alpha, once per item
         if (fill || stroke) {
             if (m_geo) {  // coverage of the item's segments
                 const uint4 ga = my_rec[0], gb = my_rec[1];
@@ -261,11 +295,18 @@ __device__ __forceinline__ void fine_tile(const PmFrameArgs &A, FineWarpSmem *w,
                     int4 *pc = reinterpret_cast<int4 *>(&w->cov[g ? my_off1 : my_off0]);
                     const int4 c = *pc;
                     *pc = make_int4(0, 0, 0, 0);
-                    const int backdrop = (int)t_w0;
-                    run += c.x; al[0] = pm_resolve_fill(a.x + run, backdrop, even_odd);
-                    run += c.y; al[1] = pm_resolve_fill(a.y + run, backdrop, even_odd);
-                    run += c.z; al[2] = pm_resolve_fill(a.z + run, backdrop, even_odd);
-                    run += c.w; al[3] = pm_resolve_fill(a.w + run, backdrop, even_odd);
+                    if (!even_odd) {  // (warp-uniform branch: the two rules must not both be evaluated)
+                        run += c.x; al[0] = pm_resolve_fill_nz(a.x + run, bd_fx);
+                        run += c.y; al[1] = pm_resolve_fill_nz(a.y + run, bd_fx);
+                        run += c.z; al[2] = pm_resolve_fill_nz(a.z + run, bd_fx);
+                        run += c.w; al[3] = pm_resolve_fill_nz(a.w + run, bd_fx);
+                    } else {
+                        const int backdrop = (int)t_w0;
+                        run += c.x; al[0] = pm_resolve_fill_alpha_eo(a.x + run, backdrop);
+                        run += c.y; al[1] = pm_resolve_fill_alpha_eo(a.y + run, backdrop);
+                        run += c.z; al[2] = pm_resolve_fill_alpha_eo(a.z + run, backdrop);
+                        run += c.w; al[3] = pm_resolve_fill_alpha_eo(a.w + run, backdrop);
+                    }
                 } else {  // renderDf, metal:58-60
                     const float lim = half_width + 0.5f;
                     al[0] = a.x ? pm_saturate(lim - __uint_as_float(~(uint32_t)a.x)) : 0.0f;
@@ -299,8 +340,7 @@ __device__ __forceinline__ void fine_tile(const PmFrameArgs &A, FineWarpSmem *w,
         srgb_bytes4<EXACT>(r, rb);
         srgb_bytes4<EXACT>(gg, gb);
         srgb_bytes4<EXACT>(bl, bb);
-        const uint4 px = make_uint4(rb[0] | (gb[0] << 8) | (bb[0] << 16) | 0xff000000u, rb[1] | (gb[1] << 8) | (bb[1] << 16) | 0xff000000u,
-                                    rb[2] | (gb[2] << 8) | (bb[2] << 16) | 0xff000000u, rb[3] | (gb[3] << 8) | (bb[3] << 16) | 0xff000000u);
+        const uint4 px = make_uint4(pack_rgb(rb[0], gb[0], bb[0]), pack_rgb(rb[1], gb[1], bb[1]), pack_rgb(rb[2], gb[2], bb[2]), pack_rgb(rb[3], gb[3], bb[3]));
         __stcs(reinterpret_cast<uint4 *>(dst) + g, px);
         if (F32) {  // debug render: the un-quantised values
             dst32[4 * g + 0] = make_float4(pm_linear_to_srgb<EXACT>(r.x), pm_linear_to_srgb<EXACT>(gg.x), pm_linear_to_srgb<EXACT>(bl.x), 1.0f);
@@ -364,12 +404,31 @@ __device__ __forceinline__ void fine_solid_batch(const PmFrameArgs &A, uint32_t 
 struct FineList {
     const uint32_t *medium, *full;
     uint32_t n_medium, n_total;
+    uint32_t n4, n2;  // tickets that stand for 4 / 2 consecutive positions (see fine_next)
 };
 // (atom.inc with a bound that is never reached, not atom.add: see the header)
 __device__ __forceinline__ uint32_t fine_claim(const PmFrameArgs &A, uint32_t lane) {
     uint32_t c = 0;
     if (lane == 0) asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(c) : "l"(&A.queue->tile_next) : "memory");
     return c;
+}
+// Positions are handed out by TICKET, and a ticket stands for a run of consecutive positions: one position each
+// for the medium tiles at the head of the list (the long jobs), then PM_FINE_CHUNK positions per ticket for most of
+// the light tiles, then 2, then 1 again for the tail (guided self-scheduling: the kernel still ends evenly, and the
+// counter sees a quarter of the atomics -- with one atomic per tile ~4,000 warps queue on one L2 address and a
+// claim took microseconds: a fifth of all warp stall samples in the round-2 profile).
+struct FineRun { uint32_t pos, end; };
+__device__ __forceinline__ uint32_t fine_next(const PmFrameArgs &A, const FineList &L, FineRun &r, uint32_t lane) {
+    if (r.pos < r.end) return r.pos++;
+    uint32_t t = __shfl_sync(PM_FULL_MASK, fine_claim(A, lane), 0), start, len = 1;
+    if (t < L.n_medium) start = t;
+    else if ((t -= L.n_medium) < L.n4) { start = L.n_medium + PM_FINE_CHUNK * t; len = PM_FINE_CHUNK; }
+    else if ((t -= L.n4) < L.n2) { start = L.n_medium + PM_FINE_CHUNK * L.n4 + 2u * t; len = 2; }
+    else start = L.n_medium + PM_FINE_CHUNK * L.n4 + 2u * L.n2 + (t - L.n2);
+    if (start > L.n_total) start = L.n_total;  // (also keeps the sums below from wrapping after many empty claims)
+    r.pos = start + 1u;
+    r.end = start + len < L.n_total ? start + len : L.n_total;
+    return start;
 }
 __device__ __forceinline__ void fine_fetch_entry(const FineList &L, FineWarpSmem *w, uint32_t b, uint32_t pos, uint32_t lane) {
     if (lane == 0) {
@@ -404,6 +463,8 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
     L.full = A.complex_list;
     L.n_medium = n_medium;
     L.n_total = n_medium + n_complex;
+    L.n4 = (n_complex - n_complex / PM_FINE_CHUNK_TAIL) / PM_FINE_CHUNK;                 // all but the last 1/PM_FINE_CHUNK_TAIL of the full list
+    L.n2 = (n_complex - PM_FINE_CHUNK * L.n4) / 4u;                                       // half of what is left
     __syncwarp();
     const uint32_t batches_per_row = (A.n_tx + 31u) / 32u;
     const uint32_t n_batches = batches_per_row * A.n_rows;
@@ -412,22 +473,19 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
         if (complex_left && (prefer_complex || !batches_left)) {
             complex_left = false;
             // fill the pipeline
-            uint32_t p = __shfl_sync(PM_FULL_MASK, fine_claim(A, lane), 0);
+            FineRun run{0u, 0u};
+            uint32_t p = fine_next(A, L, run, lane);
             if (p >= L.n_total) continue;
             fine_fetch_entry(L, w, 0, p, lane);
             uint32_t ph = p >= L.n_medium ? 1u : 0u;  // bit k: tile i + k of the pipeline comes from the full list
-            uint32_t pend = fine_claim(A, lane);
+            p = fine_next(A, L, run, lane);
             cp_async_wait<0>();
             __syncwarp();
             fine_prefetch(A, w, 0, w->ent[0], lane);
-            p = __shfl_sync(PM_FULL_MASK, pend, 0);
             bool v_next = p < L.n_total;
             if (v_next) {
                 fine_fetch_entry(L, w, 1, p, lane);
                 ph |= p >= L.n_medium ? 2u : 0u;
-#if PM_FINE_PEND
-                pend = fine_claim(A, lane);
-#endif
             }
             uint32_t b = 0;
             for (;;) {
@@ -437,18 +495,12 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
                 bool v_nn = false;
                 if (v_next) {
                     fine_prefetch(A, w, b ^ 1u, w->ent[b ^ 1u], lane);
-#if PM_FINE_PEND
-                    p = __shfl_sync(PM_FULL_MASK, pend, 0);  // claimed while the previous tile was rendered
-#else
-                    p = __shfl_sync(PM_FULL_MASK, fine_claim(A, lane), 0);
-#endif
+                    __syncwarp();  // (every lane has read ent[b] before it is overwritten)
+                    p = fine_next(A, L, run, lane);
                     v_nn = p < L.n_total;
                     if (v_nn) {
-                        fine_fetch_entry(L, w, b, p, lane);  // (every lane has read ent[b]: the shuffle above synchronises)
+                        fine_fetch_entry(L, w, b, p, lane);
                         ph |= p >= L.n_medium ? 4u : 0u;
-#if PM_FINE_PEND
-                        pend = fine_claim(A, lane);
-#endif
                     }
                 }
                 fine_tile<F32, EXACT>(A, w, b, entry, (ph & 1u) != 0, lane);

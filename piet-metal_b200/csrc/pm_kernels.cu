@@ -162,15 +162,21 @@ __global__ void __launch_bounds__(1024) k_plan(const uint8_t *scene, uint32_t n_
             {
                 const ItemSpan spi = item_span(scene, items_ix, i, tile_y0, tile_y1, n_tx);
                 PmItemInfo ii;
-                ii.t_lo = spi.t_lo; ii.t_hi = spi.t_hi; ii.r_lo = spi.r_lo; ii.rows = spi.rows; ii.bd_base = eb; ii.pad[0] = ii.pad[1] = 0;
-                item_info[i] = ii;
+                ii.t_lo = spi.t_lo; ii.t_hi = spi.t_hi; ii.r_lo = spi.r_lo; ii.rows = spi.rows; ii.bd_base = (uint32_t)eb;
+                ii.rgba = 0; ii.tag_flags = spi.tag; ii.w0 = 0;
                 // the item's colour as the fill kernels blend it: unpack_unorm4x8_srgb_to_half (metal:503, :541, :548)
                 // through the look-up table; Cmd_Circle paints opaque black (metal:491)
                 float4 paint = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
                 if (spi.tag == PM_ITEM_LINE || spi.tag == PM_ITEM_FILL || spi.tag == PM_ITEM_POLY) {
-                    const uint32_t rgba = ld_u32(scene + items_ix + (size_t)i * PM_ITEM_SIZE + (spi.tag == PM_ITEM_POLY ? PM_POLY_RGBA : PM_FILL_RGBA));
+                    const uint8_t *it = scene + items_ix + (size_t)i * PM_ITEM_SIZE;
+                    const uint32_t rgba = ld_u32(it + (spi.tag == PM_ITEM_POLY ? PM_POLY_RGBA : PM_FILL_RGBA));
                     paint = make_float4(srgb_lut[rgba & 0xffu], srgb_lut[(rgba >> 8) & 0xffu], srgb_lut[(rgba >> 16) & 0xffu], srgb_lut[256u + (rgba >> 24)]);
+                    ii.rgba = rgba;
+                    if (spi.tag == PM_ITEM_FILL && (ld_u32(it + PM_FILL_FLAGS) & PM_FILL_EVEN_ODD) != 0) ii.tag_flags |= PM_INFO_EVEN_ODD;
+                    if (spi.tag == PM_ITEM_POLY) ii.w0 = pm_f2u(0.5f * ld_f32(it + PM_POLY_WIDTH));
+                    if (spi.tag == PM_ITEM_LINE) ii.w0 = pm_f2u(0.5f * ld_f32(it + PM_LINE_WIDTH));
                 }
+                item_info[i] = ii;
                 item_paint[i] = paint;
             }
             // second pass (row_info given): tabulate the item's (tile row, 32-tile chunk) units for k_row
@@ -258,8 +264,8 @@ __device__ __forceinline__ SegCtx segment_of(const uint8_t *scene, uint32_t n_it
 }
 
 __global__ void __launch_bounds__(256) k_pieces_count(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0,
-                                                      uint32_t tile_y1, uint32_t n_tx, const u64 *plan_a, uint32_t n_segments,
-                                                      PmSegInfo *seg_info, uint32_t *piece_cnt) {
+                                                      uint32_t tile_y1, uint32_t n_tx, const u64 *plan_a, const u64 *plan_b,
+                                                      uint32_t n_segments, PmSegInfo *seg_info, uint32_t *piece_cnt) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_segments) return;
     uint32_t item;
@@ -267,6 +273,7 @@ __global__ void __launch_bounds__(256) k_pieces_count(const uint8_t *scene, uint
     PmSegInfo si;
     si.sx = c.sg.sx; si.sy = c.sg.sy; si.ex = c.sg.ex; si.ey = c.sg.ey;
     si.item = item; si.k = g - (uint32_t)plan_a[item]; si.hw = c.hw; si.tag = c.sp.tag;
+    si.t_lo = c.sp.t_lo; si.t_hi = c.sp.t_hi; si.r_lo = c.sp.r_lo; si.bd_base = (uint32_t)plan_b[item];
     seg_info[g] = si;
     u64 cnt = 0;
     for (int r = c.ra; r <= c.rb; r++) {
@@ -467,12 +474,10 @@ __global__ void __launch_bounds__(256, PM_SEG_CTAS) k_seg(const PmFrameArgs A) {
     if (q >= A.n_pieces) return;
     const uint2 pi = A.piece_info[q];
     const uint4 *sp4 = reinterpret_cast<const uint4 *>(&A.seg_info[pi.x]);
-    const uint4 s0 = sp4[0], s1 = sp4[1];  // sx sy ex ey | item k hw tag
-    const uint4 *ip4 = reinterpret_cast<const uint4 *>(&A.item_info[s1.x]);
-    const uint4 i0 = ip4[0], i1 = ip4[1];  // t_lo t_hi r_lo rows | bd_base
+    const uint4 s0 = sp4[0], s1 = sp4[1], s2 = sp4[2];  // sx sy ex ey | item k hw tag | t_lo t_hi r_lo bd_base
     const PmSeg sg = pm_seg(pm_u2f(s0.x), pm_u2f(s0.y), pm_u2f(s0.z), pm_u2f(s0.w));
-    const uint32_t item = s1.x, k = s1.y, t_lo = i0.x, t_hi = i0.y, r_lo = i0.z;
-    const u64 bd_base = ((u64)i1.y << 32) | i1.x;
+    const uint32_t item = s1.x, k = s1.y, t_lo = s2.x, t_hi = s2.y, r_lo = s2.z;
+    const u64 bd_base = s2.w;
     const uint32_t row = (pi.y >> 15) & 0x7fffu, t = pi.y & 0x7fffu;
     const float y0 = (float)(row * PM_TILE_H);
     BinSink sink{A, A.bd + bd_base + (size_t)(row - r_lo) * (t_hi - t_lo + 2u), t_lo, (row - A.tile_y0) * A.n_tx, item};
@@ -497,20 +502,21 @@ __global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) 
     if (unit >= A.n_row_units) return;
     const uint2 ri = A.row_info[unit];  // (item, tile row << 16 | chunk), tabulated by k_plan
     const uint32_t item = ri.x;
-    const ItemSpan sp = item_span(A.scene, A.items_ix, item, A.tile_y0, A.tile_y0 + A.n_rows, A.n_tx);
+    const uint4 *ip4 = reinterpret_cast<const uint4 *>(&A.item_info[item]);
+    const uint4 i0 = ip4[0], i1 = ip4[1];  // t_lo t_hi r_lo rows | bd_base rgba tag_flags w0  (k_plan)
+    const uint32_t tag = i1.z & 0xffu, rgba = i1.y;
     const uint8_t *it = A.scene + A.items_ix + (size_t)item * PM_ITEM_SIZE;
-    const uint32_t span = sp.t_hi - sp.t_lo + 1;
+    const uint32_t span = i0.y - i0.x + 1;
     const uint32_t row = ri.y >> 16, j0 = (ri.y & 0xffffu) * 32u;
-    const uint32_t t_lo = sp.t_lo;
+    const uint32_t t_lo = i0.x;
     const float y0 = (float)(row * PM_TILE_H);
-    const uint32_t *bd = A.bd + A.plan_b[item] + (size_t)(row - sp.r_lo) * (span + 1);
+    const uint32_t *bd = A.bd + i1.x + (size_t)(row - i0.z) * (span + 1);
     BinSink sink{A, nullptr, t_lo, (row - A.tile_y0) * A.n_tx, item};
     const uint32_t j = j0 + lane;
 
-    if (sp.tag == PM_ITEM_FILL) {
-        const uint32_t rgba = ld_u32(it + PM_FILL_RGBA);
+    if (tag == PM_ITEM_FILL) {
         // PM_FLAG_FILL_RULES: the item's flags word may ask for the even-odd rule (extension; the reference ignores it)
-        const bool even_odd = (A.flags & PM_FLAG_FILL_RULES) != 0 && (ld_u32(it + PM_FILL_FLAGS) & PM_FILL_EVEN_ODD) != 0;
+        const bool even_odd = (A.flags & PM_FLAG_FILL_RULES) != 0 && (i1.z & PM_INFO_EVEN_ODD) != 0;
         // backdrop entering this chunk: sum of the deltas of the tiles before it
         int carry = 0;
         for (uint32_t q = lane; q < j0; q += 32) carry += (int)bd[q] >> 1;
@@ -534,11 +540,9 @@ __global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) 
                 }
             }
         }
-    } else if (sp.tag == PM_ITEM_POLY) {
-        if (j < span && (bd[j] & 1u))
-            sink.trailer(t_lo + j, PM_REC_STROKE, PM_REC_SEG_MAX, pm_f2u(0.5f * ld_f32(it + PM_POLY_WIDTH)), ld_u32(it + PM_POLY_RGBA));
-    } else if (sp.tag == PM_ITEM_LINE) {  // metal:223-247
-        const uint32_t rgba = ld_u32(it + PM_LINE_RGBA);
+    } else if (tag == PM_ITEM_POLY) {
+        if (j < span && (bd[j] & 1u)) sink.trailer(t_lo + j, PM_REC_STROKE, PM_REC_SEG_MAX, i1.w, rgba);
+    } else if (tag == PM_ITEM_LINE) {  // metal:223-247
         const float width = ld_f32(it + PM_LINE_WIDTH);
         const float2 s = ld_f2(it + PM_LINE_START), e = ld_f2(it + PM_LINE_END);
         const PmSeg g = pm_seg(s.x, s.y, e.x, e.y);
@@ -551,7 +555,7 @@ __global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) 
                 sink.trailer(t, PM_REC_STROKE, PM_REC_SEG_MAX, pm_f2u(0.5f * width), rgba);
             }
         }
-    } else if (sp.tag == PM_ITEM_CIRCLE) {  // metal:218-222
+    } else if (tag == PM_ITEM_CIRCLE) {  // metal:218-222
         const pm_bbox bb = *reinterpret_cast<const pm_bbox *>(A.scene + PM_GROUP_HEADER_SIZE + (size_t)item * PM_BBOX_SIZE);
         const uint32_t b_lo = (uint32_t)bb.x0 | ((uint32_t)bb.y0 << 16), b_hi = (uint32_t)bb.x1 | ((uint32_t)bb.y1 << 16);
         if (j < span) sink.trailer(t_lo + j, PM_REC_CIRCLE, 0, b_lo, b_hi);
@@ -575,9 +579,9 @@ void pm_launch_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, u
 }
 
 void pm_launch_pieces_count(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
-                            const unsigned long long *plan_a, uint32_t n_segments, PmSegInfo *seg_info, uint32_t *piece_cnt,
-                            PmPlanResult *result, cudaStream_t s) {
-    if (n_segments) k_pieces_count<<<(n_segments + 255) / 256, 256, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, n_segments, seg_info, piece_cnt);
+                            const unsigned long long *plan_a, const unsigned long long *plan_b, uint32_t n_segments, PmSegInfo *seg_info,
+                            uint32_t *piece_cnt, PmPlanResult *result, cudaStream_t s) {
+    if (n_segments) k_pieces_count<<<(n_segments + 255) / 256, 256, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, plan_b, n_segments, seg_info, piece_cnt);
     k_pieces_scan<<<1, 1024, 0, s>>>(piece_cnt, n_segments, result);
 }
 

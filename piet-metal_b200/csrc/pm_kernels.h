@@ -51,8 +51,15 @@ struct PmFrameReport {
 
 // Plan-time copies of what k_seg needs about a segment / an item, laid out for two 16-byte loads each
 // (the scene's own layout would cost five dependent loads per thread, and k_seg is latency bound).
-struct alignas(16) PmSegInfo { float sx, sy, ex, ey; uint32_t item, k; float hw; uint32_t tag; };
-struct alignas(16) PmItemInfo { uint32_t t_lo, t_hi, r_lo, rows; unsigned long long bd_base; uint32_t pad[2]; };
+struct alignas(16) PmSegInfo {
+    float sx, sy, ex, ey; uint32_t item, k; float hw; uint32_t tag;
+    uint32_t t_lo, t_hi, r_lo, bd_base;  // copied from the segment's item (PmItemInfo): one dependent load less in k_seg
+};
+// PmItemInfo: everything k_seg and k_row need about an item in two 16-byte loads -- tile span of its bbox inside the
+// strip, first word of its backdrop scratch (below 2^31, checked by the plan), its colour (rgba8 as encoded), its tag
+// with the even-odd bit (bit 8), and w0 = the bits of half its stroke width (Poly / Line).
+struct alignas(16) PmItemInfo { uint32_t t_lo, t_hi, r_lo, rows; uint32_t bd_base, rgba, tag_flags, w0; };
+#define PM_INFO_EVEN_ODD 0x100u
 
 struct PmFrameArgs {
     const uint8_t *scene;       // encoded scene in device memory
@@ -122,8 +129,8 @@ void pm_launch_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, u
                     uint32_t row_info_cap, const float *srgb_lut, float4 *item_paint, PmPlanResult *result, cudaStream_t s);
 // The k_seg work list: count + prefix (result->n_pieces, piece_cnt becomes the per-segment offset), then fill.
 void pm_launch_pieces_count(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
-                            const unsigned long long *plan_a, uint32_t n_segments, PmSegInfo *seg_info, uint32_t *piece_cnt,
-                            PmPlanResult *result, cudaStream_t s);
+                            const unsigned long long *plan_a, const unsigned long long *plan_b, uint32_t n_segments, PmSegInfo *seg_info,
+                            uint32_t *piece_cnt, PmPlanResult *result, cudaStream_t s);
 void pm_launch_pieces_fill(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
                            const unsigned long long *plan_a, uint32_t n_segments, const uint32_t *piece_off, uint2 *piece_info,
                            uint32_t piece_cap, cudaStream_t s);

@@ -199,7 +199,7 @@ int run_plan(pm_renderer *r) {
         r->seg_cap = (size_t)res.n_segments + 1;
     }
     // the k_seg pieces: count and prefix, then (once the table is large enough) fill
-    pm_launch_pieces_count(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, res.n_segments,
+    pm_launch_pieces_count(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, r->plan_b, res.n_segments,
                            r->seg_info, r->piece_off, r->dev_plan, r->stream);
     PM_CUDA(cudaGetLastError());
     PM_CUDA(cudaMemcpyAsync(&res, r->dev_plan, sizeof res, cudaMemcpyDeviceToHost, r->stream));

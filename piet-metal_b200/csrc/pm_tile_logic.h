@@ -32,7 +32,12 @@ struct PmSeg {
     float a, b, c;             // a*x + b*y + c = 0 (metal:267-269)
 };
 
-PM_HD float pm_sign(float x) { return (float)((x > 0.0f) - (x < 0.0f)); }  // MSL sign(): sign(0) = 0
+PM_HD float pm_sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }  // MSL sign(): sign(0) = 0 (and sign(NaN) = 0 here)
+// sign(u) == sign(v) without materialising the signs (two compares per side; in the bisection loops one side is invariant)
+PM_HD bool pm_same_sign(float u, float v) {
+    const bool up = u > 0.0f, un = u < 0.0f, vp = v > 0.0f, vn = v < 0.0f;
+    return (up && vp) || (un && vn) || (!up && !un && !vp && !vn);
+}
 
 PM_HD PmSeg pm_seg(float sx, float sy, float ex, float ey) {
     PmSeg g;
@@ -47,6 +52,14 @@ PM_HD PmSeg pm_seg(float sx, float sy, float ex, float ey) {
 
 // "If all four corners are on same side of line, cull" (metal:237-241 and every copy of it).
 PM_HD bool pm_cross4(float s00, float s01, float s10, float s11) { return s00 * s01 + s00 * s10 + s00 * s11 < 3.0f; }
+// The same test on the four corner VALUES (v = a*x + b*y + c) instead of their signs: the products of signs sum to 3
+// exactly when the four signs are equal and not zero, i.e. when the values are all positive or all negative
+// (a NaN compares false both ways, like sign(NaN) = 0 above: "crosses").
+PM_HD bool pm_cross4v(float v00, float v01, float v10, float v11) {
+    const bool all_pos = v00 > 0.0f && v01 > 0.0f && v10 > 0.0f && v11 > 0.0f;
+    const bool all_neg = v00 < 0.0f && v01 < 0.0f && v10 < 0.0f && v11 < 0.0f;
+    return !(all_pos || all_neg);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Fill items (metal:248-365)
@@ -66,20 +79,16 @@ PM_HD bool pm_fill_strip_vote(const PmSeg &g, float y0, float sx0) {
     float ybot = fminf(y0 + 16.0f, g.mxy);
     float top = g.b * ytop;
     float bot = g.b * ybot;
-    float s_top_left = pm_sign(right - g.a * 16.0f + y0 * g.b + g.c);  // top left of rightmost tile in strip
-    float s00 = pm_sign(top + left + g.c);
-    float s01 = pm_sign(top + right + g.c);
-    float s10 = pm_sign(bot + left + g.c);
-    float s11 = pm_sign(bot + right + g.c);
+    float v_top_left = right - g.a * 16.0f + y0 * g.b + g.c;  // top left of rightmost tile in strip
     bool fill_hit = false;
-    if (s_top_left == pm_sign(g.a) && g.mny <= y0) fill_hit = true;   // left ray intersects, need backdrop
-    if (pm_cross4(s00, s01, s10, s11) && g.mxx > sx0) fill_hit = true; // intersects strip
+    if (pm_same_sign(v_top_left, g.a) && g.mny <= y0) fill_hit = true;   // left ray intersects, need backdrop
+    if (pm_cross4v(top + left + g.c, top + right + g.c, bot + left + g.c, bot + right + g.c) && g.mxx > sx0) fill_hit = true; // intersects strip
     return fill_hit;
 }
 
 // sTopLeft == sign(a) for the tile whose left edge is x0 (metal:326, :331).
 PM_HD bool pm_fill_backdrop_side(const PmSeg &g, float x0, float y0) {
-    return pm_sign(g.a * x0 + y0 * g.b + g.c) == pm_sign(g.a);
+    return pm_same_sign(g.a * x0 + y0 * g.b + g.c, g.a);
 }
 
 // First tile index in [0, n_tiles_x] whose top-left corner is on the sign(a) side; n_tiles_x if
@@ -97,7 +106,7 @@ PM_HD uint32_t pm_fill_backdrop_first_tile(const PmSeg &g, float y0, uint32_t n_
 // sTopLeft, taken at the top-left corner of the strip's rightmost tile, is on the sign(a) side.
 PM_HD bool pm_fill_strip_side(const PmSeg &g, float y0, float sx0) {
     float right = g.a * (sx0 + 256.0f);
-    return pm_sign(right - g.a * 16.0f + y0 * g.b + g.c) == pm_sign(g.a);
+    return pm_same_sign(right - g.a * 16.0f + y0 * g.b + g.c, g.a);
 }
 // First strip index in [0, n_strips] for which pm_fill_strip_side holds (monotone in the strip
 // index for the same reason as the tile test).  Needs a != 0.
@@ -127,12 +136,9 @@ PM_HD PmFillEmit pm_fill_tile_test(const PmSeg &g, float x0, float y0) {
     float ybot = fminf(y0 + 16.0f, g.mxy);
     float top = g.b * ytop;
     float bot = g.b * ybot;
-    float s00 = pm_sign(top + left + g.c);
-    float s01 = pm_sign(top + right + g.c);
-    float s10 = pm_sign(bot + left + g.c);
-    float s11 = pm_sign(bot + right + g.c);
-    r.s00 = s00;
-    bool crosses = pm_cross4(s00, s01, s10, s11);
+    const float v00 = top + left + g.c;
+    r.s00 = pm_sign(v00);
+    bool crosses = pm_cross4v(v00, top + right + g.c, bot + left + g.c, bot + right + g.c);
     if (g.mnx < x0 && g.mxx > x0) {
         float y_edge = g.sy + (g.ey - g.sy) * ((g.sx - x0) / g.b);  // mix(start.y, end.y, (start.x - x0) / b)
         if (y_edge >= y0 && y_edge < y0 + 16.0f) {
@@ -269,11 +275,7 @@ PM_HD bool pm_stroke_cross(const PmSeg &g, float xl, float xr, float yt, float y
     float right = g.a * (xr + hw);
     float top = g.b * (yt - hw);
     float bot = g.b * (yb + hw);
-    float s00 = pm_sign(top + left + g.c);
-    float s01 = pm_sign(top + right + g.c);
-    float s10 = pm_sign(bot + left + g.c);
-    float s11 = pm_sign(bot + right + g.c);
-    return pm_cross4(s00, s01, s10, s11);
+    return pm_cross4v(top + left + g.c, top + right + g.c, bot + left + g.c, bot + right + g.c);
 }
 
 // Group-level pre-cull vote for segment seg_index (metal:375-398).  The corner test uses the y
