@@ -25,6 +25,7 @@
 // is compiled into a warp-aggregated atomic plus a shuffle that waits for it).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/piet_metal_b200.h"
 #include "pm_cover.cuh"
@@ -47,11 +48,14 @@ typedef unsigned long long u64;
 #ifndef PM_FINE_CHUNK
 #define PM_FINE_CHUNK 4u         // positions per ticket in the bulk of the list of light tiles (fine_next)
 #endif
-#ifndef PM_FINE_CHUNK_TAIL
-#define PM_FINE_CHUNK_TAIL 5u    // the last 1/5 of that list is handed out in twos and ones
+#ifndef PM_FINE_TAIL_PER_WARP
+#define PM_FINE_TAIL_PER_WARP 3u // tiles per warp at the end of the list that are handed out one by one (and as many in twos before them)
 #endif
 #ifndef PM_FINE_MAGIC_ROUND
 #define PM_FINE_MAGIC_ROUND 1    // sRGB bytes rounded with an FADD2 (magic number) instead of cvt.rni.sat.u8 on the XU pipe
+#endif
+#ifndef PM_FINE_CTA_TICKETS
+#define PM_FINE_CTA_TICKETS 1    // the first two tickets of every warp come from one atomic per CTA
 #endif
 #ifndef PM_FINE_SOLID_EVERY
 #define PM_FINE_SOLID_EVERY 4    // one warp in this many prefers the solid batches, the rest the tiles with records
@@ -66,7 +70,8 @@ struct FineWarpSmem {
                               // [2]: records 16..31 of a tile that has them (the start of its first overflow block)
     u64 hdr[2][2];            // the prefetched tiles' cnt / occ words
     uint32_t ent[2];          // list entry (packed tile row, column) of the tile that uses buffer b next
-    uint32_t pad[6];
+    u64 bar[2];               // PM_FINE_BULK: one mbarrier per prefetch buffer (unused otherwise)
+    uint32_t pad[2];
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -165,11 +170,39 @@ __device__ __noinline__ float4 fine_circle_alpha4(uint32_t bbox_lo, uint32_t bbo
 }
 
 // Starts the copy of a tile's cnt / occ words and inline record slots into buffer b (one commit group).
+// PM_FINE_BULK=1 (A/B variant, see profiles/README.md): the 512-byte record block comes as ONE TMA bulk copy
+// (cp.async.bulk -> UBLKCP) issued by lane 0 and completes on the buffer's mbarrier instead of 32 lanes' LDGSTS.
+#ifndef PM_FINE_BULK
+#define PM_FINE_BULK 0
+#endif
 __device__ __forceinline__ void fine_prefetch(const PmFrameArgs &A, FineWarpSmem *w, uint32_t b, uint32_t entry, uint32_t lane) {
     const size_t tile = (size_t)(entry >> 16) * A.n_tx + (entry & 0xffffu);
+#if PM_FINE_BULK
+    if (lane == 0) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&w->bar[b]), dst = (uint32_t)__cvta_generic_to_shared(&w->rec[b][0]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer was last read through the generic proxy
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 512;" ::"r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 512, [%2];"
+                     ::"r"(dst), "l"(&A.pool[tile * PM_TILE_SLOTS]), "r"(bar) : "memory");
+    }
+#else
     cp_async16(&w->rec[b][lane], reinterpret_cast<const uint4 *>(&A.pool[tile * PM_TILE_SLOTS]) + lane);
+#endif
     if (lane < 2) cp_async8(&w->hdr[b][lane], lane == 0 ? &A.cnt[tile] : &A.occ[tile]);
     cp_async_commit();
+}
+// PM_FINE_BULK: waits for the bulk copy into buffer b (phase bit `ph` of its mbarrier)
+__device__ __forceinline__ void fine_bulk_wait(FineWarpSmem *w, uint32_t b, uint32_t ph) {
+#if PM_FINE_BULK
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&w->bar[b]);
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(ph) : "memory");
+    } while (!done);
+#else
+    (void)w; (void)b; (void)ph;
+#endif
 }
 
 // Records 16..n-1 of a tile with 17..32 records: the first slots of its first overflow block (pm_pixel_logic.h), copied
@@ -239,20 +272,26 @@ __device__ __forceinline__ void fine_tile(const PmFrameArgs &A, FineWarpSmem *w,
     const int my_off0 = pm_cov_swz((int)prow, (int)half * 8), my_off1 = pm_cov_swz((int)prow, (int)half * 8 + 4);
     PmCoverAcc cacc{w->acc, w->cov};
 
-    // items in painter's order: repeatedly take the smallest item id not drawn yet
+    // items in painter's order: repeatedly take the smallest item id not drawn yet.  The tile's linear colour goes
+    // through shared memory only BETWEEN items: the first item blends over the base colour from registers and the
+    // last one hands its result straight to the sRGB encode, so a tile with one item never touches the colour planes
+    // (the L1 data pipe -- LDS / STS / shuffles -- is the busiest unit of this kernel after the issue slots).
+    uint32_t cur_item = __reduce_min_sync(PM_FULL_MASK, my_item);  // (has_draw: there is one)
     for (;;) {
-        const uint32_t cur_item = __reduce_min_sync(PM_FULL_MASK, my_item);
-        if (cur_item == 0xffffffffu) break;
         const bool of_item = my_item == cur_item;
         // the item's closing record says what it is (DrawFill / Stroke / Circle / Solid)
         const uint32_t m_tr = __ballot_sync(PM_FULL_MASK, of_item && my_kind >= PM_REC_CIRCLE);
         const bool mine = of_item && my_kind <= PM_REC_LINE;
         const uint32_t m_geo = __ballot_sync(PM_FULL_MASK, mine);
         if (of_item) my_item = 0xffffffffu;  // done
-        if (m_tr == 0) continue;             // cannot happen for a well-formed list
-        const uint32_t tr_lane = __ffs(m_tr) - 1;
-        const uint4 tr = w->rec[tr_lane < PM_TILE_SLOTS ? b : 2u][2 * (tr_lane & (PM_TILE_SLOTS - 1))];
-        const uint32_t t_kind = tr.y & 15u, t_w0 = tr.z, t_w1 = tr.w;
+        const uint32_t next_item = __reduce_min_sync(PM_FULL_MASK, my_item);
+        const bool last = next_item == 0xffffffffu;
+        uint32_t t_kind = 15u, t_w0 = 0, t_w1 = 0;  // no closing record (cannot happen for a well-formed list): draws nothing
+        if (m_tr) {
+            const uint32_t tr_lane = __ffs(m_tr) - 1;
+            const uint4 tr = w->rec[tr_lane < PM_TILE_SLOTS ? b : 2u][2 * (tr_lane & (PM_TILE_SLOTS - 1))];
+            t_kind = tr.y & 15u; t_w0 = tr.z; t_w1 = tr.w;
+        }
         float4 paint = make_float4(0.0f, 0.0f, 0.0f, 1.0f);  // Cmd_Circle paints black (metal:491)
         if (t_kind != PM_REC_CIRCLE) paint = __ldg(&A.item_paint[cur_item]);
         const bool stroke = t_kind == PM_REC_STROKE, fill = pm_rec_is_drawfill(t_kind), even_odd = t_kind == PM_REC_DRAWFILL_EO;
@@ -271,15 +310,6 @@ __device__ __forceinline__ void fine_tile(const PmFrameArgs &A, FineWarpSmem *w,
                 const int sum = ((c0.x + c0.y) + (c0.z + c0.w)) + ((c1.x + c1.y) + (c1.z + c1.w));
                 const int other = __shfl_xor_sync(PM_FULL_MASK, sum, 1);
                 run = half ? other : 0;
-            }
-        }
-        if (fresh) {
-            fresh = false;
-            #pragma unroll
-            for (int g = 0; g < 2; g++) {
-                w->rgb[0][g][lane] = make_float4(base.x, base.x, base.x, base.x);
-                w->rgb[1][g][lane] = make_float4(base.y, base.y, base.y, base.y);
-                w->rgb[2][g][lane] = make_float4(base.z, base.z, base.z, base.z);
             }
         }
         // resolve this lane's 8 pixels, clear their coverage for the next item, and blend (metal:505, :543, :549).
@@ -317,8 +347,8 @@ __device__ __forceinline__ void fine_tile(const PmFrameArgs &A, FineWarpSmem *w,
             } else if (t_kind == PM_REC_CIRCLE) {
                 const float4 ca = fine_circle_alpha4(t_w0, t_w1, tile_x0 + (float)(half * 8u + 4u * (uint32_t)g), tile_y0 + (float)prow);
                 al[0] = ca.x; al[1] = ca.y; al[2] = ca.z; al[3] = ca.w;
-            } else {  // PM_REC_SOLID: a translucent full cover
-                al[0] = al[1] = al[2] = al[3] = 1.0f;
+            } else {  // PM_REC_SOLID: a translucent full cover (15: nothing)
+                al[0] = al[1] = al[2] = al[3] = t_kind == PM_REC_SOLID ? 1.0f : 0.0f;
             }
             const u64 pa2 = pk2(paint.w, paint.w);
             const u64 al01 = mul2(pk2(al[0], al[1]), pa2), al23 = mul2(pk2(al[2], al[3]), pa2);
@@ -326,28 +356,36 @@ __device__ __forceinline__ void fine_tile(const PmFrameArgs &A, FineWarpSmem *w,
             upk2(al01, a0, a1);
             upk2(al23, a2, a3);
             const u64 nal01 = pk2(-a0, -a1), nal23 = pk2(-a2, -a3);
-            w->rgb[0][g][lane] = blend4(w->rgb[0][g][lane], paint.x, al01, al23, nal01, nal23);
-            w->rgb[1][g][lane] = blend4(w->rgb[1][g][lane], paint.y, al01, al23, nal01, nal23);
-            w->rgb[2][g][lane] = blend4(w->rgb[2][g][lane], paint.z, al01, al23, nal01, nal23);
+            float4 vr, vg, vb;
+            if (fresh) {
+                vr = make_float4(base.x, base.x, base.x, base.x); vg = make_float4(base.y, base.y, base.y, base.y); vb = make_float4(base.z, base.z, base.z, base.z);
+            } else {
+                vr = w->rgb[0][g][lane]; vg = w->rgb[1][g][lane]; vb = w->rgb[2][g][lane];
+            }
+            vr = blend4(vr, paint.x, al01, al23, nal01, nal23);
+            vg = blend4(vg, paint.y, al01, al23, nal01, nal23);
+            vb = blend4(vb, paint.z, al01, al23, nal01, nal23);
+            if (!last) {
+                w->rgb[0][g][lane] = vr; w->rgb[1][g][lane] = vg; w->rgb[2][g][lane] = vb;
+            } else {
+                uint32_t rb[4], gb[4], bb[4];
+                srgb_bytes4<EXACT>(vr, rb);
+                srgb_bytes4<EXACT>(vg, gb);
+                srgb_bytes4<EXACT>(vb, bb);
+                const uint4 px = make_uint4(pack_rgb(rb[0], gb[0], bb[0]), pack_rgb(rb[1], gb[1], bb[1]), pack_rgb(rb[2], gb[2], bb[2]), pack_rgb(rb[3], gb[3], bb[3]));
+                __stcs(reinterpret_cast<uint4 *>(dst) + g, px);
+                if (F32) {  // debug render: the un-quantised values
+                    dst32[4 * g + 0] = make_float4(pm_linear_to_srgb<EXACT>(vr.x), pm_linear_to_srgb<EXACT>(vg.x), pm_linear_to_srgb<EXACT>(vb.x), 1.0f);
+                    dst32[4 * g + 1] = make_float4(pm_linear_to_srgb<EXACT>(vr.y), pm_linear_to_srgb<EXACT>(vg.y), pm_linear_to_srgb<EXACT>(vb.y), 1.0f);
+                    dst32[4 * g + 2] = make_float4(pm_linear_to_srgb<EXACT>(vr.z), pm_linear_to_srgb<EXACT>(vg.z), pm_linear_to_srgb<EXACT>(vb.z), 1.0f);
+                    dst32[4 * g + 3] = make_float4(pm_linear_to_srgb<EXACT>(vr.w), pm_linear_to_srgb<EXACT>(vg.w), pm_linear_to_srgb<EXACT>(vb.w), 1.0f);
+                }
+            }
         }
         __syncwarp();
-    }
-
-    #pragma unroll 1
-    for (int g = 0; g < 2; g++) {
-        const float4 r = w->rgb[0][g][lane], gg = w->rgb[1][g][lane], bl = w->rgb[2][g][lane];
-        uint32_t rb[4], gb[4], bb[4];
-        srgb_bytes4<EXACT>(r, rb);
-        srgb_bytes4<EXACT>(gg, gb);
-        srgb_bytes4<EXACT>(bl, bb);
-        const uint4 px = make_uint4(pack_rgb(rb[0], gb[0], bb[0]), pack_rgb(rb[1], gb[1], bb[1]), pack_rgb(rb[2], gb[2], bb[2]), pack_rgb(rb[3], gb[3], bb[3]));
-        __stcs(reinterpret_cast<uint4 *>(dst) + g, px);
-        if (F32) {  // debug render: the un-quantised values
-            dst32[4 * g + 0] = make_float4(pm_linear_to_srgb<EXACT>(r.x), pm_linear_to_srgb<EXACT>(gg.x), pm_linear_to_srgb<EXACT>(bl.x), 1.0f);
-            dst32[4 * g + 1] = make_float4(pm_linear_to_srgb<EXACT>(r.y), pm_linear_to_srgb<EXACT>(gg.y), pm_linear_to_srgb<EXACT>(bl.y), 1.0f);
-            dst32[4 * g + 2] = make_float4(pm_linear_to_srgb<EXACT>(r.z), pm_linear_to_srgb<EXACT>(gg.z), pm_linear_to_srgb<EXACT>(bl.z), 1.0f);
-            dst32[4 * g + 3] = make_float4(pm_linear_to_srgb<EXACT>(r.w), pm_linear_to_srgb<EXACT>(gg.w), pm_linear_to_srgb<EXACT>(bl.w), 1.0f);
-        }
+        if (last) break;
+        fresh = false;
+        cur_item = next_item;
     }
 }
 
@@ -417,10 +455,15 @@ __device__ __forceinline__ uint32_t fine_claim(const PmFrameArgs &A, uint32_t la
 // the light tiles, then 2, then 1 again for the tail (guided self-scheduling: the kernel still ends evenly, and the
 // counter sees a quarter of the atomics -- with one atomic per tile ~4,000 warps queue on one L2 address and a
 // claim took microseconds: a fifth of all warp stall samples in the round-2 profile).
-struct FineRun { uint32_t pos, end; };
+// `pre`, `n_pre`: tickets this warp already owns -- the first two of every warp come out of ONE atomic per CTA at the
+// start of the kernel (4,000 warps asking the counter twice each at the same moment kept the last of them waiting
+// for 10-20 us: an L2 slice serves one atomic on one address every few cycles).
+struct FineRun { uint32_t pos, end, pre, n_pre, pre_stride; };
 __device__ __forceinline__ uint32_t fine_next(const PmFrameArgs &A, const FineList &L, FineRun &r, uint32_t lane) {
     if (r.pos < r.end) return r.pos++;
-    uint32_t t = __shfl_sync(PM_FULL_MASK, fine_claim(A, lane), 0), start, len = 1;
+    uint32_t t, start, len = 1;
+    if (r.n_pre) { t = r.pre; r.pre += r.pre_stride; r.n_pre--; }
+    else t = __shfl_sync(PM_FULL_MASK, fine_claim(A, lane), 0);
     if (t < L.n_medium) start = t;
     else if ((t -= L.n_medium) < L.n4) { start = L.n_medium + PM_FINE_CHUNK * t; len = PM_FINE_CHUNK; }
     else if ((t -= L.n4) < L.n2) { start = L.n_medium + PM_FINE_CHUNK * L.n4 + 2u * t; len = 2; }
@@ -444,7 +487,15 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
     extern __shared__ __align__(16) unsigned char s_raw[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FineWarpSmem *w = reinterpret_cast<FineWarpSmem *>(s_raw) + warp;
+    __shared__ uint32_t s_first_ticket;
     for (uint32_t i = lane; i < 256; i += 32) { w->acc[i] = 0; w->cov[i] = 0; }
+#if PM_FINE_BULK
+    if (lane < 2) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&w->bar[lane])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t bar_phase = 0;  // bit b: the phase the next wait on buffer b expects
+#endif
     // Programmatic dependent launch (pm_kernels.cu): this grid is released by k_heavy, whose CTAs signal only after
     // binning has completed -- so there is no wait here; the wait at the END of the kernel makes this grid's
     // completion imply k_heavy's, which is what the next frame's k_seg depends on.
@@ -458,13 +509,29 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
     }
     const size_t n_tiles = (size_t)A.n_rows * A.n_tx;
     const bool prefer_complex = (warp % PM_FINE_SOLID_EVERY) != (PM_FINE_SOLID_EVERY - 1);
+    constexpr uint32_t kComplexWarps = PM_FINE_WARPS - PM_FINE_WARPS / PM_FINE_SOLID_EVERY;
+    // the first two tickets of every warp that starts with the tiles with records: one atomic for the whole CTA
+#if PM_FINE_CTA_TICKETS
+    if (threadIdx.x == 0) s_first_ticket = atomicAdd(&A.queue->tile_next, 2u * kComplexWarps);
+    __syncthreads();
+    FineRun run{0u, 0u, s_first_ticket + (warp - (warp + 1u) / PM_FINE_SOLID_EVERY), prefer_complex ? 2u : 0u, kComplexWarps};
+#else
+    FineRun run{0u, 0u, 0u, 0u, 0u};
+#endif
     FineList L;
     L.medium = A.complex_list + 2 * n_tiles;
     L.full = A.complex_list;
     L.n_medium = n_medium;
     L.n_total = n_medium + n_complex;
-    L.n4 = (n_complex - n_complex / PM_FINE_CHUNK_TAIL) / PM_FINE_CHUNK;                 // all but the last 1/PM_FINE_CHUNK_TAIL of the full list
-    L.n2 = (n_complex - PM_FINE_CHUNK * L.n4) / 4u;                                       // half of what is left
+    {   // guided: the last PM_FINE_TAIL_PER_WARP tiles per warp of the list go out one by one, as many before them in
+        // twos, the rest (the bulk of a large frame) PM_FINE_CHUNK at a time; a narrow multi-GPU strip with about one
+        // tile per warp is handed out tile by tile
+        const uint32_t per = gridDim.x * kComplexWarps * PM_FINE_TAIL_PER_WARP;
+        const uint32_t singles = n_complex < per ? n_complex : per;
+        const uint32_t twos = n_complex - singles < per ? n_complex - singles : per;
+        L.n4 = (n_complex - singles - twos) / PM_FINE_CHUNK;
+        L.n2 = twos / 2u;
+    }
     __syncwarp();
     const uint32_t batches_per_row = (A.n_tx + 31u) / 32u;
     const uint32_t n_batches = batches_per_row * A.n_rows;
@@ -473,7 +540,6 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
         if (complex_left && (prefer_complex || !batches_left)) {
             complex_left = false;
             // fill the pipeline
-            FineRun run{0u, 0u};
             uint32_t p = fine_next(A, L, run, lane);
             if (p >= L.n_total) continue;
             fine_fetch_entry(L, w, 0, p, lane);
@@ -490,6 +556,10 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
             uint32_t b = 0;
             for (;;) {
                 cp_async_wait<0>();
+#if PM_FINE_BULK
+                fine_bulk_wait(w, b, (bar_phase >> b) & 1u);
+                bar_phase ^= 1u << b;
+#endif
                 __syncwarp();
                 const uint32_t entry = w->ent[b];
                 bool v_nn = false;
@@ -561,7 +631,11 @@ static cudaError_t fine_launch(const PmFrameArgs &a, int grid, bool overlap, cud
 
 cudaError_t pm_launch_fine(const PmFrameArgs &a, int sm_count, bool overlap, cudaStream_t s) {
     // persistent: enough CTAs to fill every SM, work pulled from two queues
-    const int grid = sm_count * PM_FINE_CTAS;
+    int grid = sm_count * PM_FINE_CTAS;
+    {   // experiment switch: fewer resident CTAs per SM with the same code (is the kernel latency- or throughput-bound?)
+        static const char *e = getenv("PM_DEBUG_FINE_CTAS");
+        if (e && atoi(e) > 0) grid = sm_count * atoi(e);
+    }
     const bool exact = (a.flags & PM_FLAG_EXACT_SRGB) != 0;
     if (a.fb32) {  // debug render with the fp32 parity buffer
         return exact ? fine_launch<true, true>(a, grid, overlap, s) : fine_launch<true, false>(a, grid, overlap, s);

@@ -1,0 +1,7 @@
+#!/bin/bash
+set -u
+OUT=gpurun_out; mkdir -p $OUT
+TAG=${1:-v24}
+( time timeout 600 python -m pytest tests -m gpu -x -q ) > $OUT/${TAG}_pytest.log 2>&1; tail -4 $OUT/${TAG}_pytest.log | head -2
+BENCH_ARGS="--steps 200" tools/ab_bench.sh 2>&1 | tee $OUT/${TAG}_ab.txt
+echo "== strips 8192"; SPECS="8:0 8:3" tools/strip_study.sh 8192 2>&1 | tee $OUT/${TAG}_strips.txt
