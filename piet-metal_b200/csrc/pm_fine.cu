@@ -482,11 +482,20 @@ __device__ __forceinline__ void fine_fetch_entry(const FineList &L, FineWarpSmem
     cp_async_commit();
 }
 
+#ifndef PM_FINE_TIMELINE
+#define PM_FINE_TIMELINE 0
+#endif
+__device__ __forceinline__ unsigned long long tl_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
 template <bool F32, bool EXACT>
 __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const PmFrameArgs A) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FineWarpSmem *w = reinterpret_cast<FineWarpSmem *>(s_raw) + warp;
+#if PM_FINE_TIMELINE  // debug build: per-warp [kernel entry, first tile, last tile end, exit], longest tile, tiles, time in tiles
+    const unsigned long long tl_start = tl_now();
+    unsigned long long tl_first = 0, tl_last = 0, tl_long = 0, tl_tiles = 0, tl_sum = 0;
+#endif
     __shared__ uint32_t s_first_ticket;
     for (uint32_t i = lane; i < 256; i += 32) { w->acc[i] = 0; w->cov[i] = 0; }
 #if PM_FINE_BULK
@@ -512,9 +521,12 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
     constexpr uint32_t kComplexWarps = PM_FINE_WARPS - PM_FINE_WARPS / PM_FINE_SOLID_EVERY;
     // the first two tickets of every warp that starts with the tiles with records: one atomic for the whole CTA
 #if PM_FINE_CTA_TICKETS
-    if (threadIdx.x == 0) s_first_ticket = atomicAdd(&A.queue->tile_next, 2u * kComplexWarps);
+    // (two tickets per warp when the list is long; one when it holds only a few tiles per warp -- a narrow strip --
+    // so that they spread over all the warps)
+    const uint32_t n_pre = n_medium + n_complex >= 4u * gridDim.x * kComplexWarps ? 2u : 1u;
+    if (threadIdx.x == 0) s_first_ticket = atomicAdd(&A.queue->tile_next, n_pre * kComplexWarps);
     __syncthreads();
-    FineRun run{0u, 0u, s_first_ticket + (warp - (warp + 1u) / PM_FINE_SOLID_EVERY), prefer_complex ? 2u : 0u, kComplexWarps};
+    FineRun run{0u, 0u, s_first_ticket + (warp - (warp + 1u) / PM_FINE_SOLID_EVERY), prefer_complex ? n_pre : 0u, kComplexWarps};
 #else
     FineRun run{0u, 0u, 0u, 0u, 0u};
 #endif
@@ -573,8 +585,19 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
                         ph |= p >= L.n_medium ? 4u : 0u;
                     }
                 }
+#if PM_FINE_TIMELINE
+                const unsigned long long tl_a = tl_now();
+#endif
                 fine_tile<F32, EXACT>(A, w, b, entry, (ph & 1u) != 0, lane);
                 __syncwarp();
+#if PM_FINE_TIMELINE
+                {
+                    const unsigned long long tl_b = tl_now(), d = tl_b - tl_a;
+                    if (tl_first == 0) tl_first = tl_a;
+                    tl_last = tl_b; tl_tiles++; tl_sum += d;
+                    if (d > (tl_long >> 32)) tl_long = (d << 32) | entry;
+                }
+#endif
                 if (!v_next) break;
                 b ^= 1u;
                 ph >>= 1;
@@ -588,6 +611,12 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
             fine_solid_batch<F32>(A, q, batches_per_row, lane);
         }
     }
+#if PM_FINE_TIMELINE
+    if (A.debug && lane == 0) {
+        unsigned long long *d = A.debug + (1u << 19) + 8ull * (blockIdx.x * PM_FINE_WARPS + warp);
+        d[0] = tl_start; d[1] = tl_first; d[2] = tl_last; d[3] = tl_now(); d[4] = tl_long; d[5] = tl_tiles; d[6] = tl_sum; d[7] = 1;
+    }
+#endif
     asm volatile("griddepcontrol.wait;" ::: "memory");  // k_heavy (and everything before it) has completed
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // the counters the next frame will use (nobody reads this frame's any more)
         A.counters_next->n_complex = 0;

@@ -449,14 +449,16 @@ struct BinSink {
 #ifndef PM_SEG_CTAS
 #define PM_SEG_CTAS 5  // resident CTAs per SM k_seg is compiled for (5: 43 registers as the compiler likes it)
 #endif
+// PM_DEBUG_SEG=1: per-CTA [start, end] in globaltimer ns, two words per CTA (k_seg from word 0, k_row from word 2^18;
+// tools/grid_timeline.py)
+struct CtaTimer {
+    unsigned long long *slot;
+    __device__ static unsigned long long now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+    __device__ CtaTimer(unsigned long long *debug, uint32_t base) : slot(debug && (threadIdx.x & 31) == 0 ? debug + base + 2 * blockIdx.x : nullptr) { if (slot) atomicMin(slot, now()); }  // (one lane per warp)
+    __device__ ~CtaTimer() { if (slot) atomicMax(slot + 1, now()); }
+};
 __global__ void __launch_bounds__(256, PM_SEG_CTAS) k_seg(const PmFrameArgs A) {
-    // PM_DEBUG_SEG=1: per-CTA [start, end] in globaltimer ns, two words per CTA
-    struct Timer {
-        const PmFrameArgs &A;
-        __device__ static unsigned long long now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-        __device__ Timer(const PmFrameArgs &a) : A(a) { if (A.debug) atomicMin(&A.debug[2 * blockIdx.x], now()); }
-        __device__ ~Timer() { if (A.debug) atomicMax(&A.debug[2 * blockIdx.x + 1], now()); }
-    } timer(A);
+    CtaTimer timer(A.debug, 0);
     pm_grid_launch_dependents();
     pm_grid_wait();  // the previous frame's fill kernel is done with the queues, the lists and the scratch
     {   // the backdrop scratch the NEXT frame will use (last touched by the frame before this one): no memset in the frame
@@ -497,6 +499,7 @@ __global__ void __launch_bounds__(256, PM_SEG_CTAS) k_seg(const PmFrameArgs A) {
 __global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t unit = blockIdx.x * PM_ROW_WARPS + warp;
+    CtaTimer timer(A.debug, 1u << 18);
     pm_grid_launch_dependents();
     pm_grid_wait();  // k_seg has finished
     if (unit >= A.n_row_units) return;

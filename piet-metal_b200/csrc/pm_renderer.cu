@@ -805,6 +805,11 @@ int pm_debug_read(pm_renderer *r, unsigned long long *dst, size_t n_words) {
     if (!r || !dst || !r->debug || n_words > (1u << 20)) return PM_ERR_STATE;
     PM_CUDA(cudaStreamSynchronize(r->stream));
     PM_CUDA(cudaMemcpy(dst, r->debug, n_words * 8, cudaMemcpyDeviceToHost));
+    {   // start over: the kernels keep the minimum start / maximum end per slot
+        std::vector<unsigned long long> init(1u << 20);
+        for (size_t i = 0; i < init.size(); i += 2) { init[i] = ~0ull; init[i + 1] = 0; }
+        PM_CUDA(cudaMemcpy(r->debug, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+    }
     return PM_OK;
 }
 
