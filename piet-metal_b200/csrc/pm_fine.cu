@@ -220,11 +220,10 @@ __device__ __noinline__ uint32_t fine_fetch_ext(const PmFrameArgs &A, FineWarpSm
 // One tile that owns records; its header words and inline records are in buffer b.  All 32 lanes execute this
 // together.  Pixel layout: lane l owns pixel row (l >> 1), pixels 8 * (l & 1) .. +7.
 template <bool F32, bool EXACT>
-__device__ __forceinline__ void fine_tile(const PmFrameArgs &A, FineWarpSmem *w, uint32_t b, uint32_t entry, bool full_list, uint32_t lane) {
+__device__ __forceinline__ void fine_tile(const PmFrameArgs &A, FineWarpSmem *w, uint32_t b, uint32_t entry, uint32_t lane) {
     const u64 cw = w->hdr[b][0], ow = w->hdr[b][1];
     uint32_t n = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
-    if (n > PM_WARP_RECORDS) return;  // k_heavy renders it
-    if (full_list && n >= PM_MEDIUM_MIN) return;  // drawn from the list of medium tiles, which is walked first
+    if (n > PM_WARP_RECORDS) return;  // (k_heavy's: k_list does not put such a tile on this kernel's lists)
     const uint32_t occ_item1 = (uint32_t)(ow >> 32) == A.stamp ? (uint32_t)ow : 0u;
     const uint32_t trow = entry >> 16, tx = entry & 0xffffu;
     if (n > PM_TILE_SLOTS) n = fine_fetch_ext(A, w, (size_t)trow * A.n_tx + tx, n, lane);  // (rare: 1-2 % of the tiles)
@@ -440,8 +439,8 @@ __device__ __forceinline__ void fine_solid_batch(const PmFrameArgs &A, uint32_t 
 // b ^ 1) and the one after it (its list entry in flight into ent[b]); only the claim itself (one L2 atomic per
 // tile) is waited for.
 struct FineList {
-    const uint32_t *medium, *full;
-    uint32_t n_medium, n_total;
+    const uint32_t *medium, *mid, *low;  // the three classes k_list wrote for this kernel, walked in this order
+    uint32_t n_medium, n_mid, n_total;
     uint32_t n4, n2;  // tickets that stand for 4 / 2 consecutive positions (see fine_next)
 };
 // (atom.inc with a bound that is never reached, not atom.add: see the header)
@@ -476,7 +475,7 @@ __device__ __forceinline__ uint32_t fine_next(const PmFrameArgs &A, const FineLi
 __device__ __forceinline__ void fine_fetch_entry(const FineList &L, FineWarpSmem *w, uint32_t b, uint32_t pos, uint32_t lane) {
     if (lane == 0) {
         const uint32_t s = (uint32_t)__cvta_generic_to_shared(&w->ent[b]);
-        const uint32_t *src = pos < L.n_medium ? &L.medium[pos] : &L.full[pos - L.n_medium];
+        const uint32_t *src = pos < L.n_medium ? &L.medium[pos] : (pos - L.n_medium < L.n_mid ? &L.mid[pos - L.n_medium] : &L.low[pos - L.n_medium - L.n_mid]);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(src) : "memory");
     }
     cp_async_commit();
@@ -509,9 +508,9 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
     // binning has completed -- so there is no wait here; the wait at the END of the kernel makes this grid's
     // completion imply k_heavy's, which is what the next frame's k_seg depends on.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const uint32_t n_complex = A.counters->n_complex, n_medium = A.counters->n_medium;
+    const uint32_t n_medium = A.counters->n_medium, n_mid = A.counters->n_mid, n_light = n_mid + A.counters->n_low;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        A.report->n_complex = n_complex;
+        A.report->n_complex = A.counters->n_complex;
         A.report->n_overflow = A.counters->n_overflow;
         A.report->n_heavy = A.counters->n_heavy;
         A.report->frame = A.stamp;
@@ -523,7 +522,7 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
 #if PM_FINE_CTA_TICKETS
     // (two tickets per warp when the list is long; one when it holds only a few tiles per warp -- a narrow strip --
     // so that they spread over all the warps)
-    const uint32_t n_pre = n_medium + n_complex >= 4u * gridDim.x * kComplexWarps ? 2u : 1u;
+    const uint32_t n_pre = n_medium + n_light >= 4u * gridDim.x * kComplexWarps ? 2u : 1u;
     if (threadIdx.x == 0) s_first_ticket = atomicAdd(&A.queue->tile_next, n_pre * kComplexWarps);
     __syncthreads();
     FineRun run{0u, 0u, s_first_ticket + (warp - (warp + 1u) / PM_FINE_SOLID_EVERY), prefer_complex ? n_pre : 0u, kComplexWarps};
@@ -532,16 +531,18 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
 #endif
     FineList L;
     L.medium = A.complex_list + 2 * n_tiles;
-    L.full = A.complex_list;
+    L.mid = A.complex_list + 3 * n_tiles;
+    L.low = A.complex_list;
     L.n_medium = n_medium;
-    L.n_total = n_medium + n_complex;
+    L.n_mid = n_mid;
+    L.n_total = n_medium + n_light;
     {   // guided: the last PM_FINE_TAIL_PER_WARP tiles per warp of the list go out one by one, as many before them in
         // twos, the rest (the bulk of a large frame) PM_FINE_CHUNK at a time; a narrow multi-GPU strip with about one
         // tile per warp is handed out tile by tile
         const uint32_t per = gridDim.x * kComplexWarps * PM_FINE_TAIL_PER_WARP;
-        const uint32_t singles = n_complex < per ? n_complex : per;
-        const uint32_t twos = n_complex - singles < per ? n_complex - singles : per;
-        L.n4 = (n_complex - singles - twos) / PM_FINE_CHUNK;
+        const uint32_t singles = n_light < per ? n_light : per;
+        const uint32_t twos = n_light - singles < per ? n_light - singles : per;
+        L.n4 = (n_light - singles - twos) / PM_FINE_CHUNK;
         L.n2 = twos / 2u;
     }
     __syncwarp();
@@ -555,7 +556,6 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
             uint32_t p = fine_next(A, L, run, lane);
             if (p >= L.n_total) continue;
             fine_fetch_entry(L, w, 0, p, lane);
-            uint32_t ph = p >= L.n_medium ? 1u : 0u;  // bit k: tile i + k of the pipeline comes from the full list
             p = fine_next(A, L, run, lane);
             cp_async_wait<0>();
             __syncwarp();
@@ -563,7 +563,6 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
             bool v_next = p < L.n_total;
             if (v_next) {
                 fine_fetch_entry(L, w, 1, p, lane);
-                ph |= p >= L.n_medium ? 2u : 0u;
             }
             uint32_t b = 0;
             for (;;) {
@@ -582,13 +581,12 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
                     v_nn = p < L.n_total;
                     if (v_nn) {
                         fine_fetch_entry(L, w, b, p, lane);
-                        ph |= p >= L.n_medium ? 4u : 0u;
                     }
                 }
 #if PM_FINE_TIMELINE
                 const unsigned long long tl_a = tl_now();
 #endif
-                fine_tile<F32, EXACT>(A, w, b, entry, (ph & 1u) != 0, lane);
+                fine_tile<F32, EXACT>(A, w, b, entry, lane);
                 __syncwarp();
 #if PM_FINE_TIMELINE
                 {
@@ -600,7 +598,6 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
 #endif
                 if (!v_next) break;
                 b ^= 1u;
-                ph >>= 1;
                 v_next = v_nn;
             }
         } else {
@@ -623,6 +620,8 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
         A.counters_next->n_overflow = 0;
         A.counters_next->n_heavy = 0;
         A.counters_next->n_medium = 0;
+        A.counters_next->n_mid = 0;
+        A.counters_next->n_low = 0;
     }
 }
 

@@ -376,7 +376,7 @@ static cudaError_t heavy_launch(const PmFrameArgs &a, int grid, bool overlap, cu
 cudaError_t pm_launch_heavy(const PmFrameArgs &a, int sm_count, bool overlap, cudaStream_t s) {
     // Persistent: the number of heavy tiles is only known on the device; CTAs without work leave at once.  One CTA of
     // eight warps per SM: three quarters of the SM's registers stay free for k_fine's CTAs, which run beside this kernel.
-    const int grid = sm_count * PM_HEAVY_GRID_PER_SM;
+    const int grid = sm_count * (a.heavy_ctas_per_sm ? (int)a.heavy_ctas_per_sm : PM_HEAVY_GRID_PER_SM);
     const bool exact = (a.flags & PM_FLAG_EXACT_SRGB) != 0;
     if (a.fb32) return exact ? heavy_launch<true, true>(a, grid, overlap, s) : heavy_launch<true, false>(a, grid, overlap, s);
     return exact ? heavy_launch<false, true>(a, grid, overlap, s) : heavy_launch<false, false>(a, grid, overlap, s);

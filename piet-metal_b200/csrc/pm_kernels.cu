@@ -10,6 +10,7 @@
 //   k_row          one warp per (item, tile row, 32-tile chunk): prefix-sums the backdrop deltas and closes
 //                  the item per tile -- DrawFill / Solid / opaque cover (64-bit atomic max), Stroke; Line and
 //                  Circle items are binned here directly                          (k_seg, k_row: per frame)
+//   k_list         one thread per tile: the fill kernels' work lists by class from the final record counts (per frame)
 //   k_fine         fill/blend: see pm_fine.cu
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -407,24 +408,6 @@ struct BinSink {
         const uint4 *src = reinterpret_cast<const uint4 *>(&r);
         dst[0] = src[0];
         dst[1] = src[1];
-        if (pos == PM_HEAVY_MIN - 1u) {  // more records than a warp of k_fine holds: the tile is "heavy", k_heavy renders it
-            const uint32_t h = atomicAdd(&A.counters->n_heavy, 1u);
-            A.complex_list[A.n_rows * A.n_tx + h] = ((tile - t) / A.n_tx << 16) | t;
-        }
-        if (pos == PM_MEDIUM_MIN - 1u) {  // the tile has become "medium": k_fine walks these first (third list)
-            cg::coalesced_group g = cg::coalesced_threads();
-            uint32_t base = 0;
-            if (g.thread_rank() == 0) base = atomicAdd(&A.counters->n_medium, g.size());
-            base = g.shfl(base, 0);
-            A.complex_list[2u * A.n_rows * A.n_tx + base + g.thread_rank()] = ((tile - t) / A.n_tx << 16) | t;
-        }
-        if (pos == 0) {  // first record of the tile this frame: queue it for the fill kernel
-            cg::coalesced_group g = cg::coalesced_threads();
-            uint32_t base = 0;
-            if (g.thread_rank() == 0) base = atomicAdd(&A.counters->n_complex, g.size());
-            base = g.shfl(base, 0);
-            A.complex_list[base + g.thread_rank()] = ((tile - t) / A.n_tx << 16) | t;  // (strip-local tile row, tile column)
-        }
     }
     __device__ __forceinline__ void fill(uint32_t t, uint32_t seg, const PmFillEmit &e, const PmSeg &g) {
         append(t, pm_rec_fill(item, seg, t, e, g));
@@ -565,6 +548,52 @@ __global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) 
     }
 }
 
+// One thread per tile, after binning: the fill kernels' work lists from the FINAL record counts -- four disjoint
+// classes (heavy for k_heavy; medium, mid, low for k_fine, which walks them in that order: long jobs first, the
+// cheapest last), appended warp-wise (one atomic per warp and class) so that the entries stay in tile order.
+// (Binning used to append a tile to a list when its count crossed a threshold: three more atomic paths, and a second
+// dependent atomic, on k_seg's and k_row's critical path; tiles listed twice and skipped after their prefetch in k_fine.)
+#ifndef PM_LIST_SCRAMBLE
+#define PM_LIST_SCRAMBLE 0
+#endif
+__global__ void __launch_bounds__(256) k_list(const PmFrameArgs A) {
+    pm_grid_launch_dependents();
+    pm_grid_wait();  // k_row has finished
+    const uint32_t n_tiles = A.n_rows * A.n_tx;
+    uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+#if PM_LIST_SCRAMBLE
+    // (experiment) list order decoupled from tile order: thread -> tile through a multiplicative permutation of the
+    // power-of-two range that covers the tiles
+    {
+        uint32_t bits = 1;
+        while ((1u << bits) < n_tiles) bits++;
+        const uint32_t mask = (1u << bits) - 1u;
+        tile = tile <= mask ? (tile * PM_LIST_SCRAMBLE) & mask : tile;
+    }
+#endif
+    uint32_t n = 0;
+    if (tile < n_tiles) {
+        const u64 cw = A.cnt[tile];
+        n = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
+    }
+    const uint32_t any = __ballot_sync(PM_FULL_MASK, n != 0);
+    if (any == 0) return;
+    const uint32_t cls = n >= PM_HEAVY_MIN ? 1u : (n >= PM_MEDIUM_MIN ? 2u : (n >= PM_MID_MIN ? 3u : 0u));  // quarter of complex_list
+    const uint32_t row = tile / A.n_tx, entry = (row << 16) | (tile - row * A.n_tx);  // (strip-local tile row, tile column)
+    if (lane == 0) atomicAdd(&A.counters->n_complex, (uint32_t)__popc(any));
+    #pragma unroll
+    for (uint32_t c = 0; c < 4; c++) {
+        const uint32_t m = __ballot_sync(PM_FULL_MASK, n != 0 && cls == c);
+        if (m == 0) continue;
+        uint32_t *counter = c == 0 ? &A.counters->n_low : (c == 1 ? &A.counters->n_heavy : (c == 2 ? &A.counters->n_medium : &A.counters->n_mid));
+        uint32_t base = 0;
+        if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(counter, (uint32_t)__popc(m));
+        base = __shfl_sync(PM_FULL_MASK, base, __ffs(m) - 1);
+        if (n != 0 && cls == c) A.complex_list[(size_t)c * n_tiles + base + __popc(m & ((1u << lane) - 1u))] = entry;
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -617,6 +646,15 @@ cudaError_t pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid,
     if (a.n_row_units || overlap) {
         const uint32_t grid_row = (a.n_row_units + PM_ROW_WARPS - 1) / PM_ROW_WARPS;
         if ((e = launch_overlapped(k_row, dim3(grid_row ? grid_row : 1), dim3(PM_ROW_WARPS * 32), overlap, s, a)) != cudaSuccess) return e;
+        launched++;
+    }
+    {
+        const uint32_t n_tiles = a.n_rows * a.n_tx;
+        uint32_t n_threads = n_tiles;
+#if PM_LIST_SCRAMBLE
+        while (n_threads & (n_threads - 1u)) n_threads += n_threads & (0u - n_threads);  // next power of two
+#endif
+        if ((e = launch_overlapped(k_list, dim3((n_threads + 255u) / 256u), dim3(256), overlap, s, a)) != cudaSuccess) return e;
         launched++;
     }
     if (mid && (e = cudaEventRecord(mid, s)) != cudaSuccess) return e;

@@ -9,17 +9,26 @@
 // clear the set frame f+1 will use (no memset node in the frame).  Each counter sits on a cache line of its own:
 // binning adds to all of them concurrently, and atomics on one line are served one at a time.
 struct PmBinCounters {
-    uint32_t n_complex;   // tiles that own at least one record
+    uint32_t n_complex;   // tiles that own at least one record (k_list: the sum of the four classes below)
     uint32_t pad0[31];
     uint32_t n_overflow;  // pool records allocated behind the inline slots (overflow blocks, headers included)
     uint32_t pad1[31];
-    uint32_t n_heavy;     // tiles with at least PM_HEAVY_MIN records: rendered by k_heavy, a whole CTA each
+    uint32_t n_heavy;     // tiles with at least PM_HEAVY_MIN records: rendered by k_heavy
     uint32_t pad2[31];
-    uint32_t n_medium;    // tiles with at least PM_MEDIUM_MIN records: k_fine starts with these
+    uint32_t n_medium;    // tiles with PM_MEDIUM_MIN .. PM_WARP_RECORDS records: k_fine starts with these (the long jobs)
     uint32_t pad3[31];
+    uint32_t n_mid;       // tiles with PM_MID_MIN .. PM_MEDIUM_MIN - 1 records: next
+    uint32_t pad4[31];
+    uint32_t n_low;       // tiles with fewer: last, so that the kernel ends on its cheapest jobs
+    uint32_t pad5[31];
 };
+// The work lists of the fill kernels, written by k_list after binning from the final record counts: four disjoint
+// classes, each in its own quarter of complex_list (n_tiles entries: low | heavy | medium | mid), entries in tile order.
 #ifndef PM_MEDIUM_MIN
 #define PM_MEDIUM_MIN 6u
+#endif
+#ifndef PM_MID_MIN
+#define PM_MID_MIN 2u     // (measured on the 8192^2 tiger: 2 -> frame 144.6 us, 3 -> 148.2 us)
 #endif
 // Records up to which a tile is k_fine's (one warp per tile); tiles with more go to k_heavy (one CTA per tile).
 // 16 = the inline slots.  k_fine can take up to 32 (one record per lane; records 16..31 are the start of the
@@ -86,7 +95,7 @@ struct PmFrameArgs {
     unsigned long long *ovf;
     PmRecord *pool;             // [n_tiles * PM_TILE_SLOTS inline slots][overflow_cap records]
     uint32_t overflow_cap;
-    uint32_t *complex_list;     // 3 * n_rows * n_tx: tiles with records | the heavy ones among them | the medium ones
+    uint32_t *complex_list;     // 4 * n_rows * n_tx: the tiles with records by class (k_list): low | heavy | medium | mid
     PmBinCounters *counters;    // this frame's set
     PmBinCounters *counters_next;
     PmFineQueue *queue;
@@ -100,6 +109,7 @@ struct PmFrameArgs {
     unsigned long long *debug;  // optional per-CTA cycle counts of k_seg (PM_DEBUG_SEG=1)
     const float *srgb_lut;      // 512 floats: [0,256) sRGB byte -> linear, [256,512) alpha byte / 255
     const float4 *item_paint;   // per item: linear r, g, b and alpha of its colour (k_plan; Circle: opaque black)
+    uint32_t heavy_ctas_per_sm; // k_heavy's grid: 1 beside a k_fine that dominates the frame, 3 when the heavy tiles do (host heuristic)
 };
 
 // A set of paths in device memory (pm_flatten.cu; the host-side description is pm_path_set in the public header).

@@ -148,7 +148,7 @@ int alloc_surface(pm_renderer *r) {
         PM_CUDA(cudaMalloc(&r->occ, n_tiles * sizeof(unsigned long long)));
         PM_CUDA(cudaMalloc(&r->cnt, n_tiles * sizeof(unsigned long long)));
         PM_CUDA(cudaMalloc(&r->ovf, n_tiles * sizeof(unsigned long long)));
-        PM_CUDA(cudaMalloc(&r->complex_list, 3 * n_tiles * sizeof(uint32_t)));  // tiles with records | the heavy ones among them | the medium ones
+        PM_CUDA(cudaMalloc(&r->complex_list, 4 * n_tiles * sizeof(uint32_t)));  // the tiles with records by class: low | heavy | medium | mid (k_list)
         r->tiles_cap = n_tiles;
     }
     if (r->fb32) { PM_CUDA(cudaFree(r->fb32)); r->fb32 = nullptr; }
@@ -296,6 +296,14 @@ int enqueue_frame(pm_renderer *r, bool debug_f32) {
     a.srgb_lut = r->lut;
     a.item_paint = r->item_paint;
     a.debug = r->debug;
+    {   // k_heavy's share of the SMs, from what the last reported frame held (mapped host memory, read without a sync:
+        // a heuristic, any value renders the same pixels): when the records behind the inline slots outweigh the tiles
+        // k_fine draws -- small surfaces, the dense synthetic scenes -- k_heavy is the frame and gets three CTAs per SM
+        const volatile PmFrameReport *rep = r->report;
+        const uint32_t n_ovf = rep->n_overflow, n_cplx = rep->n_complex;
+        a.heavy_ctas_per_sm = (rep->frame != 0 && (uint64_t)n_ovf > 4ull * n_cplx) ? 3u : 1u;
+        if (const char *e = getenv("PM_DEBUG_HEAVY_CTAS")) { if (atoi(e) > 0) a.heavy_ctas_per_sm = (uint32_t)atoi(e); }
+    }
     const uint32_t slot = r->frame % EVENT_RING;
     const int mode = debug_f32 ? 1 : r->frame_events;
     const bool events = mode != 0, split = mode == 1;
@@ -648,7 +656,7 @@ int pm_renderer_sync(pm_renderer *r, pm_frame_stats *stats) {
         stats->n_tiles = (r->tile_y1 - r->tile_y0) * r->n_tx;
         stats->n_overflow_records = r->report->n_overflow;
         stats->n_complex_tiles = r->report->n_complex;
-        stats->n_launches = r->n_launches;  /* k_seg, k_row, k_heavy, k_fine */
+        stats->n_launches = r->n_launches;  /* k_seg, k_row, k_list, k_heavy, k_fine */
         stats->retries = r->retries - retries_before;
     }
     r->frames_unsynced = 0;

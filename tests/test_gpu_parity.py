@@ -135,7 +135,7 @@ def test_render_host_roundtrip(pm, renderer):
     renderer.init_scene(scene)
     renderer.draw()
     assert np.array_equal(img, renderer.read_rgba8())
-    assert stats.n_launches == 4 and stats.n_complex_tiles > 0  # k_seg, k_row, k_heavy, k_fine
+    assert stats.n_launches == 5 and stats.n_complex_tiles > 0  # k_seg, k_row, k_list, k_heavy, k_fine
 
 
 def test_scene_device_pointer_path(pm, renderer):
