@@ -259,7 +259,10 @@ int pm_renderer_render_host(pm_renderer *r, const uint8_t *scene, size_t len, ui
                             size_t stride, pm_frame_stats *stats);
 
 /* Device pointer / pitch of the strip's framebuffer and the stream the frame is enqueued on
- * (cudaStream_t), for zero-copy consumers such as a torch tensor view. */
+ * (cudaStream_t), for zero-copy consumers such as a torch tensor view.  A zero-copy consumer must call
+ * pm_renderer_sync() before it uses the pixels of a frame: that is where a frame whose records did not fit the
+ * record pool is detected (the pool grows and the frame is rendered again; pm_frame_stats.retries counts it) --
+ * ordering work on the stream alone would see such a frame with records missing. */
 int pm_renderer_framebuffer(pm_renderer *r, void **dev_ptr, size_t *pitch_bytes, uint32_t *rows);
 int pm_renderer_stream(pm_renderer *r, void **cuda_stream);
 

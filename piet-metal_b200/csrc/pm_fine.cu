@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(PM_FINE_WARPS * 32, PM_FINE_CTAS) k_fine(const
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t n_medium = A.counters->n_medium, n_mid = A.counters->n_mid, n_light = n_mid + A.counters->n_low;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        A.report->n_complex = A.counters->n_complex;
+        A.report->n_complex = A.counters->n_heavy + n_medium + n_light;
         A.report->n_overflow = A.counters->n_overflow;
         A.report->n_heavy = A.counters->n_heavy;
         A.report->frame = A.stamp;

@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(PM_HEAVY_THREADS, PM_HEAVY_CTAS) k_heavy(const
     const uint32_t *list = A.complex_list + (size_t)A.n_rows * A.n_tx;
     __syncthreads();
     uint32_t n_min_cta = 0;
-    if (pm_heavy_warp_mode(n_heavy, gridDim.x, A.counters->n_complex)) {
+    if (pm_heavy_warp_mode(n_heavy, gridDim.x, n_heavy + A.counters->n_medium + A.counters->n_mid + A.counters->n_low)) {
         // many heavy tiles: a warp each (up to PM_HEAVY_WARP_CAP records); what is left is drawn CTA-wise below
         HeavyWarpState *ws = &sh->ws[warp];
         for (;;) {

@@ -137,7 +137,7 @@ __device__ __forceinline__ u64 block_scan_excl(u64 v, u64 *warp_excl, u64 *block
 
 __global__ void __launch_bounds__(1024) k_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0,
                                                uint32_t tile_y1, uint32_t n_tx, u64 *plan_a, u64 *plan_b, PmItemInfo *item_info,
-                                               uint2 *row_info, uint32_t row_info_cap, const float *srgb_lut, float4 *item_paint,
+                                               PmRowInfo *row_info, uint32_t row_info_cap, const float *srgb_lut, float4 *item_paint,
                                                PmPlanResult *result) {
     __shared__ u64 warp_excl[32];
     __shared__ u64 total_a, total_b, carry_a, carry_b;
@@ -160,9 +160,9 @@ __global__ void __launch_bounds__(1024) k_plan(const uint8_t *scene, uint32_t n_
         if (i < n_items) {
             plan_a[i] = ea;
             plan_b[i] = eb;
+            PmItemInfo ii;
             {
                 const ItemSpan spi = item_span(scene, items_ix, i, tile_y0, tile_y1, n_tx);
-                PmItemInfo ii;
                 ii.t_lo = spi.t_lo; ii.t_hi = spi.t_hi; ii.r_lo = spi.r_lo; ii.rows = spi.rows; ii.bd_base = (uint32_t)eb;
                 ii.rgba = 0; ii.tag_flags = spi.tag; ii.w0 = 0;
                 // the item's colour as the fill kernels blend it: unpack_unorm4x8_srgb_to_half (metal:503, :541, :548)
@@ -186,7 +186,14 @@ __global__ void __launch_bounds__(1024) k_plan(const uint8_t *scene, uint32_t n_
                 const uint32_t chunks = (sp.t_hi - sp.t_lo + 32u) / 32u;
                 uint32_t u = (uint32_t)(ea >> 32);
                 for (uint32_t r = 0; r < sp.rows; r++)
-                    for (uint32_t c = 0; c < chunks && u < row_info_cap; c++, u++) row_info[u] = make_uint2(i, ((sp.r_lo + r) << 16) | c);
+                    for (uint32_t c = 0; c < chunks && u < row_info_cap; c++, u++) {
+                        PmRowInfo ri;
+                        ri.item = i; ri.row_chunk = ((sp.r_lo + r) << 16) | c;
+                        ri.bd_row = (uint32_t)eb + r * (sp.t_hi - sp.t_lo + 2u);
+                        ri.t_lo_span = sp.t_lo | ((sp.t_hi - sp.t_lo + 1u) << 16);
+                        ri.rgba = ii.rgba; ri.tag_flags = ii.tag_flags; ri.w0 = ii.w0; ri.pad = 0;
+                        row_info[u] = ri;
+                    }
             }
         }
         // a carry out of the low half (or 2^31 in either half) would corrupt the packed prefixes
@@ -440,7 +447,10 @@ struct CtaTimer {
     __device__ CtaTimer(unsigned long long *debug, uint32_t base) : slot(debug && (threadIdx.x & 31) == 0 ? debug + base + 2 * blockIdx.x : nullptr) { if (slot) atomicMin(slot, now()); }  // (one lane per warp)
     __device__ ~CtaTimer() { if (slot) atomicMax(slot + 1, now()); }
 };
-__global__ void __launch_bounds__(256, PM_SEG_CTAS) k_seg(const PmFrameArgs A) {
+#ifndef PM_SEG_THREADS
+#define PM_SEG_THREADS 256
+#endif
+__global__ void __launch_bounds__(PM_SEG_THREADS, PM_SEG_CTAS * 256 / PM_SEG_THREADS) k_seg(const PmFrameArgs A) {
     CtaTimer timer(A.debug, 0);
     pm_grid_launch_dependents();
     pm_grid_wait();  // the previous frame's fill kernel is done with the queues, the lists and the scratch
@@ -478,7 +488,9 @@ __global__ void __launch_bounds__(256, PM_SEG_CTAS) k_seg(const PmFrameArgs A) {
 // Solid / opaque cover per tile of a Fill item (metal:359-363), Stroke per tile of a Poly item
 // (metal:441-443).  Line and Circle items have no segments and are binned here directly
 // (metal:218-247).  The scratch alternates between two buffers; k_seg clears the one the next frame will use.
+#ifndef PM_ROW_WARPS
 #define PM_ROW_WARPS 8
+#endif
 __global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t unit = blockIdx.x * PM_ROW_WARPS + warp;
@@ -486,28 +498,30 @@ __global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) 
     pm_grid_launch_dependents();
     pm_grid_wait();  // k_seg has finished
     if (unit >= A.n_row_units) return;
-    const uint2 ri = A.row_info[unit];  // (item, tile row << 16 | chunk), tabulated by k_plan
-    const uint32_t item = ri.x;
-    const uint4 *ip4 = reinterpret_cast<const uint4 *>(&A.item_info[item]);
-    const uint4 i0 = ip4[0], i1 = ip4[1];  // t_lo t_hi r_lo rows | bd_base rgba tag_flags w0  (k_plan)
-    const uint32_t tag = i1.z & 0xffu, rgba = i1.y;
+    const uint4 *rp4 = reinterpret_cast<const uint4 *>(&A.row_info[unit]);  // tabulated by k_plan
+    const uint4 r0 = rp4[0], r1 = rp4[1];  // item, row << 16 | chunk, bd_row, t_lo | span << 16 || rgba, tag_flags, w0
+    const uint32_t item = r0.x;
+    const uint32_t tag = r1.y & 0xffu, rgba = r1.x;
     const uint8_t *it = A.scene + A.items_ix + (size_t)item * PM_ITEM_SIZE;
-    const uint32_t span = i0.y - i0.x + 1;
-    const uint32_t row = ri.y >> 16, j0 = (ri.y & 0xffffu) * 32u;
-    const uint32_t t_lo = i0.x;
+    const uint32_t span = r0.w >> 16;
+    const uint32_t row = r0.y >> 16, j0 = (r0.y & 0xffffu) * 32u;
+    const uint32_t t_lo = r0.w & 0xffffu;
     const float y0 = (float)(row * PM_TILE_H);
-    const uint32_t *bd = A.bd + i1.x + (size_t)(row - i0.z) * (span + 1);
+    const uint32_t *bd = A.bd + r0.z;
     BinSink sink{A, nullptr, t_lo, (row - A.tile_y0) * A.n_tx, item};
     const uint32_t j = j0 + lane;
 
     if (tag == PM_ITEM_FILL) {
         // PM_FLAG_FILL_RULES: the item's flags word may ask for the even-odd rule (extension; the reference ignores it)
-        const bool even_odd = (A.flags & PM_FLAG_FILL_RULES) != 0 && (i1.z & PM_INFO_EVEN_ODD) != 0;
+        const bool even_odd = (A.flags & PM_FLAG_FILL_RULES) != 0 && (r1.y & PM_INFO_EVEN_ODD) != 0;
         // backdrop entering this chunk: sum of the deltas of the tiles before it
-        int carry = 0;
-        for (uint32_t q = lane; q < j0; q += 32) carry += (int)bd[q] >> 1;
-        carry = __reduce_add_sync(PM_FULL_MASK, carry);
         const uint32_t v = j < span ? bd[j] : 0u;
+        int carry = 0;
+        if (j0) {  // (most items are narrower than 32 tiles: one chunk, nothing before it)
+            #pragma unroll 1
+            for (uint32_t q = lane; q < j0; q += 32) carry += (int)bd[q] >> 1;
+            carry = __reduce_add_sync(PM_FULL_MASK, carry);
+        }
         int incl = (int)v >> 1;
         for (int o = 1; o < 32; o <<= 1) {
             int u = __shfl_up_sync(PM_FULL_MASK, incl, o);
@@ -527,7 +541,7 @@ __global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) 
             }
         }
     } else if (tag == PM_ITEM_POLY) {
-        if (j < span && (bd[j] & 1u)) sink.trailer(t_lo + j, PM_REC_STROKE, PM_REC_SEG_MAX, i1.w, rgba);
+        if (j < span && (bd[j] & 1u)) sink.trailer(t_lo + j, PM_REC_STROKE, PM_REC_SEG_MAX, r1.z, rgba);
     } else if (tag == PM_ITEM_LINE) {  // metal:223-247
         const float width = ld_f32(it + PM_LINE_WIDTH);
         const float2 s = ld_f2(it + PM_LINE_START), e = ld_f2(it + PM_LINE_END);
@@ -556,12 +570,14 @@ __global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) 
 #ifndef PM_LIST_SCRAMBLE
 #define PM_LIST_SCRAMBLE 0
 #endif
-__global__ void __launch_bounds__(256) k_list(const PmFrameArgs A) {
+#define PM_LIST_THREADS 1024
+__global__ void __launch_bounds__(PM_LIST_THREADS) k_list(const PmFrameArgs A) {
+    __shared__ uint32_t s_cnt[4][PM_LIST_THREADS / 32];
     pm_grid_launch_dependents();
     pm_grid_wait();  // k_row has finished
     const uint32_t n_tiles = A.n_rows * A.n_tx;
     uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #if PM_LIST_SCRAMBLE
     // (experiment) list order decoupled from tile order: thread -> tile through a multiplicative permutation of the
     // power-of-two range that covers the tiles
@@ -577,20 +593,39 @@ __global__ void __launch_bounds__(256) k_list(const PmFrameArgs A) {
         const u64 cw = A.cnt[tile];
         n = (uint32_t)(cw >> 32) == A.stamp ? (uint32_t)cw : 0u;
     }
-    const uint32_t any = __ballot_sync(PM_FULL_MASK, n != 0);
-    if (any == 0) return;
+    if (!__syncthreads_or(n != 0)) return;
     const uint32_t cls = n >= PM_HEAVY_MIN ? 1u : (n >= PM_MEDIUM_MIN ? 2u : (n >= PM_MID_MIN ? 3u : 0u));  // quarter of complex_list
-    const uint32_t row = tile / A.n_tx, entry = (row << 16) | (tile - row * A.n_tx);  // (strip-local tile row, tile column)
-    if (lane == 0) atomicAdd(&A.counters->n_complex, (uint32_t)__popc(any));
+    // One atomic per CTA and class (a counter serves an atomic every few cycles: one per warp -- 8,192 of them on
+    // the same address at 8192^2 -- made this kernel as long as k_seg).  Per warp: the class masks; warp c then turns
+    // the 32 per-warp counts of class c into offsets behind one reservation.
+    uint32_t my_mask = 0;
     #pragma unroll
     for (uint32_t c = 0; c < 4; c++) {
         const uint32_t m = __ballot_sync(PM_FULL_MASK, n != 0 && cls == c);
-        if (m == 0) continue;
-        uint32_t *counter = c == 0 ? &A.counters->n_low : (c == 1 ? &A.counters->n_heavy : (c == 2 ? &A.counters->n_medium : &A.counters->n_mid));
+        if (cls == c) my_mask = m;
+        if (lane == c) s_cnt[c][warp] = (uint32_t)__popc(m);
+    }
+    __syncthreads();
+    if (warp < 4) {
+        const uint32_t v = s_cnt[warp][lane];
+        uint32_t incl = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(PM_FULL_MASK, incl, o);
+            if (lane >= (uint32_t)o) incl += u;
+        }
         uint32_t base = 0;
-        if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(counter, (uint32_t)__popc(m));
-        base = __shfl_sync(PM_FULL_MASK, base, __ffs(m) - 1);
-        if (n != 0 && cls == c) A.complex_list[(size_t)c * n_tiles + base + __popc(m & ((1u << lane) - 1u))] = entry;
+        if (lane == 31 && incl) {
+            uint32_t *counter = warp == 0 ? &A.counters->n_low : (warp == 1 ? &A.counters->n_heavy : (warp == 2 ? &A.counters->n_medium : &A.counters->n_mid));
+            base = atomicAdd(counter, incl);
+        }
+        base = __shfl_sync(PM_FULL_MASK, base, 31);
+        s_cnt[warp][lane] = base + incl - v;
+    }
+    __syncthreads();
+    if (n != 0) {
+        const uint32_t row = tile / A.n_tx, entry = (row << 16) | (tile - row * A.n_tx);  // (strip-local tile row, tile column)
+        A.complex_list[(size_t)cls * n_tiles + s_cnt[cls][warp] + __popc(my_mask & ((1u << lane) - 1u))] = entry;
     }
 }
 
@@ -604,7 +639,7 @@ void pm_launch_validate(const uint8_t *scene, uint32_t scene_len, uint32_t *err,
 }
 
 void pm_launch_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1,
-                    uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, PmItemInfo *item_info, uint2 *row_info,
+                    uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, PmItemInfo *item_info, PmRowInfo *row_info,
                     uint32_t row_info_cap, const float *srgb_lut, float4 *item_paint, PmPlanResult *result, cudaStream_t s) {
     k_plan<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, plan_b, item_info, row_info, row_info_cap, srgb_lut,
                               item_paint, result);
@@ -638,9 +673,9 @@ cudaError_t pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid,
                             uint32_t *n_launched) {
     cudaError_t e;
     uint32_t launched = 0;
-    uint32_t grid_seg = (a.n_pieces + 255u) / 256u;
+    uint32_t grid_seg = (a.n_pieces + PM_SEG_THREADS - 1u) / PM_SEG_THREADS;
     if (grid_seg == 0) grid_seg = 1;  // still clears the fill kernels' queues
-    if ((e = launch_overlapped(k_seg, dim3(grid_seg), dim3(256), overlap, s, a)) != cudaSuccess) return e;
+    if ((e = launch_overlapped(k_seg, dim3(grid_seg), dim3(PM_SEG_THREADS), overlap, s, a)) != cudaSuccess) return e;
     launched++;
     // (k_row runs even without units when the launches overlap: the chain of grid dependencies must not skip a kernel)
     if (a.n_row_units || overlap) {
@@ -654,7 +689,7 @@ cudaError_t pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid,
 #if PM_LIST_SCRAMBLE
         while (n_threads & (n_threads - 1u)) n_threads += n_threads & (0u - n_threads);  // next power of two
 #endif
-        if ((e = launch_overlapped(k_list, dim3((n_threads + 255u) / 256u), dim3(256), overlap, s, a)) != cudaSuccess) return e;
+        if ((e = launch_overlapped(k_list, dim3((n_threads + PM_LIST_THREADS - 1u) / PM_LIST_THREADS), dim3(PM_LIST_THREADS), overlap, s, a)) != cudaSuccess) return e;
         launched++;
     }
     if (mid && (e = cudaEventRecord(mid, s)) != cudaSuccess) return e;

@@ -9,7 +9,7 @@
 // clear the set frame f+1 will use (no memset node in the frame).  Each counter sits on a cache line of its own:
 // binning adds to all of them concurrently, and atomics on one line are served one at a time.
 struct PmBinCounters {
-    uint32_t n_complex;   // tiles that own at least one record (k_list: the sum of the four classes below)
+    uint32_t n_complex;   // (unused: the number of tiles with records is the sum of the four classes below)
     uint32_t pad0[31];
     uint32_t n_overflow;  // pool records allocated behind the inline slots (overflow blocks, headers included)
     uint32_t pad1[31];
@@ -70,6 +70,15 @@ struct alignas(16) PmSegInfo {
 struct alignas(16) PmItemInfo { uint32_t t_lo, t_hi, r_lo, rows; uint32_t bd_base, rgba, tag_flags, w0; };
 #define PM_INFO_EVEN_ODD 0x100u
 
+// One k_row unit = (item, tile row, chunk of 32 tiles), with what k_row needs of the item copied in (one dependent load
+// less: k_row is a chain of dependent loads and atomics).
+struct alignas(16) PmRowInfo {
+    uint32_t item, row_chunk;   // tile row << 16 | chunk
+    uint32_t bd_row;            // first word of the (item, row)'s slice of the backdrop scratch
+    uint32_t t_lo_span;         // first tile column of the item | (tile span << 16)
+    uint32_t rgba, tag_flags, w0, pad;
+};
+
 struct PmFrameArgs {
     const uint8_t *scene;       // encoded scene in device memory
     uint32_t scene_len;
@@ -80,7 +89,7 @@ struct PmFrameArgs {
     const uint2 *piece_info;           // per k_seg thread: segment, flags | tile row << 15 | tile column (k_pieces_*)
     const PmSegInfo *seg_info;         // per segment (k_pieces_*)
     const PmItemInfo *item_info;       // per item (k_plan)
-    const uint2 *row_info;             // per k_row unit: item, tile row << 16 | 32-tile chunk
+    const PmRowInfo *row_info;         // per k_row unit (k_plan): everything the warp needs in one 32-byte load
     uint32_t n_segments;        // segments of the Fill / Poly items that touch the strip
     uint32_t n_pieces;          // k_seg threads
     uint32_t n_row_units;       // k_row warps: (item, tile row) pairs inside the strip
@@ -135,7 +144,7 @@ struct PmPlanResult { uint32_t n_segments; uint32_t n_rows; unsigned long long b
 void pm_launch_validate(const uint8_t *scene, uint32_t scene_len, uint32_t *err, cudaStream_t s);
 // Fills plan_a / plan_b [0..n_items] and result (device) for the given strip.
 void pm_launch_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1,
-                    uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, PmItemInfo *item_info, uint2 *row_info,
+                    uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, PmItemInfo *item_info, PmRowInfo *row_info,
                     uint32_t row_info_cap, const float *srgb_lut, float4 *item_paint, PmPlanResult *result, cudaStream_t s);
 // The k_seg work list: count + prefix (result->n_pieces, piece_cnt becomes the per-segment offset), then fill.
 void pm_launch_pieces_count(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,

@@ -63,7 +63,8 @@ struct pm_renderer {
     size_t seg_cap = 0;
     PmItemInfo *item_info = nullptr;
     float4 *item_paint = nullptr;   // per item: linear colour + alpha (k_plan)
-    uint2 *piece_info = nullptr, *row_info = nullptr;
+    uint2 *piece_info = nullptr;
+    PmRowInfo *row_info = nullptr;
     size_t piece_cap = 0, row_info_cap = 0;
     uint32_t *bd = nullptr;  // backdrop scratch, zero between frames
     unsigned long long *debug = nullptr;
@@ -184,7 +185,7 @@ int run_plan(pm_renderer *r) {
         if (r->row_info) PM_CUDA(cudaFree(r->row_info));
         r->row_info = nullptr;
         r->row_info_cap = 0;
-        PM_CUDA(cudaMalloc(&r->row_info, ((size_t)res.n_rows + res.n_rows / 8 + 1) * sizeof(uint2)));
+        PM_CUDA(cudaMalloc(&r->row_info, ((size_t)res.n_rows + res.n_rows / 8 + 1) * sizeof(PmRowInfo)));
         r->row_info_cap = (size_t)res.n_rows + res.n_rows / 8 + 1;
     }
     if (res.error) { g_last_error = "scene has more than 2^31 segments or (item, tile row) pairs"; return PM_ERR_INVALID_ARG; }

@@ -16,13 +16,13 @@ for l in open("$OUT/${TAG}_configs.jsonl"):
     d=json.loads(l); r=d["roofline"]; f=d["frame_stats"]
     print("%-28s %8.1f us/frame %9.0f Mpx/s | fine %.1f us (%.3f of HBM) heavy %.1f bin %.1f plan %.2f ms | complex %d heavy %d | e2e %.0f Mpx/s" % (d["config"]["workload"], d["ms_per_step"]*1e3, d["value"], r["kernel_ms"]*1e3, r["frac"], r["heavy_kernel_ms"]*1e3, r["bin_kernel_ms"]*1e3, r["plan_ms"], f["complex_tiles"], f["heavy_tiles"], d["e2e"]["value"]))
 PY
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 48 --csv --log-file $OUT/${TAG}_launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 75 -c 60 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 6 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $OUT/${TAG}_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_fine|k_heavy|k_seg|k_row" -s 40 -c 4 -f -o $OUT/${TAG}_frame \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_fine|k_heavy|k_seg|k_row|k_list" -s 50 -c 5 -f -o $OUT/${TAG}_frame \
     python bench.py --steps 6 --warmup 3 --no-cpu-baseline --e2e-steps 1 >> $OUT/${TAG}_ncu.log 2>&1
 ncu -i $OUT/${TAG}_frame.ncu-rep --page raw --csv > $OUT/${TAG}_frame_raw.csv 2>/dev/null
 ncu -i $OUT/${TAG}_frame.ncu-rep --page source --csv > $OUT/${TAG}_frame_source.csv 2>/dev/null
-timeout 900 ncu --set full --clock-control none -k regex:"k_fine|k_heavy|k_seg|k_row" -s 40 -c 4 -f -o $OUT/${TAG}_cfg4 \
+timeout 900 ncu --set full --clock-control none -k regex:"k_fine|k_heavy|k_seg|k_row|k_list" -s 50 -c 5 -f -o $OUT/${TAG}_cfg4 \
     python bench.py --scene rand_bezier --size 8192 --steps 6 --warmup 3 --no-cpu-baseline --e2e-steps 1 >> $OUT/${TAG}_ncu.log 2>&1
 ncu -i $OUT/${TAG}_cfg4.ncu-rep --page raw --csv > $OUT/${TAG}_cfg4_raw.csv 2>/dev/null
 ls -la $OUT/${TAG}_*
