@@ -82,10 +82,13 @@ typedef unsigned long long u64;
 // k_plan: per-item prefixes for the two binning kernels (once per scene / size / strip)
 //   plan_a[i]  low 32 bits: segments of items < i (k_seg: one thread per segment)
 //              high 32 bits: (tile row, 32-tile chunk) pairs of items < i (k_row: one warp each)
-//   plan_b[i]  words of the backdrop scratch before item i: rows * (tile span + 1) per item
+//   plan_b[i]  words of the backdrop scratch before item i: rows * pm_bd_stride(tile span) per item
 // Items that do not touch the strip count nothing.
 // ---------------------------------------------------------------------------------------------
 struct ItemSpan { uint32_t tag, r_lo, rows, t_lo, t_hi, n_points; };
+// words of one (item, tile row) slice of the backdrop scratch: tile span + 1, rounded up to whole 16-byte units so
+// that k_row can sum the deltas of the chunks before its own with 128-bit loads
+__device__ __forceinline__ uint32_t pm_bd_stride(uint32_t span) { return (span + 1u + 3u) & ~3u; }
 
 __device__ __forceinline__ ItemSpan item_span(const uint8_t *scene, uint32_t items_ix, uint32_t i, uint32_t tile_y0,
                                               uint32_t tile_y1, uint32_t n_tx) {
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(1024) k_plan(const uint8_t *scene, uint32_t n_
             if (sp.rows) {
                 const uint32_t n_seg = sp.tag == PM_ITEM_FILL ? sp.n_points : (sp.tag == PM_ITEM_POLY ? sp.n_points - 1u : 0u);
                 ca = ((u64)(sp.rows * ((sp.t_hi - sp.t_lo + 32u) / 32u)) << 32) | n_seg;  // rows x 32-tile chunks
-                if (sp.tag == PM_ITEM_FILL || sp.tag == PM_ITEM_POLY) cb = (u64)sp.rows * (sp.t_hi - sp.t_lo + 2u);
+                if (sp.tag == PM_ITEM_FILL || sp.tag == PM_ITEM_POLY) cb = (u64)sp.rows * pm_bd_stride(sp.t_hi - sp.t_lo + 1u);
             }
         }
         const u64 ea = carry_a + block_scan_excl(ca, warp_excl, &total_a);
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(1024) k_plan(const uint8_t *scene, uint32_t n_
                     for (uint32_t c = 0; c < chunks && u < row_info_cap; c++, u++) {
                         PmRowInfo ri;
                         ri.item = i; ri.row_chunk = ((sp.r_lo + r) << 16) | c;
-                        ri.bd_row = (uint32_t)eb + r * (sp.t_hi - sp.t_lo + 2u);
+                        ri.bd_row = (uint32_t)eb + r * pm_bd_stride(sp.t_hi - sp.t_lo + 1u);
                         ri.t_lo_span = sp.t_lo | ((sp.t_hi - sp.t_lo + 1u) << 16);
                         ri.rgba = ii.rgba; ri.tag_flags = ii.tag_flags; ri.w0 = ii.w0; ri.pad = 0;
                         row_info[u] = ri;
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(PM_SEG_THREADS, PM_SEG_CTAS * 256 / PM_SEG_THR
     const u64 bd_base = s2.w;
     const uint32_t row = (pi.y >> 15) & 0x7fffu, t = pi.y & 0x7fffu;
     const float y0 = (float)(row * PM_TILE_H);
-    BinSink sink{A, A.bd + bd_base + (size_t)(row - r_lo) * (t_hi - t_lo + 2u), t_lo, (row - A.tile_y0) * A.n_tx, item};
+    BinSink sink{A, A.bd + bd_base + (size_t)(row - r_lo) * pm_bd_stride(t_hi - t_lo + 1u), t_lo, (row - A.tile_y0) * A.n_tx, item};
     if (s1.w == PM_ITEM_FILL) {
         if (pi.y & PM_PIECE_FIRST) pm_fill_backdrop_row(sink, sg, y0, t_lo, t_hi, A.n_tx);
         if (pi.y & PM_PIECE_TILE) pm_fill_candidate_tile(sink, sg, y0, t, k);
@@ -519,7 +522,10 @@ __global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) 
         int carry = 0;
         if (j0) {  // (most items are narrower than 32 tiles: one chunk, nothing before it)
             #pragma unroll 1
-            for (uint32_t q = lane; q < j0; q += 32) carry += (int)bd[q] >> 1;
+            for (uint32_t q = lane * 4u; q < j0; q += 128u) {  // (the slice starts on a 16-byte boundary: pm_bd_stride)
+                const uint4 d = *reinterpret_cast<const uint4 *>(&bd[q]);
+                carry += ((int)d.x >> 1) + ((int)d.y >> 1) + ((int)d.z >> 1) + ((int)d.w >> 1);
+            }
             carry = __reduce_add_sync(PM_FULL_MASK, carry);
         }
         int incl = (int)v >> 1;
