@@ -345,6 +345,31 @@ def test_frames_without_events_are_identical(pm, renderer):
     assert np.array_equal(renderer.read_rgba8(), want)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_frames", [2, 7])
+def test_overlapped_frames_large(pm, renderer, n_frames):
+    """Back-to-back frames without events (kernels and frames chained by programmatic dependent launch) at a size
+    where the kernels' tails are long: after an even and an odd number of frames, pixels and per-tile item lists are
+    those of a single synchronous frame."""
+    w = h = 4096
+    scene = pm.build_scene(pm.SCENE_TIGER, w, h)
+    renderer.drawable_size_will_change(w, h)
+    renderer.init_scene(scene)
+    renderer.draw()
+    want = renderer.read_rgba8()
+    want_off, want_items, want_solid = renderer.read_tile_items()
+    renderer.set_frame_events(False)
+    try:
+        for _ in range(n_frames):
+            renderer.draw()
+        renderer.sync()
+        assert np.array_equal(renderer.read_rgba8(), want)
+        off, items, solid = renderer.read_tile_items()
+        assert np.array_equal(off, want_off) and np.array_equal(items, want_items) and np.array_equal(solid, want_solid)
+    finally:
+        renderer.set_frame_events(True)
+
+
 def test_balanced_strips_equal_full_frame(pm, renderer):
     """Cost-balanced (unequal) row strips of the tiger and of the glyph scene reproduce the full frame byte for byte."""
     for kind, size, count in ((pm.SCENE_TIGER, 2048, 0), (pm.SCENE_GLYPHS, 1024, 6000)):

@@ -44,13 +44,29 @@ def show(name, a):
     print("       running CTAs every 2 us:", " ".join(str(int(((s <= t) & (e > t)).sum())) for t in ts))
 show("k_seg", seg); show("k_row", row)
 f = d[1 << 19:(1 << 19) + 8 * 148 * 4 * 8].reshape(-1, 8)
-f = f[f[:, 7] == 1]
+f = f[f[:, 7] != 0]
 if len(f):
     st, first, last, ex = [(f[:, k] - t0) / 1e3 for k in range(4)]
-    has = f[:, 5] > 0
+    n_tiles_w = f[:, 5] & 0xffffffff
+    has = n_tiles_w > 0
     print("k_fine %5d warps: entry %6.1f..%6.1f us, first tile starts %6.1f..%6.1f (median %.1f), last tile ends median %.1f max %.1f, exit max %.1f" %
           (len(f), st.min(), st.max(), first[has].min(), first[has].max(), np.median(first[has]), np.median(last[has]), last[has].max(), ex.max()))
     print("       tiles per warp median %d max %d; time in tiles per warp median %.1f us; longest tile %.1f us (p99 of per-warp longest %.1f)" %
-          (np.median(f[:, 5]), f[:, 5].max(), np.median(f[:, 6]) / 1e3, (f[:, 4] >> 32).max() / 1e3, np.percentile(f[:, 4] >> 32, 99) / 1e3))
+          (np.median(n_tiles_w), n_tiles_w.max(), 0.0, (f[:, 4] >> 32).max() / 1e3, np.percentile(f[:, 4] >> 32, 99) / 1e3))
     ts = np.arange(st.min(), ex.max(), 4.0)
     print("       warps inside [first tile, last tile end] every 4 us:", " ".join(str(int((has & (first <= t) & (last > t)).sum())) for t in ts))
+    # the end of the kernel in detail: warps still inside tiles every 2 us over the last 30 us, and the latest long tiles
+    t_end = ex.max()
+    ts = np.arange(t_end - 30.0, t_end, 2.0)
+    print("       last 30 us, warps inside tiles every 2 us:", " ".join(str(int((has & (first <= t) & (last > t)).sum())) for t in ts))
+    print("       CTAs' exits: p50 %.1f p90 %.1f p99 %.1f max %.1f us before the end" % tuple(t_end - np.percentile(ex, [50, 10, 1, 0])))
+    dur = (f[:, 4] >> 32) / 1e3
+    lstart = (f[:, 7] - t0) / 1e3
+    lend = lstart + dur
+    lstart2 = (f[:, 6] - t0) / 1e3
+    order = np.argsort(-last)[:16]
+    print("       the tiles that end last: (end, us before kernel end; duration us; tile row, col; tiles this warp drew)")
+    for k in order:
+        if not has[k]: continue
+        e = int(f[k, 5] >> 32)
+        print("         -%.1f us  %.1f us  (%d, %d)  %d tiles" % (t_end - last[k], last[k] - lstart2[k], e >> 16, e & 0xffff, n_tiles_w[k]))
