@@ -341,7 +341,7 @@ def main():
             "gpu_launches": int(st.n_launches) * args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_fine (fill/blend: stores the framebuffer)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "traffic_note": "not measured in this run; the ncu capture of this workload is profiles/r02c_ncu_summary.json (k_fine: 29.6 MB read + 224.3 MB written per launch)",
+                         "traffic_note": "not measured in this run; the ncu capture of this workload is profiles/r02d_ncu_summary.json (k_fine: 29.6 MB read + 225.1 MB written per launch)",
                          "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": fine_ms_max,
                          "bin_kernel_ms": bin_ms, "heavy_kernel_ms": heavy_ms, "plan_ms": plan_ms,
                          "note": "kernel times from a second pass with every kernel group timed on its own (no overlap)"},

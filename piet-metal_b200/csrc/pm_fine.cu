@@ -49,10 +49,11 @@ typedef unsigned long long u64;
 #define PM_FINE_CHUNK 4u         // positions per ticket in the bulk of the list of light tiles (fine_next)
 #endif
 #ifndef PM_FINE_TAIL_PER_WARP
-#define PM_FINE_TAIL_PER_WARP 4u // tiles per warp at the end of the list that are handed out one by one (and as many in twos before them).
+#define PM_FINE_TAIL_PER_WARP 6u // tiles per warp at the end of the list that are handed out one by one (and as many in twos before them).
                                  // A warp owns up to three tiles at a time (rendering, records in flight, list entry in flight), so the
                                  // kernel's tail is about three tiles long whatever the chunks are; coarse chunks near the end add to it.
-                                 // 8192^2 tiger, frame / k_fine alone: 2 -> 139.2 / 98.0 us, 3 -> 137.2 / 96.5, 4 -> 134.5 / 93.6, 6 -> 134.3 / 93.4
+                                 // 8192^2 tiger, frame / k_fine alone: 2 -> 139.2 / 98.0 us, 3 -> 137.2 / 96.5, 4 -> 134.5 / 93.6, 6 -> 134.3 / 93.4;
+                                 // with the cheapest tiles (one or two records) last, PM_MID_MIN = 3: 6 -> 134.0 / 92.2
 #endif
 #ifndef PM_FINE_MAGIC_ROUND
 #define PM_FINE_MAGIC_ROUND 1    // sRGB bytes rounded with an FADD2 (magic number) instead of cvt.rni.sat.u8 on the XU pipe

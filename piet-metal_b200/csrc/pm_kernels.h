@@ -28,7 +28,7 @@ struct PmBinCounters {
 #define PM_MEDIUM_MIN 6u
 #endif
 #ifndef PM_MID_MIN
-#define PM_MID_MIN 2u     // (measured on the 8192^2 tiger: 2 -> frame 144.6 us, 3 -> 148.2 us)
+#define PM_MID_MIN 3u     // (8192^2 tiger, with six single-tile tickets per warp at the end of the list: 3 -> frame 134.0 us, 2 -> 135.1, 4 -> 137.0)
 #endif
 // Records up to which a tile is k_fine's (one warp per tile); tiles with more go to k_heavy (one CTA per tile).
 // 16 = the inline slots.  k_fine can take up to 32 (one record per lane; records 16..31 are the start of the
