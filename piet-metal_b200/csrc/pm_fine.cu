@@ -7,22 +7,24 @@
 // one CTA per tile), which runs beside this kernel.
 //
 // Persistent CTAs; a warp pulls work from two queues:
-//   * tiles with records: the list binning wrote, medium tiles first, one position per claim (see FineList).  While
-//     tile i is rendered, the header words and the 16 inline record slots (512 B) of tile i+1 are in flight
-//     (cp.async into the other half of a double buffer in shared memory), and so are the list entry of tile i+2
-//     and the claim of tile i+3;
+//   * tiles with records: the three lists k_list wrote for this kernel (medium, mid, low: long jobs first, the
+//     cheapest last), positions handed out by ticket (see FineList / fine_next).  While tile i is rendered, the
+//     header words and the 16 inline record slots (512 B) of tile i+1 are in flight (cp.async into the other half
+//     of a double buffer in shared memory), and so is the list entry of tile i+2;
 //   * batches of 32 consecutive solid tiles (every store instruction is a full 512-byte run of one pixel row).
 // Per tile: the items are taken in painter's order by repeated warp-min over the item ids of the (at most 16)
 // records, one record per lane; coverage of one item is accumulated in shared memory in 8.24 fixed point by lanes
 // that enumerate (record, pixel row) pairs and then (pair, pixel) units (pm_cover.cuh); lane l owns pixel row
-// l / 2, pixels 8 (l & 1) .. +7, resolves their alpha, and blends into the tile's linear colour, which lives in a
-// lane-private slice of shared memory (packed two-wide FMAs, FFMA2); the sRGB encode and the two 128-bit
-// framebuffer stores per lane happen once per tile.  An item's linear colour comes from a per-item table built at
-// plan time (k_plan), not from the sRGB look-up table.
+// l / 2, pixels 8 (l & 1) .. +7, resolves their alpha, and blends (packed two-wide FMAs, FFMA2) into the tile's
+// linear colour, which goes through a lane-private slice of shared memory only between items; the sRGB encode and
+// the two 128-bit framebuffer stores per lane happen once per tile.  An item's linear colour comes from a per-item
+// table built at plan time (k_plan), not from the sRGB look-up table.
 //
-// Kept from the first round's measurements (profiles/README.md): the kernel is issue-bound, so what counts is warp
-// instructions per tile and resident warps; claims are atom.inc on purpose (an atom.add on a warp-uniform address
-// is compiled into a warp-aggregated atomic plus a shuffle that waits for it).
+// What the measurements say (profiles/README.md): the kernel is throughput-bound on its instruction mix (issue
+// slots ~70 %, L1 data pipe ~58 %; 21 resident warps per SM are only 5 % slower than 28), so what counts is warp
+// instructions per tile; its tail is as long as the three tiles a warp owns at a time; claims are atom.inc on
+// purpose (an atom.add on a warp-uniform address is compiled into a warp-aggregated atomic plus a shuffle that
+// waits for it), and as few as possible (a counter serves one atomic every few cycles).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -434,14 +436,12 @@ __device__ __forceinline__ void fine_solid_batch(const PmFrameArgs &A, uint32_t 
     }
 }
 
-// Work list of the tiles with records, as k_fine walks it: the medium tiles (PM_MEDIUM_MIN or more records: the
-// long jobs) first, then the full list, in which the medium and heavy ones are skipped.  Positions are claimed one
-// at a time (a warp renders only about 14 tiles per frame at 8192^2, ~9 us each: anything coarser shows up as idle
-// SMs at the end of the kernel; dealing a part of the list statically was measured and lost, because the CTAs
-// that start late -- k_heavy's CTAs run on the same SMs -- keep their share waiting).  Four tiles are in the
-// pipeline: the tile being rendered (buffer b), the next one (its header words and records in flight into buffer
-// b ^ 1) and the one after it (its list entry in flight into ent[b]); only the claim itself (one L2 atomic per
-// tile) is waited for.
+// Work list of the tiles with records, as k_fine walks it: k_list's three classes one after the other -- medium
+// (PM_MEDIUM_MIN .. PM_WARP_RECORDS records: the long jobs), mid, low (one or two records: the cheapest, last).
+// Three tiles are in a warp's pipeline: the tile being rendered (buffer b), the next one (its header words and
+// records in flight into buffer b ^ 1) and the one after it (its list entry in flight into ent[b]); only a ticket
+// (one L2 atomic per run of positions) is waited for.  Dealing a part of the list statically was measured and lost:
+// the CTAs that start late -- k_heavy's CTA holds one of the four slots of an SM -- keep their share waiting.
 struct FineList {
     const uint32_t *medium, *mid, *low;  // the three classes k_list wrote for this kernel, walked in this order
     uint32_t n_medium, n_mid, n_total;

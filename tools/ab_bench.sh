@@ -1,5 +1,6 @@
 #!/bin/bash
 # A/B: bench every library under piet-metal_b200/variants/ plus the default one (kernel times only).
+shopt -s nullglob
 for lib in piet-metal_b200/libpiet_metal_b200.so piet-metal_b200/variants/*.so; do
   for rep in 1 2; do
     PM_LIB=$PWD/$lib python bench.py --no-cpu-baseline --e2e-steps 1 ${BENCH_ARGS:-} 2>/dev/null | python -c "
