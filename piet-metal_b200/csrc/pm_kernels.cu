@@ -1,8 +1,8 @@
 // CUDA kernels of the render path (sm_100a).  Compiled with -fmad=false: see pm_tile_logic.h.
 //
 //   k_validate     bounds/finite check of an uploaded scene                      (the reference has none)
-//   k_plan         per-item prefixes: segments, (tile row, 32-tile chunk) units of k_row, backdrop-scratch
-//                  words; item table                                              (once per scene/size/strip)
+//   k_plan_*       per-item prefixes: segments, (tile row, 32-tile chunk) units of k_row, backdrop-scratch
+//                  words; item table; k_row's unit table                          (once per scene/size/strip)
 //   k_pieces_*     per segment: the conservative list of (tile row, candidate tile) "pieces" = k_seg threads
 //                  (count, prefix, fill: three kernels)
 //   k_seg          one thread per piece: the exact tile tests of TestApp/PietRender.metal:248-445 for one
@@ -138,80 +138,101 @@ __device__ __forceinline__ u64 block_scan_excl(u64 v, u64 *warp_excl, u64 *block
     return r;
 }
 
-__global__ void __launch_bounds__(1024) k_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0,
-                                               uint32_t tile_y1, uint32_t n_tx, u64 *plan_a, u64 *plan_b, PmItemInfo *item_info,
-                                               PmRowInfo *row_info, uint32_t row_info_cap, const float *srgb_lut, float4 *item_paint,
-                                               PmPlanResult *result) {
+// Three kernels (the plan is redone for every scene that is uploaded, i.e. inside every end-to-end frame; as one
+// CTA looping over the items and writing every item's k_row units one after the other it took 0.3 ms for the tiger's
+// 304 wide items and 1.9 ms for 100 k glyphs):
+//   k_plan_count  one thread per item: its counts (into plan_a / plan_b), its PmItemInfo and its linear colour
+//   k_plan_scan   one CTA: the counts become exclusive prefixes in place (every thread a contiguous chunk)
+//   k_plan_rows   one thread per k_row unit: its PmRowInfo (the item by binary search in the prefixes)
+__global__ void __launch_bounds__(256) k_plan_count(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0,
+                                                    uint32_t tile_y1, uint32_t n_tx, u64 *plan_a, u64 *plan_b, PmItemInfo *item_info,
+                                                    const float *srgb_lut, float4 *item_paint) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const ItemSpan sp = item_span(scene, items_ix, i, tile_y0, tile_y1, n_tx);
+    u64 ca = 0, cb = 0;
+    if (sp.rows) {
+        const uint32_t n_seg = sp.tag == PM_ITEM_FILL ? sp.n_points : (sp.tag == PM_ITEM_POLY ? sp.n_points - 1u : 0u);
+        ca = ((u64)(sp.rows * ((sp.t_hi - sp.t_lo + 32u) / 32u)) << 32) | n_seg;  // rows x 32-tile chunks
+        if (sp.tag == PM_ITEM_FILL || sp.tag == PM_ITEM_POLY) cb = (u64)sp.rows * pm_bd_stride(sp.t_hi - sp.t_lo + 1u);
+    }
+    plan_a[i] = ca;
+    plan_b[i] = cb;
+    PmItemInfo ii;
+    ii.t_lo = sp.t_lo; ii.t_hi = sp.t_hi; ii.r_lo = sp.r_lo; ii.rows = sp.rows; ii.bd_base = 0;
+    ii.rgba = 0; ii.tag_flags = sp.tag; ii.w0 = 0;
+    // the item's colour as the fill kernels blend it: unpack_unorm4x8_srgb_to_half (metal:503, :541, :548)
+    // through the look-up table; Cmd_Circle paints opaque black (metal:491)
+    float4 paint = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+    if (sp.tag == PM_ITEM_LINE || sp.tag == PM_ITEM_FILL || sp.tag == PM_ITEM_POLY) {
+        const uint8_t *it = scene + items_ix + (size_t)i * PM_ITEM_SIZE;
+        const uint32_t rgba = ld_u32(it + (sp.tag == PM_ITEM_POLY ? PM_POLY_RGBA : PM_FILL_RGBA));
+        paint = make_float4(srgb_lut[rgba & 0xffu], srgb_lut[(rgba >> 8) & 0xffu], srgb_lut[(rgba >> 16) & 0xffu], srgb_lut[256u + (rgba >> 24)]);
+        ii.rgba = rgba;
+        if (sp.tag == PM_ITEM_FILL && (ld_u32(it + PM_FILL_FLAGS) & PM_FILL_EVEN_ODD) != 0) ii.tag_flags |= PM_INFO_EVEN_ODD;
+        if (sp.tag == PM_ITEM_POLY) ii.w0 = pm_f2u(0.5f * ld_f32(it + PM_POLY_WIDTH));
+        if (sp.tag == PM_ITEM_LINE) ii.w0 = pm_f2u(0.5f * ld_f32(it + PM_LINE_WIDTH));
+    }
+    item_info[i] = ii;
+    item_paint[i] = paint;
+}
+
+// plan_a / plan_b [0, n_items): counts -> exclusive prefixes, in place; [n_items] = the totals; result (device)
+__global__ void __launch_bounds__(1024) k_plan_scan(uint32_t n_items, u64 *plan_a, u64 *plan_b, PmPlanResult *result) {
     __shared__ u64 warp_excl[32];
-    __shared__ u64 total_a, total_b, carry_a, carry_b;
+    __shared__ u64 total_lo, total_hi, total_b;
     const uint32_t tid = threadIdx.x;
-    if (tid == 0) { carry_a = 0; carry_b = 0; }
-    __syncthreads();
-    for (uint32_t base = 0; base < n_items; base += blockDim.x) {
-        const uint32_t i = base + tid;
-        u64 ca = 0, cb = 0;
-        if (i < n_items) {
-            const ItemSpan sp = item_span(scene, items_ix, i, tile_y0, tile_y1, n_tx);
-            if (sp.rows) {
-                const uint32_t n_seg = sp.tag == PM_ITEM_FILL ? sp.n_points : (sp.tag == PM_ITEM_POLY ? sp.n_points - 1u : 0u);
-                ca = ((u64)(sp.rows * ((sp.t_hi - sp.t_lo + 32u) / 32u)) << 32) | n_seg;  // rows x 32-tile chunks
-                if (sp.tag == PM_ITEM_FILL || sp.tag == PM_ITEM_POLY) cb = (u64)sp.rows * pm_bd_stride(sp.t_hi - sp.t_lo + 1u);
-            }
-        }
-        const u64 ea = carry_a + block_scan_excl(ca, warp_excl, &total_a);
-        const u64 eb = carry_b + block_scan_excl(cb, warp_excl, &total_b);
-        if (i < n_items) {
-            plan_a[i] = ea;
-            plan_b[i] = eb;
-            PmItemInfo ii;
-            {
-                const ItemSpan spi = item_span(scene, items_ix, i, tile_y0, tile_y1, n_tx);
-                ii.t_lo = spi.t_lo; ii.t_hi = spi.t_hi; ii.r_lo = spi.r_lo; ii.rows = spi.rows; ii.bd_base = (uint32_t)eb;
-                ii.rgba = 0; ii.tag_flags = spi.tag; ii.w0 = 0;
-                // the item's colour as the fill kernels blend it: unpack_unorm4x8_srgb_to_half (metal:503, :541, :548)
-                // through the look-up table; Cmd_Circle paints opaque black (metal:491)
-                float4 paint = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
-                if (spi.tag == PM_ITEM_LINE || spi.tag == PM_ITEM_FILL || spi.tag == PM_ITEM_POLY) {
-                    const uint8_t *it = scene + items_ix + (size_t)i * PM_ITEM_SIZE;
-                    const uint32_t rgba = ld_u32(it + (spi.tag == PM_ITEM_POLY ? PM_POLY_RGBA : PM_FILL_RGBA));
-                    paint = make_float4(srgb_lut[rgba & 0xffu], srgb_lut[(rgba >> 8) & 0xffu], srgb_lut[(rgba >> 16) & 0xffu], srgb_lut[256u + (rgba >> 24)]);
-                    ii.rgba = rgba;
-                    if (spi.tag == PM_ITEM_FILL && (ld_u32(it + PM_FILL_FLAGS) & PM_FILL_EVEN_ODD) != 0) ii.tag_flags |= PM_INFO_EVEN_ODD;
-                    if (spi.tag == PM_ITEM_POLY) ii.w0 = pm_f2u(0.5f * ld_f32(it + PM_POLY_WIDTH));
-                    if (spi.tag == PM_ITEM_LINE) ii.w0 = pm_f2u(0.5f * ld_f32(it + PM_LINE_WIDTH));
-                }
-                item_info[i] = ii;
-                item_paint[i] = paint;
-            }
-            // second pass (row_info given): tabulate the item's (tile row, 32-tile chunk) units for k_row
-            if (row_info && ca != 0) {
-                const ItemSpan sp = item_span(scene, items_ix, i, tile_y0, tile_y1, n_tx);
-                const uint32_t chunks = (sp.t_hi - sp.t_lo + 32u) / 32u;
-                uint32_t u = (uint32_t)(ea >> 32);
-                for (uint32_t r = 0; r < sp.rows; r++)
-                    for (uint32_t c = 0; c < chunks && u < row_info_cap; c++, u++) {
-                        PmRowInfo ri;
-                        ri.item = i; ri.row_chunk = ((sp.r_lo + r) << 16) | c;
-                        ri.bd_row = (uint32_t)eb + r * pm_bd_stride(sp.t_hi - sp.t_lo + 1u);
-                        ri.t_lo_span = sp.t_lo | ((sp.t_hi - sp.t_lo + 1u) << 16);
-                        ri.rgba = ii.rgba; ri.tag_flags = ii.tag_flags; ri.w0 = ii.w0; ri.pad = 0;
-                        row_info[u] = ri;
-                    }
-            }
-        }
-        // a carry out of the low half (or 2^31 in either half) would corrupt the packed prefixes
-        if (((ea + ca) & 0x8000000080000000ull) != 0) result->error = 1;
-        __syncthreads();
-        if (tid == 0) { carry_a += total_a; carry_b += total_b; }
-        __syncthreads();
+    const uint32_t chunk = (n_items + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = tid * chunk < n_items ? tid * chunk : n_items;
+    const uint32_t hi = lo + chunk < n_items ? lo + chunk : n_items;
+    // the two halves of plan_a are summed apart: a carry out of the low half (or 2^31 in either half) would corrupt
+    // the packed prefixes and has to be reported, not wrapped
+    u64 s_lo = 0, s_hi = 0, s_b = 0;
+    for (uint32_t i = lo; i < hi; i++) { const u64 a = plan_a[i]; s_lo += a & 0xffffffffull; s_hi += a >> 32; s_b += plan_b[i]; }
+    u64 r_lo = block_scan_excl(s_lo, warp_excl, &total_lo);
+    u64 r_hi = block_scan_excl(s_hi, warp_excl, &total_hi);
+    u64 r_b = block_scan_excl(s_b, warp_excl, &total_b);
+    const bool bad = total_lo >= 0x80000000ull || total_hi >= 0x80000000ull;
+    for (uint32_t i = lo; i < hi && !bad; i++) {
+        const u64 a = plan_a[i], b = plan_b[i];
+        plan_a[i] = (r_hi << 32) | r_lo;
+        plan_b[i] = r_b;
+        r_lo += a & 0xffffffffull; r_hi += a >> 32; r_b += b;
     }
     if (tid == 0) {
-        plan_a[n_items] = carry_a;
-        plan_b[n_items] = carry_b;
-        result->n_segments = (uint32_t)carry_a;
-        result->n_rows = (uint32_t)(carry_a >> 32);
-        result->bd_words = carry_b;
+        if (bad) { result->error = 1; return; }
+        plan_a[n_items] = (total_hi << 32) | total_lo;
+        plan_b[n_items] = total_b;
+        result->n_segments = (uint32_t)total_lo;
+        result->n_rows = (uint32_t)total_hi;
+        result->bd_words = total_b;
     }
+}
+
+// largest i with (plan_a[i] >> 32) <= u: the item that owns k_row unit u (items without units share their successor's prefix)
+__device__ __forceinline__ uint32_t item_of_unit(const u64 *plan_a, uint32_t n_items, uint32_t u) {
+    uint32_t lo = 0, hi = n_items;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((uint32_t)(plan_a[mid] >> 32) <= u) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) k_plan_rows(uint32_t n_items, uint32_t n_units, const u64 *plan_a, const u64 *plan_b,
+                                                   const PmItemInfo *item_info, PmRowInfo *row_info) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    const uint32_t i = item_of_unit(plan_a, n_items, u);
+    const PmItemInfo ii = item_info[i];
+    const uint32_t span = ii.t_hi - ii.t_lo + 1u, chunks = (span + 31u) / 32u;
+    const uint32_t k = u - (uint32_t)(plan_a[i] >> 32), r = k / chunks, c = k - r * chunks;
+    PmRowInfo ri;
+    ri.item = i; ri.row_chunk = ((ii.r_lo + r) << 16) | c;
+    ri.bd_row = (uint32_t)plan_b[i] + r * pm_bd_stride(span);
+    ri.t_lo_span = ii.t_lo | (span << 16);
+    ri.rgba = ii.rgba; ri.tag_flags = ii.tag_flags; ri.w0 = ii.w0; ri.pad = 0;
+    row_info[u] = ri;
 }
 
 // One segment of a Fill / Poly item and the tile rows of the strip it can reach.  For a Fill the
@@ -645,10 +666,15 @@ void pm_launch_validate(const uint8_t *scene, uint32_t scene_len, uint32_t *err,
 }
 
 void pm_launch_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1,
-                    uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, PmItemInfo *item_info, PmRowInfo *row_info,
-                    uint32_t row_info_cap, const float *srgb_lut, float4 *item_paint, PmPlanResult *result, cudaStream_t s) {
-    k_plan<<<1, 1024, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, plan_b, item_info, row_info, row_info_cap, srgb_lut,
-                              item_paint, result);
+                    uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, PmItemInfo *item_info,
+                    const float *srgb_lut, float4 *item_paint, PmPlanResult *result, cudaStream_t s) {
+    if (n_items) k_plan_count<<<(n_items + 255) / 256, 256, 0, s>>>(scene, n_items, items_ix, tile_y0, tile_y1, n_tx, plan_a, plan_b, item_info, srgb_lut, item_paint);
+    k_plan_scan<<<1, 1024, 0, s>>>(n_items, plan_a, plan_b, result);
+}
+
+void pm_launch_plan_rows(uint32_t n_items, uint32_t n_units, const unsigned long long *plan_a, const unsigned long long *plan_b,
+                         const PmItemInfo *item_info, PmRowInfo *row_info, cudaStream_t s) {
+    if (n_units) k_plan_rows<<<(n_units + 255) / 256, 256, 0, s>>>(n_items, n_units, plan_a, plan_b, item_info, row_info);
 }
 
 void pm_launch_pieces_count(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,

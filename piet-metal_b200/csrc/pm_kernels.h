@@ -64,10 +64,10 @@ struct alignas(16) PmSegInfo {
     float sx, sy, ex, ey; uint32_t item, k; float hw; uint32_t tag;
     uint32_t t_lo, t_hi, r_lo, bd_base;  // copied from the segment's item (PmItemInfo): one dependent load less in k_seg
 };
-// PmItemInfo: everything k_seg and k_row need about an item in two 16-byte loads -- tile span of its bbox inside the
-// strip, first word of its backdrop scratch (below 2^31, checked by the plan), its colour (rgba8 as encoded), its tag
-// with the even-odd bit (bit 8), and w0 = the bits of half its stroke width (Poly / Line).
-struct alignas(16) PmItemInfo { uint32_t t_lo, t_hi, r_lo, rows; uint32_t bd_base, rgba, tag_flags, w0; };
+// PmItemInfo (plan time only: copied into PmSegInfo / PmRowInfo, which is what the frame's kernels read): tile span
+// of the item's bbox inside the strip, its colour (rgba8 as encoded), its tag with the even-odd bit (bit 8), and
+// w0 = the bits of half its stroke width (Poly / Line).
+struct alignas(16) PmItemInfo { uint32_t t_lo, t_hi, r_lo, rows; uint32_t bd_base /* unused */, rgba, tag_flags, w0; };
 #define PM_INFO_EVEN_ODD 0x100u
 
 // One k_row unit = (item, tile row, chunk of 32 tiles), with what k_row needs of the item copied in (one dependent load
@@ -88,7 +88,6 @@ struct PmFrameArgs {
     const unsigned long long *plan_b;  // per item: backdrop-scratch words before it
     const uint2 *piece_info;           // per k_seg thread: segment, flags | tile row << 15 | tile column (k_pieces_*)
     const PmSegInfo *seg_info;         // per segment (k_pieces_*)
-    const PmItemInfo *item_info;       // per item (k_plan)
     const PmRowInfo *row_info;         // per k_row unit (k_plan): everything the warp needs in one 32-byte load
     uint32_t n_segments;        // segments of the Fill / Poly items that touch the strip
     uint32_t n_pieces;          // k_seg threads
@@ -142,10 +141,13 @@ struct PmPlanResult { uint32_t n_segments; uint32_t n_rows; unsigned long long b
 // Validates an encoded scene on the device.  *err (device) becomes non-zero if a ref or count is
 // out of bounds or a coordinate is not finite.
 void pm_launch_validate(const uint8_t *scene, uint32_t scene_len, uint32_t *err, cudaStream_t s);
-// Fills plan_a / plan_b [0..n_items] and result (device) for the given strip.
+// Fills plan_a / plan_b [0..n_items], the item tables and result (device) for the given strip; then, once the host
+// knows result->n_rows (and has made room), the k_row unit table.
 void pm_launch_plan(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1,
-                    uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, PmItemInfo *item_info, PmRowInfo *row_info,
-                    uint32_t row_info_cap, const float *srgb_lut, float4 *item_paint, PmPlanResult *result, cudaStream_t s);
+                    uint32_t n_tx, unsigned long long *plan_a, unsigned long long *plan_b, PmItemInfo *item_info,
+                    const float *srgb_lut, float4 *item_paint, PmPlanResult *result, cudaStream_t s);
+void pm_launch_plan_rows(uint32_t n_items, uint32_t n_units, const unsigned long long *plan_a, const unsigned long long *plan_b,
+                         const PmItemInfo *item_info, PmRowInfo *row_info, cudaStream_t s);
 // The k_seg work list: count + prefix (result->n_pieces, piece_cnt becomes the per-segment offset), then fill.
 void pm_launch_pieces_count(const uint8_t *scene, uint32_t n_items, uint32_t items_ix, uint32_t tile_y0, uint32_t tile_y1, uint32_t n_tx,
                             const unsigned long long *plan_a, const unsigned long long *plan_b, uint32_t n_segments, PmSegInfo *seg_info,

@@ -173,20 +173,22 @@ int alloc_surface(pm_renderer *r) {
 int run_plan_timed(pm_renderer *r);
 int run_plan(pm_renderer *r) {
     PmPlanResult res;
-    // the k_row unit table is filled in the same pass that sizes it; a second pass only if it was too small
-    for (int pass = 0; pass < 2; pass++) {
-        PM_CUDA(cudaMemsetAsync(r->dev_plan, 0, sizeof(PmPlanResult), r->stream));
-        pm_launch_plan(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, r->plan_b, r->item_info,
-                       r->row_info, (uint32_t)r->row_info_cap, r->lut, r->item_paint, r->dev_plan, r->stream);
+    PM_CUDA(cudaMemsetAsync(r->dev_plan, 0, sizeof(PmPlanResult), r->stream));
+    pm_launch_plan(r->scene, r->n_items, r->items_ix, r->tile_y0, r->tile_y1, r->n_tx, r->plan_a, r->plan_b, r->item_info,
+                   r->lut, r->item_paint, r->dev_plan, r->stream);
+    PM_CUDA(cudaGetLastError());
+    PM_CUDA(cudaMemcpyAsync(&res, r->dev_plan, sizeof res, cudaMemcpyDeviceToHost, r->stream));
+    PM_CUDA(cudaStreamSynchronize(r->stream));
+    if (!res.error) {  // the k_row unit table, now that its size is known
+        if ((size_t)res.n_rows > r->row_info_cap) {
+            if (r->row_info) PM_CUDA(cudaFree(r->row_info));
+            r->row_info = nullptr;
+            r->row_info_cap = 0;
+            PM_CUDA(cudaMalloc(&r->row_info, ((size_t)res.n_rows + res.n_rows / 8 + 1) * sizeof(PmRowInfo)));
+            r->row_info_cap = (size_t)res.n_rows + res.n_rows / 8 + 1;
+        }
+        pm_launch_plan_rows(r->n_items, res.n_rows, r->plan_a, r->plan_b, r->item_info, r->row_info, r->stream);
         PM_CUDA(cudaGetLastError());
-        PM_CUDA(cudaMemcpyAsync(&res, r->dev_plan, sizeof res, cudaMemcpyDeviceToHost, r->stream));
-        PM_CUDA(cudaStreamSynchronize(r->stream));
-        if (res.error || (size_t)res.n_rows <= r->row_info_cap) break;
-        if (r->row_info) PM_CUDA(cudaFree(r->row_info));
-        r->row_info = nullptr;
-        r->row_info_cap = 0;
-        PM_CUDA(cudaMalloc(&r->row_info, ((size_t)res.n_rows + res.n_rows / 8 + 1) * sizeof(PmRowInfo)));
-        r->row_info_cap = (size_t)res.n_rows + res.n_rows / 8 + 1;
     }
     if (res.error) { g_last_error = "scene has more than 2^31 segments or (item, tile row) pairs"; return PM_ERR_INVALID_ARG; }
     if (res.bd_words > (1ull << 31)) { g_last_error = "item bounding boxes cover more than 2^31 tiles in total"; return PM_ERR_NOMEM; }
@@ -286,7 +288,7 @@ int enqueue_frame(pm_renderer *r, bool debug_f32) {
     memset(&a, 0, sizeof a);
     a.scene = r->scene; a.scene_len = r->scene_len; a.n_items = r->n_items; a.items_ix = r->items_ix;
     a.plan_a = r->plan_a; a.plan_b = r->plan_b; a.n_segments = r->n_segments; a.n_row_units = r->n_row_units; a.bd = r->bd + (size_t)(r->frame & 1) * r->bd_words; a.bd_next = r->bd + (size_t)((r->frame + 1) & 1) * r->bd_words; a.bd_quads = r->bd_words / 4;
-    a.piece_info = r->piece_info; a.seg_info = r->seg_info; a.item_info = r->item_info; a.n_pieces = r->n_pieces; a.row_info = r->row_info;
+    a.piece_info = r->piece_info; a.seg_info = r->seg_info; a.n_pieces = r->n_pieces; a.row_info = r->row_info;
     a.tile_y0 = r->tile_y0; a.n_rows = r->tile_y1 - r->tile_y0; a.n_tx = r->n_tx;
     a.occ = r->occ; a.cnt = r->cnt; a.ovf = r->ovf;
     a.pool = r->pool; a.overflow_cap = r->overflow_cap; a.complex_list = r->complex_list;
