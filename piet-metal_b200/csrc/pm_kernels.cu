@@ -515,15 +515,28 @@ __global__ void __launch_bounds__(PM_SEG_THREADS, PM_SEG_CTAS * 256 / PM_SEG_THR
 #ifndef PM_ROW_WARPS
 #define PM_ROW_WARPS 8
 #endif
-__global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) {
+#ifndef PM_ROW_PERSISTENT
+#define PM_ROW_PERSISTENT 1  // at most one resident wave of CTAs, every warp walks its units with the next unit's entry in flight
+#endif
+#ifndef PM_ROW_CTAS
+#define PM_ROW_CTAS (2048 / (PM_ROW_WARPS * 32))  // resident CTAs per SM k_row is compiled for
+#endif
+__global__ void __launch_bounds__(PM_ROW_WARPS * 32, PM_ROW_CTAS) k_row(const PmFrameArgs A) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t unit = blockIdx.x * PM_ROW_WARPS + warp;
     CtaTimer timer(A.debug, 1u << 18);
     pm_grid_launch_dependents();
     pm_grid_wait();  // k_seg has finished
+    const uint32_t stride = gridDim.x * PM_ROW_WARPS;
+    uint32_t unit = blockIdx.x * PM_ROW_WARPS + warp;
     if (unit >= A.n_row_units) return;
-    const uint4 *rp4 = reinterpret_cast<const uint4 *>(&A.row_info[unit]);  // tabulated by k_plan
-    const uint4 r0 = rp4[0], r1 = rp4[1];  // item, row << 16 | chunk, bd_row, t_lo | span << 16 || rgba, tag_flags, w0
+    // (a unit is a chain of dependent accesses -- its entry, the backdrop words, the slot claim, the record -- and the
+    // kernel is as long as the chains it runs one after the other: the next unit's entry is requested before this
+    // unit's work begins)
+    uint4 n0 = reinterpret_cast<const uint4 *>(&A.row_info[unit])[0], n1 = reinterpret_cast<const uint4 *>(&A.row_info[unit])[1];
+  for (;;) {
+    const uint4 r0 = n0, r1 = n1;  // item, row << 16 | chunk, bd_row, t_lo | span << 16 || rgba, tag_flags, w0  (k_plan_rows)
+    const uint32_t next = unit + stride;
+    if (next < A.n_row_units) { n0 = reinterpret_cast<const uint4 *>(&A.row_info[next])[0]; n1 = reinterpret_cast<const uint4 *>(&A.row_info[next])[1]; }
     const uint32_t item = r0.x;
     const uint32_t tag = r1.y & 0xffu, rgba = r1.x;
     const uint8_t *it = A.scene + A.items_ix + (size_t)item * PM_ITEM_SIZE;
@@ -587,6 +600,9 @@ __global__ void __launch_bounds__(PM_ROW_WARPS * 32) k_row(const PmFrameArgs A) 
         const uint32_t b_lo = (uint32_t)bb.x0 | ((uint32_t)bb.y0 << 16), b_hi = (uint32_t)bb.x1 | ((uint32_t)bb.y1 << 16);
         if (j < span) sink.trailer(t_lo + j, PM_REC_CIRCLE, 0, b_lo, b_hi);
     }
+    if (next >= A.n_row_units) break;
+    unit = next;
+  }
 }
 
 // One thread per tile, after binning: the fill kernels' work lists from the FINAL record counts -- four disjoint
@@ -711,7 +727,11 @@ cudaError_t pm_launch_frame(const PmFrameArgs &a, int sm_count, cudaEvent_t mid,
     launched++;
     // (k_row runs even without units when the launches overlap: the chain of grid dependencies must not skip a kernel)
     if (a.n_row_units || overlap) {
-        const uint32_t grid_row = (a.n_row_units + PM_ROW_WARPS - 1) / PM_ROW_WARPS;
+        uint32_t grid_row = (a.n_row_units + PM_ROW_WARPS - 1) / PM_ROW_WARPS;
+#if PM_ROW_PERSISTENT
+        const uint32_t row_wave = (uint32_t)sm_count * PM_ROW_CTAS;  // one resident wave
+        if (grid_row > row_wave) grid_row = row_wave;
+#endif
         if ((e = launch_overlapped(k_row, dim3(grid_row ? grid_row : 1), dim3(PM_ROW_WARPS * 32), overlap, s, a)) != cudaSuccess) return e;
         launched++;
     }
